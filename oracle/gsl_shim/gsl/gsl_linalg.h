@@ -1,0 +1,2 @@
+/* oracle GSL shim (test infrastructure): forwards to gsl_shim.h */
+#include "../gsl_shim.h"

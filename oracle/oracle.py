@@ -1,0 +1,218 @@
+"""ctypes front-ends for the two CPU checkers -- TEST INFRASTRUCTURE ONLY.
+
+* ``StructuredOracle``  -> oracle/libekforacle.so  (oracle/ekf_oracle.cpp), the runtime-capacity
+  restatement of slam_ros/Robot.cpp:126-943 (full, non-symmetrised covariance, GSL loop order).
+* ``LiteralReference``  -> oracle/_ref/libslamref.so, the reference's own Robot.cpp (Q1-patched on a
+  pipe) compiled over oracle/gsl_shim; fixed LINESIZE=100 (Robot.h:13).
+
+Neither may be used by the product path (slam_ros_b200/); see the header of ekf_oracle.cpp.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "libekforacle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libslamref.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(quiet=True):
+    """Compile the structured oracle and, where /root/reference exists, the literal reference."""
+    out = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+def have_literal():
+    return os.path.exists(_REF_SO)
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+class StructuredOracle:
+    def __init__(self, capacity_lines, gate=0.4, encoder_noise=0.024, reset_headroom=10, threads=1):
+        if not os.path.exists(_ORACLE_SO):
+            build()
+        L = self._lib = C.CDLL(_ORACLE_SO)
+        L.ekfo_create.restype = C.c_void_p
+        L.ekfo_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int]
+        L.ekfo_y_ptr.restype = _dp
+        L.ekfo_P_ptr.restype = _dp
+        for f in ("ekfo_destroy", "ekfo_set_threads", "ekfo_set_pose", "ekfo_predict", "ekfo_associate",
+                  "ekfo_gate_pair", "ekfo_update", "ekfo_last_gain", "ekfo_scan", "ekfo_localize", "ekfo_n",
+                  "ekfo_lines", "ekfo_y_ptr", "ekfo_P_ptr", "ekfo_get_pose", "ekfo_get_xpre", "ekfo_stats",
+                  "ekfo_get_live", "ekfo_get_ellipse", "ekfo_get_threads"):
+            getattr(L, f).argtypes = None
+        self._h = C.c_void_p(L.ekfo_create(int(capacity_lines), float(gate), float(encoder_noise), int(reset_headroom)))
+        if not self._h:
+            raise MemoryError("ekfo_create failed")
+        L.ekfo_set_threads(self._h, C.c_int(int(threads)))
+        self.capacity = int(capacity_lines)
+        self.n = 3 + 2 * self.capacity
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ekfo_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def threads(self):
+        return int(self._lib.ekfo_get_threads(self._h))
+
+    @property
+    def lines(self):
+        return int(self._lib.ekfo_lines(self._h))
+
+    @property
+    def pose(self):
+        p = np.zeros(3)
+        self._lib.ekfo_get_pose(self._h, p.ctypes.data_as(_dp))
+        return p
+
+    @property
+    def x_pre(self):
+        p = np.zeros(3)
+        self._lib.ekfo_get_xpre(self._h, p.ctypes.data_as(_dp))
+        return p
+
+    def set_pose(self, pose):
+        a, p = _d(pose)
+        self._lib.ekfo_set_pose(self._h, p)
+
+    def y_full(self):
+        return np.ctypeslib.as_array(self._lib.ekfo_y_ptr(self._h), shape=(self.n,)).copy()
+
+    def P_full(self):
+        return np.ctypeslib.as_array(self._lib.ekfo_P_ptr(self._h), shape=(self.n, self.n)).copy()
+
+    def P_view(self):
+        return np.ctypeslib.as_array(self._lib.ekfo_P_ptr(self._h), shape=(self.n, self.n))
+
+    def live(self):
+        nl = 3 + 2 * self.lines
+        y = np.zeros(nl)
+        P = np.zeros((nl, nl))
+        self._lib.ekfo_get_live(self._h, y.ctypes.data_as(_dp), P.ctypes.data_as(_dp))
+        return y, P
+
+    def predict(self, u):
+        a, p = _d(u)
+        x = np.zeros(3)
+        self._lib.ekfo_predict(self._h, p, x.ctypes.data_as(_dp))
+        return x
+
+    def associate(self, z, R):
+        za, zp = _d(z)
+        Ra, Rp = _d(R)
+        innov = np.zeros(2)
+        d2 = C.c_double(0)
+        j = int(self._lib.ekfo_associate(self._h, zp, Rp, innov.ctypes.data_as(_dp), C.byref(d2)))
+        return j, innov, d2.value
+
+    def gate_pair(self, j, z, R):
+        za, zp = _d(z)
+        Ra, Rp = _d(R)
+        S = np.zeros(4); Si = np.zeros(4); v = np.zeros(2); d2 = C.c_double(0)
+        self._lib.ekfo_gate_pair(self._h, C.c_int(int(j)), zp, Rp, S.ctypes.data_as(_dp), Si.ctypes.data_as(_dp),
+                                 v.ctypes.data_as(_dp), C.byref(d2))
+        return S.reshape(2, 2), Si.reshape(2, 2), v, d2.value
+
+    def update(self, j, z, R):
+        za, zp = _d(z)
+        Ra, Rp = _d(R)
+        self._lib.ekfo_update(self._h, C.c_int(int(j)), zp, Rp)
+
+    def last_gain(self):
+        K = np.zeros((self.n, 2)); KS = np.zeros((self.n, 2))
+        self._lib.ekfo_last_gain(self._h, K.ctypes.data_as(_dp), KS.ctypes.data_as(_dp))
+        return K, KS
+
+    def scan(self, u, z, R):
+        """One Robot::localize with odometry u; returns (status, j_out)."""
+        ua, up = _d(u)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 4)
+        m = z.shape[0]
+        j = np.full(max(m, 1), -1, dtype=np.int32)
+        st = self._lib.ekfo_scan(self._h, up, C.c_int(m), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp),
+                                 j.ctypes.data_as(_ip))
+        return int(st), j[:m]
+
+    def localize(self, z, R, encoder):
+        ea, ep = _d(encoder)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 4)
+        m = z.shape[0]
+        j = np.full(max(m, 1), -1, dtype=np.int32)
+        st = self._lib.ekfo_localize(self._h, C.c_int(m), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp), ep,
+                                     j.ctypes.data_as(_ip))
+        return int(st), j[:m]
+
+    def stats(self):
+        mm = C.c_double(0); g = C.c_longlong(0); mt = C.c_longlong(0); rs = C.c_longlong(0)
+        self._lib.ekfo_stats(self._h, C.byref(mm), C.byref(g), C.byref(mt), C.byref(rs))
+        return {"min_margin": mm.value, "gates": g.value, "matches": mt.value, "resets": rs.value}
+
+    def get_ellipse(self):
+        ax = (C.c_float * 2)(); ang = C.c_float(0)
+        ok = self._lib.ekfo_get_ellipse(self._h, ax, C.byref(ang))
+        return bool(ok), (float(ax[0]), float(ax[1])), float(ang.value)
+
+
+class LiteralReference:
+    """The reference's own Robot (LINESIZE = 100), driven through oracle/ref_harness.cpp."""
+
+    def __init__(self):
+        if not os.path.exists(_REF_SO):
+            build()
+        if not os.path.exists(_REF_SO):
+            raise FileNotFoundError(_REF_SO + " (needs /root/reference to build)")
+        L = self._lib = C.CDLL(_REF_SO)
+        L.ref_create.restype = C.c_void_p
+        L.ref_gate.restype = C.c_double
+        L.ref_encoder_noise.restype = C.c_double
+        L.ref_range_errors.restype = C.c_ulong
+        L.ref_badlen_errors.restype = C.c_ulong
+        self._h = C.c_void_p(L.ref_create())
+        self.capacity = int(L.ref_linesize())
+        self.n = int(L.ref_slamsize())
+        self.gate = float(L.ref_gate())
+        self.encoder_noise = float(L.ref_encoder_noise())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ref_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def localize(self, z, R, encoder):
+        ea, ep = _d(encoder)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 4)
+        self._lib.ref_localize(self._h, C.c_int(z.shape[0]), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp), ep)
+
+    def state(self):
+        y = np.zeros(self.n); P = np.zeros((self.n, self.n)); L = C.c_int(0); pose = np.zeros(3)
+        self._lib.ref_get(self._h, y.ctypes.data_as(_dp), P.ctypes.data_as(_dp), C.byref(L), pose.ctypes.data_as(_dp))
+        return y, P, int(L.value), pose
+
+    def get_ellipse(self):
+        ax = (C.c_float * 2)(); ang = C.c_float(0)
+        ok = self._lib.ref_get_ellipse(self._h, ax, C.byref(ang))
+        return bool(ok), (float(ax[0]), float(ax[1])), float(ang.value)
+
+    def range_errors(self):
+        return int(self._lib.ref_range_errors())

@@ -1,0 +1,73 @@
+/* ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * C-ABI handle around the reference's own `Robot` class (slam_ros/Robot.h:21-77) so that the
+ * UNMODIFIED reference sources -- compiled where they lie under /root/reference by
+ * oracle/Makefile into oracle/_ref/libslamref.so -- can be driven from the tests and timed by
+ * bench.py.  No reference code is copied here: this file only calls the reference's public
+ * interface (ctor, localize, getEllipse, xPos/yPos/thetaPos, P_t0) and, for the parity tap,
+ * reads its private y[] / savedLineCount (Robot.h:26-28).
+ *
+ * Harness obligations taken from SURVEY.md section 0.1:
+ *   Q2  rot must be a valid float[2] (Robot.cpp:132-134 dereferences it unconditionally);
+ *   Q3  the object must live on zeroed storage (ctor leaves y, savedLineCount, P_t0 unset);
+ *   Q14 the method prints ~60 lines per call: std::cout is put in a failed state so every
+ *       insertion is a no-op (cheaper for the reference than writing to /dev/null).
+ */
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <new>
+#include <vector>
+#include <array>
+#include <string>
+#include <fstream>
+#include <iomanip>
+#include <algorithm>
+#include <cmath>
+#include <random>
+#define private public
+#include "Robot.h"
+#undef private
+
+extern "C" {
+
+void* ref_create(void) {
+  void* mem = std::calloc(1, sizeof(Robot));
+  if (!mem) return 0;
+  std::cout.setstate(std::ios_base::failbit);
+  return new (mem) Robot(0, 0, 0);
+}
+void ref_destroy(void* h) { if (!h) return; ((Robot*)h)->~Robot(); std::free(h); }
+int ref_linesize(void) { return LINESIZE; }
+int ref_slamsize(void) { return SLAMSIZE; }
+double ref_gate(void) { return MAHALANOBIS; }
+double ref_encoder_noise(void) { return ENCODERNOISE; }
+
+/* one Robot::localize call; z = m x (alfa, r), R = m x 4 (row-major C_AR), encoder = 3 doubles */
+int ref_localize(void* h, int m, const double* z, const double* R, const double* encoder) {
+  Robot* rb = (Robot*)h;
+  std::vector<line> lines((size_t)m);
+  for (int i = 0; i < m; ++i) {
+    lines[i].alfa = z[2 * i];
+    lines[i].r = z[2 * i + 1];
+    lines[i].C_AR = gsl_matrix_alloc(2, 2);
+    for (int t = 0; t < 4; ++t) lines[i].C_AR->data[t] = R[4 * i + t];
+  }
+  float rot[2] = {0.f, 0.f};
+  rb->localize(lines, rot, encoder);
+  for (int i = 0; i < m; ++i) gsl_matrix_free(lines[i].C_AR);
+  rb->lineIntervals.data.clear();
+  return 0;
+}
+void ref_get(void* h, double* y, double* P, int* L, double* pose) {
+  Robot* rb = (Robot*)h;
+  if (y) std::memcpy(y, rb->y, sizeof(double) * SLAMSIZE);
+  if (P) std::memcpy(P, rb->P_t0, sizeof(double) * SLAMSIZE * SLAMSIZE);
+  if (L) *L = rb->savedLineCount;
+  if (pose) { pose[0] = rb->xPos; pose[1] = rb->yPos; pose[2] = rb->thetaPos; }
+}
+int ref_get_ellipse(void* h, float axii[2], float* angle) { return ((Robot*)h)->getEllipse(axii, *angle) ? 1 : 0; }
+unsigned long ref_range_errors(void) { return gsl_shim_stats().range_errors; }
+unsigned long ref_badlen_errors(void) { return gsl_shim_stats().badlen_errors; }
+
+}
