@@ -87,7 +87,7 @@ int inv2x2_lu(const double S[4], double Si[4]) {
     a[2] = l;
     a[3] = a[3] - l * a[1];
   }
-  if (a[0] == 0.0 || a[3] == 0.0) return 1;
+  if (a[0] == 0.0 || a[3] == 0.0) { Si[0] = Si[1] = Si[2] = Si[3] = 0.0; return 1; }   /* S_inv stays {0,0,0,0} (Robot.cpp:443) */
   for (int col = 0; col < 2; ++col) {
     const double e[2] = {col == 0 ? 1.0 : 0.0, col == 1 ? 1.0 : 0.0};
     double x0 = e[p0], x1 = e[p1];
@@ -430,6 +430,9 @@ void ekfo_update(void* h, int j, const double z[2], const double R[4]) {
   o->matched.push_back(j); o->matches++; o->total_matches++;
   apply_update(o, j, G);
 }
+/* extraLines.push_back(lines[line_idx]) and the end-of-scan block, for tests that drive the primitives */
+void ekfo_queue(void* h, int line_idx) { ((Oracle*)h)->extra.push_back(line_idx); }
+int ekfo_end(void* h, int m, const double* z, const double* R) { return end_scan((Oracle*)h, m, z, R); }
 void ekfo_last_gain(void* h, double* K, double* KS) {   /* n x 2 each, of the most recent update */
   Oracle* o = (Oracle*)h;
   std::memcpy(K, o->K.data(), sizeof(double) * 2 * o->n); std::memcpy(KS, o->KS.data(), sizeof(double) * 2 * o->n);

@@ -49,7 +49,7 @@ class StructuredOracle:
         L.ekfo_y_ptr.restype = _dp
         L.ekfo_P_ptr.restype = _dp
         for f in ("ekfo_destroy", "ekfo_set_threads", "ekfo_set_pose", "ekfo_predict", "ekfo_associate",
-                  "ekfo_gate_pair", "ekfo_update", "ekfo_last_gain", "ekfo_scan", "ekfo_localize", "ekfo_n",
+                  "ekfo_gate_pair", "ekfo_update", "ekfo_last_gain", "ekfo_queue", "ekfo_end", "ekfo_scan", "ekfo_localize", "ekfo_n",
                   "ekfo_lines", "ekfo_y_ptr", "ekfo_P_ptr", "ekfo_get_pose", "ekfo_get_xpre", "ekfo_stats",
                   "ekfo_get_live", "ekfo_get_ellipse", "ekfo_get_threads"):
             getattr(L, f).argtypes = None
@@ -133,6 +133,14 @@ class StructuredOracle:
         za, zp = _d(z)
         Ra, Rp = _d(R)
         self._lib.ekfo_update(self._h, C.c_int(int(j)), zp, Rp)
+
+    def queue(self, line_idx):
+        self._lib.ekfo_queue(self._h, C.c_int(int(line_idx)))
+
+    def end(self, z, R):
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 4)
+        return int(self._lib.ekfo_end(self._h, C.c_int(z.shape[0]), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp)))
 
     def last_gain(self):
         K = np.zeros((self.n, 2)); KS = np.zeros((self.n, 2))

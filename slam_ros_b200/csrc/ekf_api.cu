@@ -1,0 +1,749 @@
+/* ekf_api.cu -- the extern "C" boundary of libekfcuda (include/ekf.h): context, HBM residency,
+ * stream ordering, the per-scan launch sequence, measurement taps and the NCCL exchange of the
+ * row-sharded mode.  No arithmetic of the filter lives here -- it is all in ekf_kernels.cu.
+ */
+#include "../../include/ekf.h"
+#include "ekf_internal.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+/* ---- NCCL, bound at run time so that the library shares whatever libnccl the host process already
+ *      loaded (torch bundles its own) and has no link-time dependency in the single-GPU case ---- */
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* handle;
+  int (*GetUniqueId)(ncclUniqueId*);
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  int (*CommDestroy)(ncclComm_t);
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(int);
+};
+const int kNcclFloat64 = 8, kNcclSum = 0;
+
+NcclApi* nccl_api() {
+  static NcclApi api = {0, 0, 0, 0, 0, 0};
+  static int tried = 0;
+  if (!tried) {
+    tried = 1;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", 0};
+    for (int i = 0; names[i] && !api.handle; ++i) api.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) {
+      api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.handle, "ncclCommDestroy");
+      api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) api.handle = 0;
+    }
+  }
+  return api.handle ? &api : 0;
+}
+}  // namespace
+
+struct ekf_ctx {
+  ekf_config cfg;
+  EkfGeom g;
+  EkfBuffers b;
+  cudaStream_t stream;
+  /* per-scan inputs owned by the ctx (host path and step-wise path) */
+  int max_lines;
+  double* d_in;        /* [u(3) | x_t0(3) | z(2*max_lines) | R(4*max_lines)] */
+  double* h_in;        /* pinned mirror */
+  int* h_jout;         /* pinned */
+  EkfDevState* h_st;   /* pinned */
+  /* host-side view of the device state */
+  int L_ub;            /* upper bound of savedLineCount */
+  int pend_ub;         /* upper bound of the pending-term count */
+  int scan_open;
+  int cursor;          /* lines consumed by the open step-wise scan */
+  /* measurement */
+  int prof;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used;
+  std::vector<double> ev_bytes;
+  long long launches;
+  /* sharded */
+  ncclComm_t comm;
+  /* staging for download / upload / stats */
+  double* d_stage; size_t stage_elems;
+  double* d_partials; double* d_out3;
+  char err[256];
+};
+
+namespace {
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return EKF_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+const size_t kStageElems = (size_t)8 << 20;   /* 64 MiB staging for download/upload */
+
+double* in_u(ekf_ctx* c) { return c->d_in; }
+double* in_x(ekf_ctx* c) { return c->d_in + 3; }
+double* in_z(ekf_ctx* c) { return c->d_in + 6; }
+double* in_R(ekf_ctx* c) { return c->d_in + 6 + 2 * (size_t)c->max_lines; }
+
+int free_line_tables(ekf_ctx* ctx) {
+  cudaFree(ctx->b.jbest); cudaFree(ctx->b.jout); cudaFree(ctx->b.pidx); cudaFree(ctx->b.eidx);
+  cudaFree(ctx->b.ext); cudaFree(ctx->b.ext_cs); cudaFree(ctx->d_in);
+  cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_jout);
+  ctx->b.jbest = ctx->b.jout = ctx->b.pidx = ctx->b.eidx = ctx->b.ext = 0; ctx->b.ext_cs = 0; ctx->d_in = 0;
+  ctx->h_in = 0; ctx->h_jout = 0;
+  return 0;
+}
+
+/* (re)allocate everything sized by the number of lines in a scan; only legal between scans */
+int ensure_lines(ekf_ctx* ctx, int m) {
+  if (m <= ctx->max_lines) return EKF_OK;
+  if (ctx->scan_open && ctx->cursor > 0) {
+    snprintf(ctx->err, sizeof ctx->err, "scan has more than %d lines; raise it by calling ekf_scan once with m lines", ctx->max_lines);
+    return EKF_EINVAL;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_line_tables(ctx);
+  int cap = ctx->max_lines > 0 ? ctx->max_lines : 64;
+  while (cap < m) cap *= 2;
+  ctx->max_lines = cap;
+  const size_t n1 = (size_t)cap + 1;
+  CU(cudaMalloc(&ctx->b.jbest, n1 * sizeof(int)));
+  CU(cudaMalloc(&ctx->b.jout, n1 * sizeof(int)));
+  CU(cudaMalloc(&ctx->b.pidx, n1 * sizeof(int)));
+  CU(cudaMalloc(&ctx->b.eidx, n1 * sizeof(int)));
+  CU(cudaMalloc(&ctx->b.ext, n1 * sizeof(int)));
+  CU(cudaMalloc(&ctx->b.ext_cs, 2 * n1 * sizeof(double)));
+  CU(cudaMalloc(&ctx->d_in, (6 + 6 * (size_t)cap) * sizeof(double)));
+  CU(cudaMallocHost(&ctx->h_in, (6 + 6 * (size_t)cap) * sizeof(double)));
+  CU(cudaMallocHost(&ctx->h_jout, n1 * sizeof(int)));
+  CU(cudaMemsetAsync(ctx->b.pidx, 0, n1 * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.eidx, 0, n1 * sizeof(int), ctx->stream));
+  return EKF_OK;
+}
+
+int sweep_now(ekf_ctx* ctx, int np_ub) {
+  if (np_ub <= 0) return EKF_OK;
+  cudaEvent_t e0 = 0, e1 = 0;
+  if (ctx->prof) {
+    if (ctx->ev_used + 2 > ctx->ev.size()) {
+      for (int i = 0; i < 64; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e); }
+    }
+    e0 = ctx->ev[ctx->ev_used]; e1 = ctx->ev[ctx->ev_used + 1];
+    CU(cudaEventRecord(e0, ctx->stream));
+  }
+  CU(ekf_launch_sweep(ctx->g, ctx->b, 0, np_ub, ctx->L_ub, ctx->stream));
+  ctx->launches++;
+  if (ctx->prof) {
+    CU(cudaEventRecord(e1, ctx->stream));
+    ctx->ev_used += 2;
+    ctx->ev_bytes.push_back((double)np_ub);   /* resolved to bytes at read time with the true n */
+  }
+  return EKF_OK;
+}
+
+/* exchange of the H-column slices in the row-sharded mode: every element of colA|colB has exactly one
+ * non-zero contributor, so the sum is an exact gather */
+int exchange_slices(ekf_ctx* ctx) {
+  NcclApi* api = nccl_api();
+  if (!api || !ctx->comm) { snprintf(ctx->err, sizeof ctx->err, "NCCL not available"); return EKF_ENCCL; }
+  const int rc = api->AllReduce(ctx->b.colA, ctx->b.colA, 2 * (size_t)ctx->g.ld, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+  if (rc != 0) {
+    snprintf(ctx->err, sizeof ctx->err, "ncclAllReduce: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+    return EKF_ENCCL;
+  }
+  return EKF_OK;
+}
+
+/* gain + hot update for line `line` (j_sel: >= 0 explicit landmark, -1 association winner) */
+int enqueue_update(ekf_ctx* ctx, const double* d_z, const double* d_R, int line, int j_sel) {
+  if (ctx->pend_ub >= ctx->cfg.max_batch) {       /* fold what is pending before the list overflows */
+    int rc = sweep_now(ctx, ctx->pend_ub);
+    if (rc) return rc;
+    CU(ekf_launch_flush_done(ctx->b, line, ctx->stream));
+    ctx->launches++;
+    ctx->pend_ub = 0;
+  }
+  if (ctx->g.world == 1) {
+    CU(ekf_launch_gain(ctx->g, ctx->b, d_z, d_R, line, j_sel, 0, ctx->L_ub, ctx->cfg.max_batch, ctx->stream));
+    ctx->launches++;
+  } else {
+    CU(ekf_launch_gain(ctx->g, ctx->b, d_z, d_R, line, j_sel, 1, ctx->L_ub, ctx->cfg.max_batch, ctx->stream));
+    int rc = exchange_slices(ctx);
+    if (rc) return rc;
+    CU(ekf_launch_gain(ctx->g, ctx->b, d_z, d_R, line, j_sel, 2, ctx->L_ub, ctx->cfg.max_batch, ctx->stream));
+    ctx->launches += 2;
+  }
+  CU(ekf_launch_apply(ctx->g, ctx->b, line, j_sel, ctx->L_ub, ctx->stream));
+  ctx->launches++;
+  ctx->pend_ub++;
+  if (ctx->cfg.flags & EKF_FLAG_EAGER_SWEEP) {
+    int rc = sweep_now(ctx, ctx->pend_ub);
+    if (rc) return rc;
+    CU(ekf_launch_flush_done(ctx->b, line + 1, ctx->stream));
+    ctx->launches++;
+    ctx->pend_ub = 0;
+  }
+  return EKF_OK;
+}
+
+int enqueue_end(ekf_ctx* ctx, const double* d_z, const double* d_R, int m) {
+  int rc = sweep_now(ctx, ctx->pend_ub);
+  if (rc) return rc;
+  ctx->pend_ub = 0;
+  CU(ekf_launch_end_scan(ctx->g, ctx->b, d_z, d_R, m, ctx->L_ub, ctx->stream));
+  ctx->launches += (m > 0) ? 3 : 2;
+  long long lub = (long long)ctx->L_ub + m;
+  ctx->L_ub = (int)(lub > ctx->g.cap ? ctx->g.cap : lub);
+  ctx->scan_open = 0;
+  ctx->cursor = 0;
+  return EKF_OK;
+}
+
+/* the whole Robot::localize, enqueued without returning to the host */
+int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, const double* d_z, const double* d_R) {
+  CU(ekf_launch_predict(ctx->g, ctx->b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
+  ctx->launches++;
+  ctx->pend_ub = 0;
+  ctx->scan_open = 1;
+  if (ctx->L_ub == 0) {
+    CU(ekf_launch_queue_all(ctx->g, ctx->b, m, ctx->stream));
+    if (m > 0) ctx->launches++;
+  } else {
+    for (int i = 0; i < m; ++i) {
+      CU(ekf_launch_associate(ctx->g, ctx->b, d_z, d_R, i, ctx->L_ub, ctx->stream));
+      ctx->launches++;
+      int rc = enqueue_update(ctx, d_z, d_R, i, -1);
+      if (rc) return rc;
+    }
+  }
+  return enqueue_end(ctx, d_z, d_R, m);
+}
+
+int read_state(ekf_ctx* ctx) {
+  CU(cudaMemcpyAsync(ctx->h_st, ctx->b.st, sizeof(EkfDevState), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->scan_open) ctx->L_ub = ctx->h_st->L;
+  return EKF_OK;
+}
+
+int sticky_to_status(int sticky) {
+  if (sticky & EKF_STICKY_CAPACITY) return EKF_ECAPACITY;
+  if (sticky & EKF_STICKY_SINGULAR) return EKF_ESINGULAR;
+  return EKF_OK;
+}
+
+int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, const unsigned char* uid) {
+  if (!out || !cfg || cfg->capacity_lines < 1 || cfg->reset_headroom < 0 || world < 1 || rank < 0 || rank >= world)
+    return EKF_EINVAL;
+  ekf_ctx* ctx = new ekf_ctx();
+  memset(&ctx->b, 0, sizeof ctx->b);
+  ctx->cfg = *cfg;
+  if (ctx->cfg.max_batch <= 0) ctx->cfg.max_batch = 64;
+  ctx->err[0] = 0;
+  ctx->stream = 0; ctx->max_lines = 0; ctx->d_in = 0; ctx->h_in = 0; ctx->h_jout = 0; ctx->h_st = 0;
+  ctx->L_ub = 0; ctx->pend_ub = 0; ctx->scan_open = 0; ctx->cursor = 0;
+  ctx->prof = 0; ctx->ev_used = 0; ctx->launches = 0; ctx->comm = 0;
+  ctx->d_stage = 0; ctx->stage_elems = 0; ctx->d_partials = 0; ctx->d_out3 = 0;
+  *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    snprintf(ctx->err, sizeof ctx->err, "no CUDA device: libekfcuda has no CPU fallback");
+    return EKF_ECUDA;
+  }
+  CU(cudaSetDevice(cfg->device));
+  EkfGeom& g = ctx->g;
+  g.cap = cfg->capacity_lines;
+  g.n = 3 + 2 * g.cap;
+  g.ld = ((g.n + EKF_TILE - 1) / EKF_TILE) * EKF_TILE;
+  g.rank = rank; g.world = world;
+  g.gate = cfg->gate; g.enc_noise = cfg->encoder_noise; g.headroom = cfg->reset_headroom;
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  const size_t ld = g.ld;
+  const size_t p_rows = (size_t)ekf_local_tile_rows(g) * EKF_TILE;
+  CU(cudaMalloc(&ctx->b.st, sizeof(EkfDevState)));
+  CU(cudaMalloc(&ctx->b.y, ld * sizeof(double)));
+  CU(cudaMalloc(&ctx->b.top, 3 * ld * sizeof(double)));
+  CU(cudaMalloc(&ctx->b.diag, 4 * (size_t)g.cap * sizeof(double)));
+  CU(cudaMalloc(&ctx->b.P, p_rows * ld * sizeof(double)));
+  CU(cudaMalloc(&ctx->b.matched, (size_t)g.cap * sizeof(int)));
+  CU(cudaMalloc(&ctx->b.Kp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
+  CU(cudaMalloc(&ctx->b.KSp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
+  CU(cudaMalloc(&ctx->b.colA, 2 * ld * sizeof(double)));
+  ctx->b.colB = ctx->b.colA + ld;
+  CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
+  CU(cudaMalloc(&ctx->d_partials, 3 * (size_t)g.n * sizeof(double)));
+  CU(cudaMalloc(&ctx->d_out3, 3 * sizeof(double)));
+  CU(cudaMemsetAsync(ctx->b.st, 0, sizeof(EkfDevState), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.y, 0, ld * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.top, 0, 3 * ld * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.diag, 0, 4 * (size_t)g.cap * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.P, 0, p_rows * ld * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.matched, 0, (size_t)g.cap * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.Kp, 0, (size_t)ctx->cfg.max_batch * ld * sizeof(double2), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.KSp, 0, (size_t)ctx->cfg.max_batch * ld * sizeof(double2), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.colA, 0, 2 * ld * sizeof(double), ctx->stream));
+  int rc = ensure_lines(ctx, 64);
+  if (rc) return rc;
+  CU(ekf_launch_init(g, ctx->b, ctx->stream));
+  if (world > 1) {
+    NcclApi* api = nccl_api();
+    if (!api || !uid) { snprintf(ctx->err, sizeof ctx->err, "libnccl.so.2 could not be loaded"); return EKF_ENCCL; }
+    ncclUniqueId id;
+    memcpy(id.internal, uid, 128);
+    const int nrc = api->CommInitRank(&ctx->comm, world, id, rank);
+    if (nrc != 0) {
+      snprintf(ctx->err, sizeof ctx->err, "ncclCommInitRank: %s", api->GetErrorString ? api->GetErrorString(nrc) : "error");
+      return EKF_ENCCL;
+    }
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return EKF_OK;
+}
+
+int ensure_stage(ekf_ctx* ctx, size_t elems) {
+  if (elems <= ctx->stage_elems) return EKF_OK;
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  ctx->d_stage = 0; ctx->stage_elems = 0;
+  CU(cudaMalloc(&ctx->d_stage, elems * sizeof(double)));
+  ctx->stage_elems = elems;
+  return EKF_OK;
+}
+
+/* rows [0,nr) x cols [0,nc) of the symmetrised covariance into host memory with row stride ldp */
+int download_rect(ekf_ctx* ctx, int r0, int c0, int nr, int nc, double* P, size_t ldp) {
+  if (nr <= 0 || nc <= 0) return EKF_OK;
+  size_t rows_per = kStageElems / (size_t)nc;
+  if (rows_per < 1) rows_per = 1;
+  if (rows_per > (size_t)nr) rows_per = nr;
+  int rc = ensure_stage(ctx, rows_per * (size_t)nc);
+  if (rc) return rc;
+  for (int r = 0; r < nr; r += (int)rows_per) {
+    const int cnt = (nr - r < (int)rows_per) ? nr - r : (int)rows_per;
+    CU(ekf_launch_assemble(ctx->g, ctx->b, r0 + r, cnt, c0, nc, ctx->d_stage, nc, ctx->stream));
+    CU(cudaMemcpy2DAsync(P + (size_t)r * ldp, ldp * sizeof(double), ctx->d_stage, (size_t)nc * sizeof(double),
+                         (size_t)nc * sizeof(double), cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return EKF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ekf_version(void) { return "libekfcuda 0.1 (sm_100a)"; }
+
+int ekf_default_config(ekf_config* cfg) {
+  if (!cfg) return EKF_EINVAL;
+  cfg->capacity_lines = 100;      /* Robot.h:13 */
+  cfg->gate = 0.4;                /* Robot.h:15 */
+  cfg->encoder_noise = 0.024;     /* Robot.h:17 */
+  cfg->reset_headroom = 10;       /* Robot.cpp:893 */
+  cfg->device = 0;
+  cfg->max_batch = 64;
+  cfg->flags = 0;
+  return EKF_OK;
+}
+
+int ekf_create(ekf_ctx** out, const ekf_config* cfg) { return create_common(out, cfg, 0, 1, 0); }
+
+int ekf_nccl_unique_id(unsigned char id[128]) {
+  NcclApi* api = nccl_api();
+  if (!api || !id) return EKF_ENCCL;
+  ncclUniqueId u;
+  if (api->GetUniqueId(&u) != 0) return EKF_ENCCL;
+  memcpy(id, u.internal, 128);
+  return EKF_OK;
+}
+
+int ekf_create_sharded(ekf_ctx** out, const ekf_config* cfg, int rank, int world, const unsigned char uid[128]) {
+  return create_common(out, cfg, rank, world, uid);
+}
+
+int ekf_destroy(ekf_ctx* ctx) {
+  if (!ctx) return EKF_EINVAL;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(ctx->comm); }
+  free_line_tables(ctx);
+  cudaFree(ctx->b.st); cudaFree(ctx->b.y); cudaFree(ctx->b.top); cudaFree(ctx->b.diag); cudaFree(ctx->b.P);
+  cudaFree(ctx->b.matched); cudaFree(ctx->b.Kp); cudaFree(ctx->b.KSp); cudaFree(ctx->b.colA);
+  cudaFree(ctx->d_stage); cudaFree(ctx->d_partials); cudaFree(ctx->d_out3);
+  cudaFreeHost(ctx->h_st);
+  for (size_t i = 0; i < ctx->ev.size(); ++i) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return EKF_OK;
+}
+
+const char* ekf_last_error(const ekf_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+/* ------------------------------------------ fused path ------------------------------------------- */
+int ekf_scan(ekf_ctx* ctx, const double x_t0[3], const double u[3], int m, const double* z, const double* R,
+             int* j_out, double pose[3]) {
+  if (!ctx || !u || m < 0 || (m > 0 && (!z || !R))) return EKF_EINVAL;
+  if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_scan inside an open step-wise scan"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_lines(ctx, m);
+  if (rc) return rc;
+  double* h = ctx->h_in;
+  memcpy(h, u, 3 * sizeof(double));
+  if (x_t0) memcpy(h + 3, x_t0, 3 * sizeof(double));
+  const size_t ml = ctx->max_lines;
+  if (m > 0) { memcpy(h + 6, z, 2 * (size_t)m * sizeof(double)); memcpy(h + 6 + 2 * ml, R, 4 * (size_t)m * sizeof(double)); }
+  /* two H2D copies from pinned memory: [u|x|z] and [R] */
+  CU(cudaMemcpyAsync(ctx->d_in, h, (6 + 2 * (size_t)m) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (m > 0) CU(cudaMemcpyAsync(in_R(ctx), h + 6 + 2 * ml, 4 * (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  rc = enqueue_scan(ctx, in_u(ctx), x_t0 ? in_x(ctx) : 0, m, in_z(ctx), in_R(ctx));
+  if (rc) return rc;
+  if (m > 0 && j_out) CU(cudaMemcpyAsync(ctx->h_jout, ctx->b.jout, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = read_state(ctx);
+  if (rc) return rc;
+  if (m > 0 && j_out) memcpy(j_out, ctx->h_jout, (size_t)m * sizeof(int));
+  if (pose) memcpy(pose, ctx->h_st->pose, 3 * sizeof(double));
+  const int sticky = ctx->h_st->sticky;
+  if (sticky) {
+    CU(cudaMemsetAsync(&ctx->b.st->sticky, 0, sizeof(int), ctx->stream));
+    snprintf(ctx->err, sizeof ctx->err, "scan finished with sticky status 0x%x", sticky);
+  }
+  return sticky_to_status(sticky);
+}
+
+int ekf_scan_device(ekf_ctx* ctx, const double* d_u, int m, const double* d_z, const double* d_R, int* d_j_out) {
+  if (!ctx || !d_u || m < 0 || (m > 0 && (!d_z || !d_R))) return EKF_EINVAL;
+  if (ctx->scan_open) return EKF_ESTATE;
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_lines(ctx, m);
+  if (rc) return rc;
+  rc = enqueue_scan(ctx, d_u, 0, m, d_z, d_R);
+  if (rc) return rc;
+  if (d_j_out && m > 0)
+    CU(cudaMemcpyAsync(d_j_out, ctx->b.jout, (size_t)m * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  return EKF_OK;
+}
+
+int ekf_sync(ekf_ctx* ctx) {
+  if (!ctx) return EKF_EINVAL;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return EKF_OK;
+}
+
+/* ---------------------------------------- step-wise path ----------------------------------------- */
+int ekf_predict(ekf_ctx* ctx, const double x_t0[3], const double u[3], double x_pre[3]) {
+  if (!ctx || !u) return EKF_EINVAL;
+  if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_predict: previous scan not ended"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  double* h = ctx->h_in;
+  memcpy(h, u, 3 * sizeof(double));
+  if (x_t0) memcpy(h + 3, x_t0, 3 * sizeof(double));
+  CU(cudaMemcpyAsync(ctx->d_in, h, 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ekf_launch_predict(ctx->g, ctx->b, in_u(ctx), x_t0 ? in_x(ctx) : 0, ctx->max_lines, ctx->L_ub, ctx->stream));
+  ctx->launches++;
+  ctx->pend_ub = 0; ctx->scan_open = 1; ctx->cursor = 0;
+  int rc = read_state(ctx);
+  if (rc) return rc;
+  if (x_pre) memcpy(x_pre, ctx->h_st->x_pre, 3 * sizeof(double));
+  return EKF_OK;
+}
+
+namespace {
+int stage_line(ekf_ctx* ctx, const double z[2], const double R[4]) {
+  if (ctx->cursor >= ctx->max_lines) {
+    snprintf(ctx->err, sizeof ctx->err, "more than %d lines in a step-wise scan", ctx->max_lines);
+    return EKF_EINVAL;
+  }
+  const int i = ctx->cursor;
+  /* pinned slots mirror the device layout, so an earlier line's copy is never overwritten in flight */
+  double* hz = ctx->h_in + 6 + 2 * (size_t)i;
+  double* hR = ctx->h_in + 6 + 2 * (size_t)ctx->max_lines + 4 * (size_t)i;
+  hz[0] = z[0]; hz[1] = z[1]; hR[0] = R[0]; hR[1] = R[1]; hR[2] = R[2]; hR[3] = R[3];
+  CU(cudaMemcpyAsync(in_z(ctx) + 2 * (size_t)i, hz, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(in_R(ctx) + 4 * (size_t)i, hR, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return EKF_OK;
+}
+}  // namespace
+
+int ekf_associate(ekf_ctx* ctx, const double z[2], const double R[4], int* j_out, double innov[2]) {
+  if (!ctx || !z || !R || !j_out) return EKF_EINVAL;
+  if (!ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_associate before ekf_predict"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = stage_line(ctx, z, R);
+  if (rc) return rc;
+  const int i = ctx->cursor;
+  const int none = EKF_NO_MATCH;
+  ctx->h_jout[0] = none;
+  CU(cudaMemcpyAsync(ctx->b.jbest + i, ctx->h_jout, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ekf_launch_associate(ctx->g, ctx->b, in_z(ctx), in_R(ctx), i, ctx->L_ub, ctx->stream));
+  if (ctx->L_ub > 0) {
+    CU(ekf_launch_gain(ctx->g, ctx->b, in_z(ctx), in_R(ctx), i, -1, 3, 1, ctx->cfg.max_batch, ctx->stream));
+    ctx->launches += 2;
+  }
+  CU(cudaMemcpyAsync(ctx->h_jout, ctx->b.jbest + i, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = read_state(ctx);
+  if (rc) return rc;
+  const int j = ctx->h_jout[0];
+  *j_out = (j == EKF_NO_MATCH) ? -1 : j;
+  if (innov) { innov[0] = (j == EKF_NO_MATCH) ? 0.0 : ctx->h_st->v[0]; innov[1] = (j == EKF_NO_MATCH) ? 0.0 : ctx->h_st->v[1]; }
+  return EKF_OK;
+}
+
+int ekf_update(ekf_ctx* ctx, int j, const double z[2], const double R[4], double x_post[3]) {
+  if (!ctx || !z || !R || j < 0) return EKF_EINVAL;
+  if (!ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_update before ekf_predict"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = read_state(ctx);
+  if (rc) return rc;
+  if (j >= ctx->h_st->L) { snprintf(ctx->err, sizeof ctx->err, "ekf_update: landmark %d >= %d", j, ctx->h_st->L); return EKF_EINVAL; }
+  rc = stage_line(ctx, z, R);
+  if (rc) return rc;
+  rc = enqueue_update(ctx, in_z(ctx), in_R(ctx), ctx->cursor, j);
+  if (rc) return rc;
+  ctx->cursor++;
+  if (x_post) {
+    rc = read_state(ctx);
+    if (rc) return rc;
+    memcpy(x_post, ctx->h_st->pose, 3 * sizeof(double));
+  }
+  return EKF_OK;
+}
+
+int ekf_add_line(ekf_ctx* ctx, const double z[2], const double R[4]) {
+  if (!ctx || !z || !R) return EKF_EINVAL;
+  if (!ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_add_line before ekf_predict"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = stage_line(ctx, z, R);
+  if (rc) return rc;
+  CU(ekf_launch_apply(ctx->g, ctx->b, ctx->cursor, -2, 0, ctx->stream));
+  ctx->launches++;
+  ctx->cursor++;
+  return EKF_OK;
+}
+
+int ekf_end_scan(ekf_ctx* ctx, int n_lines, double pose[3]) {
+  if (!ctx) return EKF_EINVAL;
+  if (!ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_end_scan before ekf_predict"); return EKF_ESTATE; }
+  if (n_lines != ctx->cursor) {
+    snprintf(ctx->err, sizeof ctx->err, "ekf_end_scan: n_lines=%d but %d lines were updated/queued", n_lines, ctx->cursor);
+    return EKF_EINVAL;
+  }
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = enqueue_end(ctx, in_z(ctx), in_R(ctx), n_lines);
+  if (rc) return rc;
+  rc = read_state(ctx);
+  if (rc) return rc;
+  if (pose) memcpy(pose, ctx->h_st->pose, 3 * sizeof(double));
+  const int sticky = ctx->h_st->sticky;
+  if (sticky) CU(cudaMemsetAsync(&ctx->b.st->sticky, 0, sizeof(int), ctx->stream));
+  return sticky_to_status(sticky);
+}
+
+/* ------------------------------------------ state access ----------------------------------------- */
+int ekf_get_state(ekf_ctx* ctx, double pose[3], int* n_lines, int* sticky_status) {
+  if (!ctx) return EKF_EINVAL;
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = read_state(ctx);
+  if (rc) return rc;
+  if (pose) memcpy(pose, ctx->h_st->pose, 3 * sizeof(double));
+  if (n_lines) *n_lines = ctx->h_st->L;
+  if (sticky_status) {
+    *sticky_status = sticky_to_status(ctx->h_st->sticky);
+    if (ctx->h_st->sticky) CU(cudaMemsetAsync(&ctx->b.st->sticky, 0, sizeof(int), ctx->stream));
+  }
+  return EKF_OK;
+}
+
+int ekf_get_robot_cov(ekf_ctx* ctx, double Prr[9]) {
+  if (!ctx || !Prr) return EKF_EINVAL;
+  CU(cudaSetDevice(ctx->cfg.device));
+  double t[9];
+  CU(cudaMemcpy2DAsync(t, 3 * sizeof(double), ctx->b.top, (size_t)ctx->g.ld * sizeof(double), 3 * sizeof(double), 3,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k) Prr[3 * i + k] = (i <= k) ? t[3 * i + k] : t[3 * k + i];
+  return EKF_OK;
+}
+
+int ekf_get_ellipse(ekf_ctx* ctx, float axii[2], float* angle, int* ok) {
+  if (!ctx || !axii || !angle) return EKF_EINVAL;
+  double Prr[9];
+  int rc = ekf_get_robot_cov(ctx, Prr);
+  if (rc) return rc;
+  /* Robot.cpp:75-113 on the 2x2 block: closed-form eigen-decomposition (symmetric input) */
+  const double a = Prr[0], b = Prr[1], c = Prr[3], d = Prr[4];
+  const double tr = a + d, half = 0.5 * (a - d), disc = half * half + b * c;
+  if (disc < 0.0) { if (ok) *ok = 0; return EKF_OK; }
+  const double rt = sqrt(disc);
+  double l[2] = {0.5 * tr + rt, 0.5 * tr - rt};
+  double v[2][2];
+  for (int k = 0; k < 2; ++k) {
+    double vx, vy;
+    if (b != 0.0) { vx = b; vy = l[k] - a; }
+    else if (c != 0.0) { vx = l[k] - d; vy = c; }
+    else { vx = ((k == 0) == (a >= d)) ? 1.0 : 0.0; vy = 1.0 - vx; }
+    const double nrm = sqrt(vx * vx + vy * vy);
+    if (nrm > 0.0) { vx /= nrm; vy /= nrm; }
+    v[k][0] = vx; v[k][1] = vy;
+  }
+  if (fabs(l[1]) < fabs(l[0])) {
+    double t = l[0]; l[0] = l[1]; l[1] = t;
+    t = v[0][0]; v[0][0] = v[1][0]; v[1][0] = t;
+    t = v[0][1]; v[0][1] = v[1][1]; v[1][1] = t;
+  }
+  for (int k = 0; k < 2; ++k) axii[k] = 2.f * (float)sqrt(5.991 * fabs(l[k]));   /* Robot.cpp:104 */
+  *angle = (float)atan2(v[1][0], v[1][1]);                                          /* Robot.cpp:113 */
+  if (ok) *ok = 1;
+  return EKF_OK;
+}
+
+int ekf_download(ekf_ctx* ctx, double* y, double* P, int* n_lines) {
+  if (!ctx) return EKF_EINVAL;
+  if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_download inside an open scan"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = read_state(ctx);
+  if (rc) return rc;
+  const int n = ctx->g.n, nl = 3 + 2 * ctx->h_st->L;
+  if (n_lines) *n_lines = ctx->h_st->L;
+  if (y) {
+    memset(y, 0, (size_t)n * sizeof(double));
+    CU(cudaMemcpyAsync(y, ctx->b.y, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (P) { rc = download_rect(ctx, 0, 0, n, n, P, (size_t)n); if (rc) return rc; }
+  return EKF_OK;
+}
+
+int ekf_download_live(ekf_ctx* ctx, double* y, double* P, int ldp, int max_n, int* n_lines) {
+  if (!ctx) return EKF_EINVAL;
+  if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_download_live inside an open scan"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = read_state(ctx);
+  if (rc) return rc;
+  const int nl = 3 + 2 * ctx->h_st->L;
+  if (n_lines) *n_lines = ctx->h_st->L;
+  if (nl > max_n || (P && ldp < nl)) { snprintf(ctx->err, sizeof ctx->err, "live dimension %d exceeds the buffer", nl); return EKF_EINVAL; }
+  if (y) {
+    CU(cudaMemcpyAsync(y, ctx->b.y, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (P) { rc = download_rect(ctx, 0, 0, nl, nl, P, (size_t)ldp); if (rc) return rc; }
+  return EKF_OK;
+}
+
+int ekf_download_block(ekf_ctx* ctx, int r0, int c0, int nr, int nc, double* out) {
+  if (!ctx || !out || r0 < 0 || c0 < 0 || nr < 0 || nc < 0 || r0 + nr > ctx->g.n || c0 + nc > ctx->g.n) return EKF_EINVAL;
+  if (ctx->scan_open) return EKF_ESTATE;
+  CU(cudaSetDevice(ctx->cfg.device));
+  return download_rect(ctx, r0, c0, nr, nc, out, (size_t)nc);
+}
+
+int ekf_upload(ekf_ctx* ctx, const double* y, const double* P, int n_lines) {
+  if (!ctx || n_lines < 0 || n_lines > ctx->g.cap) return EKF_EINVAL;
+  if (ctx->scan_open) return EKF_ESTATE;
+  CU(cudaSetDevice(ctx->cfg.device));
+  const int n = ctx->g.n, nl = 3 + 2 * n_lines;
+  int rc = read_state(ctx);
+  if (rc) return rc;
+  if (y) CU(cudaMemcpyAsync(ctx->b.y, y, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (P) {
+    size_t rows_per = kStageElems / (size_t)nl;
+    if (rows_per < 1) rows_per = 1;
+    if (rows_per > (size_t)nl) rows_per = nl;
+    rc = ensure_stage(ctx, rows_per * (size_t)nl);
+    if (rc) return rc;
+    for (int r = 0; r < nl; r += (int)rows_per) {
+      const int cnt = (nl - r < (int)rows_per) ? nl - r : (int)rows_per;
+      CU(cudaMemcpy2DAsync(ctx->d_stage, (size_t)nl * sizeof(double), P + (size_t)r * n, (size_t)n * sizeof(double),
+                           (size_t)nl * sizeof(double), cnt, cudaMemcpyHostToDevice, ctx->stream));
+      CU(ekf_launch_scatter(ctx->g, ctx->b, r, cnt, nl, ctx->d_stage, nl, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  /* pose mirrors follow y[0:3] exactly as after an update (Robot.cpp:597-599) */
+  EkfDevState s = *ctx->h_st;
+  s.L = n_lines;
+  if (y) { s.pose[0] = y[0]; s.pose[1] = y[1]; s.pose[2] = y[2]; }
+  *ctx->h_st = s;
+  CU(cudaMemcpyAsync(ctx->b.st, ctx->h_st, sizeof(EkfDevState), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->L_ub = n_lines;
+  return EKF_OK;
+}
+
+int ekf_cov_stats(ekf_ctx* ctx, double* trace, double* sum, double* sumsq) {
+  if (!ctx) return EKF_EINVAL;
+  if (ctx->scan_open) return EKF_ESTATE;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(ekf_launch_cov_stats(ctx->g, ctx->b, ctx->d_partials, ctx->g.n, ctx->d_out3, ctx->stream));
+  double o[3];
+  CU(cudaMemcpyAsync(o, ctx->d_out3, sizeof o, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (trace) *trace = o[0];
+  if (sum) *sum = o[1];
+  if (sumsq) *sumsq = o[2];
+  return EKF_OK;
+}
+
+/* ------------------------------------------ measurement ------------------------------------------ */
+int ekf_profile_enable(ekf_ctx* ctx, int on) {
+  if (!ctx) return EKF_EINVAL;
+  ctx->prof = on ? 1 : 0;
+  ctx->ev_used = 0; ctx->ev_bytes.clear();
+  return EKF_OK;
+}
+
+int ekf_profile_read(ekf_ctx* ctx, int* n_sweeps, double* sweep_ms, double* sweep_bytes, long long* launches) {
+  if (!ctx) return EKF_EINVAL;
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = read_state(ctx);
+  if (rc) return rc;
+  const double n = 3.0 + 2.0 * ctx->h_st->L;
+  double ms = 0.0, bytes = 0.0;
+  const size_t ns = ctx->ev_used / 2;
+  for (size_t i = 0; i < ns; ++i) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+    ms += t;
+    bytes += 8.0 * n * (n + 1.0) + 32.0 * n * ctx->ev_bytes[i];     /* B_sweep(n, m) */
+  }
+  if (n_sweeps) *n_sweeps = (int)ns;
+  if (sweep_ms) *sweep_ms = ms;
+  if (sweep_bytes) *sweep_bytes = bytes;
+  if (launches) *launches = ctx->launches;
+  ctx->ev_used = 0; ctx->ev_bytes.clear(); ctx->launches = 0;
+  return EKF_OK;
+}
+
+int ekf_sweep_probe(ekf_ctx* ctx, int m, int repeats, double* ms_each) {
+  if (!ctx || m < 1 || m > ctx->cfg.max_batch || repeats < 1) return EKF_EINVAL;
+  if (ctx->scan_open) return EKF_ESTATE;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(ekf_launch_zero_pending(ctx->g, ctx->b, m, &ctx->b.st->np, ctx->stream));
+  CU(ekf_launch_sweep(ctx->g, ctx->b, 0, m, ctx->L_ub, ctx->stream));       /* warm-up */
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < repeats; ++i) CU(ekf_launch_sweep(ctx->g, ctx->b, 0, m, ctx->L_ub, ctx->stream));
+  CU(cudaEventRecord(e1, ctx->stream));
+  CU(cudaMemsetAsync(&ctx->b.st->np, 0, sizeof(int), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  float t = 0.f;
+  CU(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ctx->launches += repeats + 2;
+  if (ms_each) *ms_each = (double)t / repeats;
+  return EKF_OK;
+}
+
+}  /* extern "C" */

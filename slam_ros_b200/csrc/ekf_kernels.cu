@@ -1,0 +1,673 @@
+/* ekf_kernels.cu -- hand-written sm_100a kernels of libekfcuda (single filter, optionally row-sharded).
+ *
+ * Arithmetic contract: every expression that feeds the association gate, the gain or the covariance
+ * follows the scalar expansion of the GSL reference-BLAS loop the reference calls at the cited line of
+ * slam_ros/Robot.cpp: same operand order, same accumulation order, one rounding
+ * per operation.  The explicit __dmul_rn/__dadd_rn/__dsub_rn intrinsics are never contracted into FMAs
+ * (the file is also compiled with -fmad=false).  What differs from the reference by design: only the
+ * UPPER triangle of P is kept (the reference's full-matrix update lets P drift asymmetric by ulps),
+ * and sin/cos are CUDA's (<= 2 ulp) instead of glibc's.
+ */
+#include "ekf_internal.h"
+#include "ekf_device.cuh"
+
+#define EKF_BLOCK 256
+
+namespace {
+
+__device__ __forceinline__ int owner_of_row(const EkfGeom& g, int r) { return (r / EKF_TILE) % g.world; }
+__device__ __forceinline__ size_t local_row(const EkfGeom& g, int r) {
+  return (size_t)((r / EKF_TILE) / g.world) * EKF_TILE + (size_t)(r % EKF_TILE);
+}
+/* is (r,q), r <= q, one of the eagerly maintained elements? */
+__device__ __forceinline__ bool is_hot(int r, int q) {
+  return r <= 2 || q == r || (q == r + 1 && (r & 1));
+}
+/* hot element (r <= q) straight from its replica */
+__device__ __forceinline__ double hot_value(const EkfGeom& g, const EkfBuffers& b, int r, int q) {
+  if (r <= 2) return b.top[(size_t)r * g.ld + q];
+  const int j = (r - 3) >> 1;
+  if (r & 1) return b.diag[4 * j + (q - r)];   /* r = a: (a,a) or (a,b) */
+  return b.diag[4 * j + 2];                    /* r = b: (b,b) */
+}
+/* current value of a COLD upper element (r < q) owned by this rank: base minus the pending terms in order */
+__device__ __forceinline__ double cold_value(const EkfGeom& g, const EkfBuffers& b, int r, int q, int np) {
+  double p = b.P[local_row(g, r) * g.ld + q];
+  for (int i = 0; i < np; ++i)
+    p = sub_rn(p, rank2(b.KSp[(size_t)i * g.ld + r], b.Kp[(size_t)i * g.ld + q]));
+  return p;
+}
+/* 3x3 robot block with the lower half mirrored from the authoritative upper half */
+__device__ __forceinline__ void load_rr(const EkfGeom& g, const double* top, double A[3][3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int k = i; k < 3; ++k) { const double v = top[(size_t)i * g.ld + k]; A[i][k] = v; A[k][i] = v; }
+}
+
+/* Robot.cpp:367-489 for one (line, landmark j) pair; reads only replicated hot data */
+__device__ void eval_gate(const EkfGeom& g, const EkfBuffers& b, const double x_pre[3], int j,
+                          double z0, double z1, const double R[4], Gate& G) {
+  const int a = 3 + 2 * j, bb = a + 1;
+  double Cm[5][5];                                                    /* P at rows/cols {0,1,2,a,b} */
+  for (int i = 0; i < 3; ++i) {
+    for (int k = i; k < 3; ++k) { const double v = b.top[(size_t)i * g.ld + k]; Cm[i][k] = v; Cm[k][i] = v; }
+    const double va = b.top[(size_t)i * g.ld + a], vb = b.top[(size_t)i * g.ld + bb];
+    Cm[i][3] = va; Cm[3][i] = va; Cm[i][4] = vb; Cm[4][i] = vb;
+  }
+  Cm[3][3] = b.diag[4 * j]; Cm[3][4] = b.diag[4 * j + 1]; Cm[4][3] = Cm[3][4]; Cm[4][4] = b.diag[4 * j + 2];
+  gate_from_block(Cm, b.y[a], b.y[bb], x_pre, z0, z1, R, G);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Robot::Robot (Robot.cpp:20-35): P[0,0] = P[1,1] = 0.05; everything else was zero-filled by memset */
+__global__ void k_init(EkfGeom g, EkfBuffers b) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    b.top[0] = 0.05;
+    b.top[(size_t)g.ld + 1] = 0.05;
+    b.top[(size_t)2 * g.ld + 2] = 0.0;
+  }
+}
+
+/* Robot.cpp:130-258 (structured: SURVEY appendix A.2).  Also opens the scan: per-line tables. */
+__global__ void __launch_bounds__(EKF_BLOCK) k_predict(EkfGeom g, EkfBuffers b, const double* __restrict__ u,
+                                                       const double* __restrict__ x_t0, int m) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  EkfDevState* st = b.st;
+  const double* x = x_t0 ? x_t0 : st->pose;
+  const double x0 = x[0], x1 = x[1], x2 = x[2];
+  const double u0 = u[0], u2 = u[2];
+  const double ang = add_rn(x2, __ddiv_rn(u2, 2.0));
+  const double ca = cos(ang), sa = sin(ang);
+  const double F02 = mul_rn(-u0, sa), F12 = mul_rn(u0, ca);               /* :157, :160 */
+  const int nl = 3 + 2 * st->L;
+  double* t0p = b.top; double* t1p = b.top + g.ld; const double* t2p = b.top + 2 * (size_t)g.ld;
+  for (int q = 3 + gid; q < nl; q += stride) {                        /* :242 rows 0,1 of Fx*P (== cols 0,1 of (.)Fx') */
+    const double p2 = t2p[q];
+    double a0 = add_rn(0.0, t0p[q]); axpy_skip(a0, F02, p2);
+    double a1 = add_rn(0.0, t1p[q]); axpy_skip(a1, F12, p2);
+    t0p[q] = a0; t1p[q] = a1;
+  }
+  for (int i = gid; i < m; i += stride) { b.jbest[i] = EKF_NO_MATCH; b.jout[i] = -1; }
+  if (gid == 0) {
+    double A[3][3], T[3][3], Pn[3][3];
+    load_rr(g, b.top, A);
+    for (int j = 0; j < 3; ++j) {                                     /* :242 */
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+      axpy_skip(r0, 1.0, A[0][j]); axpy_skip(r1, 1.0, A[1][j]);
+      axpy_skip(r0, F02, A[2][j]); axpy_skip(r1, F12, A[2][j]); axpy_skip(r2, 1.0, A[2][j]);
+      T[0][j] = r0; T[1][j] = r1; T[2][j] = r2;
+    }
+    for (int i = 0; i < 3; ++i) {                                     /* :246 */
+      double c0 = 0.0; c0 = add_rn(c0, mul_rn(T[i][0], 1.0)); c0 = add_rn(c0, mul_rn(T[i][2], F02));
+      double c1 = 0.0; c1 = add_rn(c1, mul_rn(T[i][1], 1.0)); c1 = add_rn(c1, mul_rn(T[i][2], F12));
+      Pn[i][0] = add_rn(0.0, c0); Pn[i][1] = add_rn(0.0, c1); Pn[i][2] = T[i][2];
+    }
+    const double Fu[3][3] = {{ca, 0.0, __ddiv_rn(mul_rn(-u0, sa), 2.0)},   /* :180-188 */
+                             {sa, 1.0, __ddiv_rn(mul_rn(u0, ca), 2.0)},
+                             {0.0, 0.0, 1.0}};
+    const double qf = add_rn(__ddiv_rn(-1.0, add_rn(1.0, fabs(u0))), 1.0);   /* :215-218 */
+    const double Q[3] = {mul_rn(g.enc_noise, qf), mul_rn(mul_rn(2.0, g.enc_noise), qf), mul_rn(g.enc_noise, qf)};
+    double FQ[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < 3; ++k)                                       /* :250 (NN, Q diagonal) */
+      for (int i = 0; i < 3; ++i) {
+        const double t = mul_rn(1.0, Fu[i][k]);
+        if (t != 0.0)
+          for (int j = 0; j < 3; ++j) FQ[i][j] = add_rn(FQ[i][j], mul_rn(t, (j == k) ? Q[k] : 0.0));
+      }
+    for (int i = 0; i < 3; ++i)                                       /* :254, :258 */
+      for (int j = i; j < 3; ++j) {
+        double t = 0.0;
+        for (int k = 0; k < 3; ++k) t = add_rn(t, mul_rn(FQ[i][k], Fu[j][k]));
+        b.top[(size_t)i * g.ld + j] = add_rn(Pn[i][j], add_rn(0.0, mul_rn(1.0, t)));
+      }
+    st->x_pre[0] = add_rn(x0, mul_rn(u0, ca));                            /* :148 */
+    st->x_pre[1] = add_rn(x1, mul_rn(u0, sa));
+    st->x_pre[2] = add_rn(x2, u2);
+    if (x_t0) { st->pose[0] = x0; st->pose[1] = x1; st->pose[2] = x2; }
+    st->epoch += 1;                                                   /* matchSavedIndexes.clear(), :294 */
+    st->pbase = 0; st->np = 0;
+    b.pidx[0] = 0; b.eidx[0] = 0;
+  }
+}
+
+/* Robot.cpp:313-501 for one line: every un-matched landmark is gated in parallel; first fit = the
+ * lowest passing index (warp-shuffle min, then one atomicMin per block). */
+__global__ void __launch_bounds__(EKF_BLOCK) k_associate(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
+                                                         const double* __restrict__ R, int line) {
+  __shared__ int s_min[EKF_BLOCK / 32];
+  const EkfDevState* st = b.st;
+  const int L = st->L;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int cand = EKF_NO_MATCH;
+  if (j < L && b.matched[j] != st->epoch) {
+    const double xp[3] = {st->x_pre[0], st->x_pre[1], st->x_pre[2]};
+    const double Rl[4] = {R[4 * line], R[4 * line + 1], R[4 * line + 2], R[4 * line + 3]};
+    Gate G;
+    eval_gate(g, b, xp, j, z[2 * line], z[2 * line + 1], Rl, G);
+    if (G.singular) atomicOr(&b.st->sticky, EKF_STICKY_SINGULAR);
+    else if (!(sqrt(fabs(G.d2)) > g.gate)) cand = j;                  /* :489 */
+  }
+  cand = __reduce_min_sync(0xffffffffu, cand);
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = (threadIdx.x < EKF_BLOCK / 32) ? s_min[threadIdx.x] : EKF_NO_MATCH;
+    v = __reduce_min_sync(0xffffffffu, v);
+    if (threadIdx.x == 0 && v != EKF_NO_MATCH) atomicMin(&b.jbest[line], v);
+  }
+}
+
+/* Robot.cpp:516-560: gain rows for the matched landmark.
+ * mode 0: K, KS from local data;  mode 1: only publish the cold H-column slices this rank owns into
+ * colA/colB (zero elsewhere);  mode 2: K, KS from colA/colB (after the exchange);  mode 3: only the
+ * winner's innovation / S into the state block. */
+__global__ void __launch_bounds__(EKF_BLOCK) k_gain(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
+                                                    const double* __restrict__ R, int line, int j_override,
+                                                    int mode, int max_batch) {
+  __shared__ Gate sG;
+  const EkfDevState* st = b.st;
+  const int j = (j_override >= 0) ? j_override : b.jbest[line];
+  if (j == EKF_NO_MATCH) return;
+  const int np = b.pidx[line] - st->pbase;
+  if (np >= max_batch) return;                    /* host flushes before this can happen */
+  const int nl = 3 + 2 * st->L;
+  const int a = 3 + 2 * j, bb = a + 1;
+  if (threadIdx.x == 0 && mode != 1) {
+    const double xp[3] = {st->x_pre[0], st->x_pre[1], st->x_pre[2]};
+    const double Rl[4] = {R[4 * line], R[4 * line + 1], R[4 * line + 2], R[4 * line + 3]};
+    eval_gate(g, b, xp, j, z[2 * line], z[2 * line + 1], Rl, sG);
+    if (blockIdx.x == 0) {
+      b.st->v[0] = sG.v[0]; b.st->v[1] = sG.v[1];
+      for (int t = 0; t < 4; ++t) b.st->S[t] = sG.S[t];
+    }
+  }
+  if (mode == 3) return;                          /* innovation tap only (ekf_associate) */
+  __syncthreads();
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (int r = gid; r < nl; r += stride) {
+    /* current P[r,a], P[r,b] through the symmetric upper storage */
+    double pa, pb;
+    const int lo_a = min(r, a), hi_a = max(r, a), lo_b = min(r, bb), hi_b = max(r, bb);
+    const bool hot_a = is_hot(lo_a, hi_a), hot_b = is_hot(lo_b, hi_b);
+    if (mode == 2) {
+      pa = hot_a ? hot_value(g, b, lo_a, hi_a) : b.colA[r];
+      pb = hot_b ? hot_value(g, b, lo_b, hi_b) : b.colB[r];
+    } else {
+      const bool own_a = (g.world == 1) || owner_of_row(g, lo_a) == g.rank;
+      const bool own_b = (g.world == 1) || owner_of_row(g, lo_b) == g.rank;
+      pa = hot_a ? hot_value(g, b, lo_a, hi_a) : (own_a ? cold_value(g, b, lo_a, hi_a, np) : 0.0);
+      pb = hot_b ? hot_value(g, b, lo_b, hi_b) : (own_b ? cold_value(g, b, lo_b, hi_b, np) : 0.0);
+      if (mode == 1) {
+        b.colA[r] = hot_a ? 0.0 : pa;
+        b.colB[r] = hot_b ? 0.0 : pb;
+        continue;
+      }
+    }
+    /* P[r,0], P[r,1], P[r,2] */
+    double p0, p1, p2;
+    if (r <= 2) {
+      p0 = b.top[(size_t)min(r, 0) * g.ld + max(r, 0)];
+      p1 = b.top[(size_t)min(r, 1) * g.ld + max(r, 1)];
+      p2 = b.top[(size_t)min(r, 2) * g.ld + max(r, 2)];
+    } else {
+      p0 = b.top[r]; p1 = b.top[(size_t)g.ld + r]; p2 = b.top[(size_t)2 * g.ld + r];
+    }
+    double2 Kr, KSr;
+    gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
+    b.Kp[(size_t)np * g.ld + r] = Kr;
+    b.KSp[(size_t)np * g.ld + r] = KSr;
+  }
+}
+
+/* Robot.cpp:564-602 restricted to the hot elements (rows 0-2, 2x2 diagonal blocks) and the state
+ * vector; the cold part of P -= KS K' is deferred to k_sweep.  Also the per-line bookkeeping
+ * (:501-504, :309/:325/:493). */
+__global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, int line, int j_override) {
+  EkfDevState* st = b.st;
+  const int j = (j_override >= 0) ? j_override : (j_override == -2 ? EKF_NO_MATCH : b.jbest[line]);
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nm = b.pidx[line];
+  const int np = nm - st->pbase;
+  if (j == EKF_NO_MATCH) {
+    if (gid == 0) {
+      const int e = b.eidx[line];
+      b.ext[e] = line;
+      b.eidx[line + 1] = e + 1; b.pidx[line + 1] = nm; b.jout[line] = -1;
+    }
+    return;
+  }
+  const int stride = gridDim.x * blockDim.x;
+  const int nl = 3 + 2 * st->L;
+  const double2* K = b.Kp + (size_t)np * g.ld;
+  const double2* KS = b.KSp + (size_t)np * g.ld;
+  const double v0 = st->v[0], v1 = st->v[1];
+  const double2 ks0 = KS[0], ks1 = KS[1], ks2 = KS[2];
+  for (int q = 3 + gid; q < nl; q += stride) {
+    const double2 kq = K[q];
+    b.top[q] = sub_rn(b.top[q], rank2(ks0, kq));                        /* :564-568 rows 0..2 */
+    b.top[(size_t)g.ld + q] = sub_rn(b.top[(size_t)g.ld + q], rank2(ks1, kq));
+    b.top[(size_t)2 * g.ld + q] = sub_rn(b.top[(size_t)2 * g.ld + q], rank2(ks2, kq));
+    const double2 ksq = KS[q];
+    const int jj = (q - 3) >> 1;
+    if (q & 1) {                                                      /* q = a: (a,a), (a,b) */
+      b.diag[4 * jj] = sub_rn(b.diag[4 * jj], rank2(ksq, kq));
+      b.diag[4 * jj + 1] = sub_rn(b.diag[4 * jj + 1], rank2(ksq, K[q + 1]));
+    } else {                                                          /* q = b: (b,b) */
+      b.diag[4 * jj + 2] = sub_rn(b.diag[4 * jj + 2], rank2(ksq, kq));
+    }
+    double t = 0.0;                                                   /* :585-589  y += K * delta */
+    axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
+    b.y[q] = add_rn(b.y[q], t);
+  }
+  if (gid == 0) {
+    const double2 kk[3] = {K[0], K[1], K[2]};
+    const double2 ks[3] = {ks0, ks1, ks2};
+    for (int r = 0; r < 3; ++r)
+      for (int q = r; q < 3; ++q)
+        b.top[(size_t)r * g.ld + q] = sub_rn(b.top[(size_t)r * g.ld + q], rank2(ks[r], kk[q]));
+    double yn[3];
+    for (int r = 0; r < 3; ++r) {                                     /* :579-589 */
+      double t = 0.0;
+      axpy_skip(t, kk[r].x, v0); axpy_skip(t, kk[r].y, v1);
+      yn[r] = add_rn(st->x_pre[r], t);
+    }
+    normalize_radian(yn[2]);                                          /* :596-602 */
+    for (int r = 0; r < 3; ++r) { b.y[r] = yn[r]; st->pose[r] = yn[r]; st->x_pre[r] = yn[r]; }
+    b.matched[j] = st->epoch;                                         /* :501 */
+    b.jout[line] = j;
+    b.pidx[line + 1] = nm + 1; b.eidx[line + 1] = b.eidx[line];
+    st->np = np + 1;                                                  /* read only by the next sweep */
+  }
+}
+
+/* after a sweep in the middle of a scan: the pending list restarts empty */
+__global__ void k_flush_done(EkfBuffers b, int next_line) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { b.st->pbase = b.pidx[next_line]; b.st->np = 0; }
+}
+
+/* the map is empty (Robot.cpp:308-310): every line of the scan is queued */
+__global__ void k_queue_all(EkfGeom g, EkfBuffers b, int m) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = gid; i < m; i += gridDim.x * blockDim.x) {
+    b.ext[i] = i; b.eidx[i + 1] = i + 1; b.pidx[i + 1] = 0; b.jout[i] = -1;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* THE roofline kernel.  Robot.cpp:564-568, P -= (K S) K', for the cold part of the upper triangle:
+ * one pass that applies the scan's np pending rank-2 terms to every element in reference order.
+ * 64x64 tiles; 8 warps x 8 rows; each lane owns two adjacent columns (one 16-byte load/store per row),
+ * keeps its columns' K terms in registers (C terms at a time) and reads the rows' K S terms through
+ * warp-uniform (broadcast) loads.  P is streamed with evict-first hints so K / KS stay in L2.
+ * No masks: the stale copies of hot elements and the lower halves of diagonal tiles are swept too
+ * (nothing reads them), so the kernel is a pure read-modify-write stream. */
+struct TileId { int k, rb, cb; };
+
+__device__ __forceinline__ long long tiles_before(int T, int rank, int world, long long k) {
+  return k * (long long)(T - rank) - (long long)world * k * (k - 1) / 2;
+}
+__device__ __forceinline__ TileId decode_tile(int T, int rank, int world, long long idx) {
+  const double A = (double)(T - rank) + 0.5 * world;
+  double disc = A * A - 2.0 * world * (double)idx;
+  if (disc < 0.0) disc = 0.0;
+  long long k = (long long)((A - sqrt(disc)) / world);
+  if (k < 0) k = 0;
+  while (tiles_before(T, rank, world, k + 1) <= idx) ++k;
+  while (k > 0 && tiles_before(T, rank, world, k) > idx) --k;
+  TileId t;
+  t.k = (int)k;
+  t.rb = rank + world * (int)k;
+  t.cb = t.rb + (int)(idx - tiles_before(T, rank, world, k));
+  return t;
+}
+
+template <int C>
+__global__ void __launch_bounds__(EKF_BLOCK, 2) k_sweep(EkfGeom g, EkfBuffers b, const int* __restrict__ np_ptr) {
+  const int np = np_ptr ? *np_ptr : b.st->np;
+  if (np <= 0) return;
+  const int nl = 3 + 2 * b.st->L;
+  const int T = (nl + EKF_TILE - 1) / EKF_TILE;
+  if (g.rank >= T) return;
+  const long long K_rows = (T - g.rank + g.world - 1) / g.world;
+  const long long total = tiles_before(T, g.rank, g.world, K_rows);
+  const long long idx = blockIdx.x;
+  if (idx >= total) return;
+  const TileId t = decode_tile(T, g.rank, g.world, idx);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_base = t.rb * EKF_TILE + warp * 8;
+  const int q = t.cb * EKF_TILE + 2 * lane;
+  double* Pt = b.P + ((size_t)t.k * EKF_TILE + warp * 8) * g.ld + q;
+  const int rows = min(8, nl - r_base);
+  if (rows <= 0) return;
+  double2 p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < rows) p[i] = __ldcs(reinterpret_cast<const double2*>(Pt + (size_t)i * g.ld));
+  for (int c0 = 0; c0 < np; c0 += C) {
+    double2 kq0[C], kq1[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (c0 + c < np) {
+        const double2* Kc = b.Kp + (size_t)(c0 + c) * g.ld + q;
+        kq0[c] = __ldg(Kc); kq1[c] = __ldg(Kc + 1);
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < rows) {
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (c0 + c < np) {
+            const double2 ks = __ldg(b.KSp + (size_t)(c0 + c) * g.ld + r_base + i);
+            p[i].x = sub_rn(p[i].x, rank2(ks, kq0[c]));
+            p[i].y = sub_rn(p[i].y, rank2(ks, kq1[c]));
+          }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < rows) __stcs(reinterpret_cast<double2*>(Pt + (size_t)i * g.ld), p[i]);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Robot.cpp:702-716 then :776-866 phase A (per unmatched line: world-frame parameters, P_ll, and the
+ * rows 0..2 of its new columns -- all functions of the 3x3 robot block only). */
+__global__ void k_end_scan_a(EkfGeom g, EkfBuffers b, const double* __restrict__ z, const double* __restrict__ R, int m) {
+  EkfDevState* st = b.st;
+  __shared__ double s_pose[3];
+  __shared__ double s_y01[2];
+  if (threadIdx.x == 0) {
+    if (m == 0 || b.pidx[m] == 0) {                                   /* :702-716 */
+      b.y[0] = st->x_pre[0]; b.y[1] = st->x_pre[1]; b.y[2] = st->x_pre[2];
+      double th = st->x_pre[2];
+      normalize_radian(th);
+      st->pose[0] = st->x_pre[0]; st->pose[1] = st->x_pre[1]; st->pose[2] = th;
+    }
+    s_pose[0] = st->pose[0]; s_pose[1] = st->pose[1]; s_pose[2] = st->pose[2];
+    s_y01[0] = b.y[0]; s_y01[1] = b.y[1];
+  }
+  __syncthreads();
+  const int ne = b.eidx[m];
+  const int L = st->L;
+  const int n_add = min(ne, g.cap - L);
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->n_added = n_add;
+    if (n_add < ne) atomicOr(&st->sticky, EKF_STICKY_CAPACITY);       /* the reference overruns y[] here (Q4) */
+  }
+  double A[3][3];
+  load_rr(g, b.top, A);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_add; e += gridDim.x * blockDim.x) {
+    const int i = b.ext[e];
+    double alfa = z[2 * i], r = z[2 * i + 1];
+    const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
+    const int l = 3 + 2 * (L + e);
+    r = add_rn(r, add_rn(mul_rn(s_pose[0], cos(alfa)), mul_rn(s_pose[1], sin(alfa))));   /* :792 (Q8) */
+    alfa = add_rn(alfa, s_pose[2]);                                                 /* :793 */
+    const double cw = cos(alfa), sw = sin(alfa);
+    const double Gx[2][3] = {{0.0, 0.0, 1.0}, {cw, sw, 0.0}};
+    const double Gl[2][2] = {{1.0, 0.0}, {sub_rn(mul_rn(s_y01[1], cw), mul_rn(s_y01[0], sw)), 1.0}};   /* :797-798 */
+    normalize_radian(alfa);                                                       /* :801 */
+    b.y[l] = alfa; b.y[l + 1] = r;
+    b.ext_cs[2 * e] = cw; b.ext_cs[2 * e + 1] = sw;
+    double GP[2][3] = {{0, 0, 0}, {0, 0, 0}};                                     /* :823 (NN) */
+    for (int k = 0; k < 3; ++k)
+      for (int ii = 0; ii < 2; ++ii) {
+        const double t = mul_rn(1.0, Gx[ii][k]);
+        if (t != 0.0) for (int jj = 0; jj < 3; ++jj) GP[ii][jj] = add_rn(GP[ii][jj], mul_rn(t, A[k][jj]));
+      }
+    double Pll[2][2];
+    for (int ii = 0; ii < 2; ++ii)                                                /* :827 (NT) */
+      for (int jj = 0; jj < 2; ++jj) {
+        double t = 0.0;
+        for (int k = 0; k < 3; ++k) t = add_rn(t, mul_rn(GP[ii][k], Gx[jj][k]));
+        Pll[ii][jj] = add_rn(0.0, mul_rn(1.0, t));
+      }
+    double GR[2][2] = {{0, 0}, {0, 0}};                                           /* :831 (NN) */
+    for (int k = 0; k < 2; ++k)
+      for (int ii = 0; ii < 2; ++ii) {
+        const double t = mul_rn(1.0, Gl[ii][k]);
+        if (t != 0.0) for (int jj = 0; jj < 2; ++jj) GR[ii][jj] = add_rn(GR[ii][jj], mul_rn(t, Rl[k * 2 + jj]));
+      }
+    for (int ii = 0; ii < 2; ++ii)                                                /* :835, :839 */
+      for (int jj = 0; jj < 2; ++jj) {
+        double t = 0.0;
+        for (int k = 0; k < 2; ++k) t = add_rn(t, mul_rn(GR[ii][k], Gl[jj][k]));
+        Pll[ii][jj] = add_rn(Pll[ii][jj], add_rn(0.0, mul_rn(1.0, t)));
+      }
+    b.diag[4 * (L + e)] = Pll[0][0]; b.diag[4 * (L + e) + 1] = Pll[0][1]; b.diag[4 * (L + e) + 2] = Pll[1][1];
+    b.diag[4 * (L + e) + 3] = 0.0;
+    for (int k = 0; k < 3; ++k) {                                                 /* :856-860 for columns 0..2 */
+      double r0 = 0.0, r1 = 0.0;
+      for (int kk = 0; kk < 3; ++kk) {
+        axpy_skip(r0, mul_rn(1.0, Gx[0][kk]), A[kk][k]);
+        axpy_skip(r1, mul_rn(1.0, Gx[1][kk]), A[kk][k]);
+      }
+      b.top[(size_t)k * g.ld + l] = r0;
+      b.top[(size_t)k * g.ld + l + 1] = r1;
+    }
+  }
+}
+
+/* Robot.cpp:856-860 phase B: the new landmarks' column blocks P[k, l..l+1] = Gx * P[0:3, k], 3 <= k < l.
+ * Threads run along the new columns (coalesced row writes); blockIdx.y strides over the rows. */
+__global__ void __launch_bounds__(EKF_BLOCK) k_end_scan_b(EkfGeom g, EkfBuffers b) {
+  const EkfDevState* st = b.st;
+  const int n_add = st->n_added;
+  const int L = st->L;
+  const int c_idx = blockIdx.x * blockDim.x + threadIdx.x;     /* 0 .. 2*n_add-1 */
+  if (c_idx >= 2 * n_add) return;
+  const int e = c_idx >> 1, tsel = c_idx & 1;
+  const int l = 3 + 2 * (L + e);
+  const int col = l + tsel;
+  const double cw = b.ext_cs[2 * e], sw = b.ext_cs[2 * e + 1];
+  const double* t0p = b.top; const double* t1p = b.top + g.ld; const double* t2p = b.top + 2 * (size_t)g.ld;
+  for (int k = 3 + blockIdx.y; k < l; k += gridDim.y) {
+    if (g.world > 1 && owner_of_row(g, k) != g.rank) continue;
+    double v;
+    if (tsel == 0) { v = 0.0; axpy_skip(v, 1.0, t2p[k]); }
+    else { v = 0.0; axpy_skip(v, cw, t0p[k]); axpy_skip(v, sw, t1p[k]); }
+    b.P[local_row(g, k) * g.ld + col] = v;
+  }
+}
+
+/* ++savedLineCount (Robot.cpp:866) for every appended line, then the reset test (:893-904). */
+__global__ void k_end_scan_c(EkfGeom g, EkfBuffers b) {
+  EkfDevState* st = b.st;
+  int L = st->L + st->n_added;
+  if (L > g.cap - g.headroom) { L = 0; st->resets += 1; }
+  st->L = L;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* symmetrised read-out of rows [r0, r0+nr) x cols [c0, c0+nc) (zeros outside the live part).  In the
+ * sharded mode each rank emits only what it owns (hot elements: rank 0), so the ranks' outputs sum to
+ * the full matrix. */
+__global__ void __launch_bounds__(EKF_BLOCK) k_assemble(EkfGeom g, EkfBuffers b, int r0, int nr, int c0, int nc,
+                                                        double* __restrict__ out, int ld_out) {
+  const int nl = 3 + 2 * b.st->L;
+  const long long total = (long long)nr * nc;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int r = r0 + (int)(t / nc), q = c0 + (int)(t % nc);
+    double v = 0.0;
+    if (r < nl && q < nl) {
+      const int lo = min(r, q), hi = max(r, q);
+      if (is_hot(lo, hi)) { if (g.rank == 0) v = hot_value(g, b, lo, hi); }
+      else if (g.world == 1 || owner_of_row(g, lo) == g.rank) v = b.P[local_row(g, lo) * g.ld + hi];
+    }
+    out[(size_t)(r - r0) * ld_out + (q - c0)] = v;
+  }
+}
+
+/* inverse of k_assemble for ekf_upload: rows [r0, r0+nr) of a full row-major matrix (stride ld_in) */
+__global__ void __launch_bounds__(EKF_BLOCK) k_scatter(EkfGeom g, EkfBuffers b, int r0, int nr, int nl,
+                                                       const double* __restrict__ in, int ld_in) {
+  const long long total = (long long)nr * nl;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int r = r0 + (int)(t / nl), q = (int)(t % nl);
+    if (q < r) continue;                       /* upper triangle is authoritative */
+    const double v = in[(size_t)(r - r0) * ld_in + q];
+    if (r <= 2) b.top[(size_t)r * g.ld + q] = v;
+    else if (is_hot(r, q)) {
+      const int j = (r - 3) >> 1;
+      if (r & 1) b.diag[4 * j + (q - r)] = v; else b.diag[4 * j + 2] = v;
+    } else if (g.world == 1 || owner_of_row(g, r) == g.rank) b.P[local_row(g, r) * g.ld + q] = v;
+  }
+}
+
+/* trace / sum / sum of squares of the symmetrised live covariance.  One block per row, fixed-order
+ * tree inside the block, then a single block folds the per-row partials in index order. */
+__global__ void __launch_bounds__(EKF_BLOCK) k_cov_rows(EkfGeom g, EkfBuffers b, double* __restrict__ partials) {
+  __shared__ double s_sum[EKF_BLOCK], s_sq[EKF_BLOCK];
+  const int nl = 3 + 2 * b.st->L;
+  for (int r = blockIdx.x; r < nl; r += gridDim.x) {
+    double sum = 0.0, sq = 0.0;
+    for (int q = threadIdx.x; q < nl; q += blockDim.x) {
+      const int lo = min(r, q), hi = max(r, q);
+      double v = 0.0;
+      if (is_hot(lo, hi)) { if (g.rank == 0) v = hot_value(g, b, lo, hi); }
+      else if (g.world == 1 || owner_of_row(g, lo) == g.rank) v = b.P[local_row(g, lo) * g.ld + hi];
+      sum += v; sq += v * v;
+    }
+    s_sum[threadIdx.x] = sum; s_sq[threadIdx.x] = sq;
+    __syncthreads();
+    for (int w = EKF_BLOCK / 2; w > 0; w >>= 1) {
+      if (threadIdx.x < w) { s_sum[threadIdx.x] += s_sum[threadIdx.x + w]; s_sq[threadIdx.x] += s_sq[threadIdx.x + w]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      partials[3 * (size_t)r] = (g.rank == 0) ? hot_value(g, b, r, r) : 0.0;
+      partials[3 * (size_t)r + 1] = s_sum[0];
+      partials[3 * (size_t)r + 2] = s_sq[0];
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_cov_fold(EkfBuffers b, const double* __restrict__ partials, double* __restrict__ out3) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int nl = 3 + 2 * b.st->L;
+    double tr = 0.0, sum = 0.0, sq = 0.0;
+    for (int r = 0; r < nl; ++r) { tr += partials[3 * (size_t)r]; sum += partials[3 * (size_t)r + 1]; sq += partials[3 * (size_t)r + 2]; }
+    out3[0] = tr; out3[1] = sum; out3[2] = sq;
+  }
+}
+
+/* roofline probe: m zero-valued pending terms (P is unchanged bit for bit by the sweep) */
+__global__ void k_zero_pending(EkfGeom g, EkfBuffers b, int m, int* np) {
+  const size_t total = (size_t)m * g.ld;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    b.Kp[t] = make_double2(0.0, 0.0); b.KSp[t] = make_double2(0.0, 0.0);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *np = m;
+}
+
+inline int blocks_for(long long n, int cap = 1 << 20) {
+  long long bl = (n + EKF_BLOCK - 1) / EKF_BLOCK;
+  if (bl < 1) bl = 1;
+  if (bl > cap) bl = cap;
+  return (int)bl;
+}
+
+}  // namespace
+
+/* ---------------------------------------- launchers ---------------------------------------------- */
+cudaError_t ekf_launch_init(const EkfGeom& g, const EkfBuffers& b, cudaStream_t s) {
+  k_init<<<1, 32, 0, s>>>(g, b);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_predict(const EkfGeom& g, const EkfBuffers& b, const double* d_u, const double* d_x_t0,
+                               int m, int L_ub, cudaStream_t s) {
+  const int work = (3 + 2 * L_ub > m) ? 3 + 2 * L_ub : m;
+  k_predict<<<blocks_for(work, 1024), EKF_BLOCK, 0, s>>>(g, b, d_u, d_x_t0, m);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_associate(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
+                                 int line, int L_ub, cudaStream_t s) {
+  if (L_ub <= 0) return cudaSuccess;
+  k_associate<<<blocks_for(L_ub), EKF_BLOCK, 0, s>>>(g, b, d_z, d_R, line);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_gain(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
+                            int line, int j_override, int mode, int L_ub, int max_batch, cudaStream_t s) {
+  if (L_ub <= 0) return cudaSuccess;
+  k_gain<<<blocks_for(3 + 2 * L_ub, 2048), EKF_BLOCK, 0, s>>>(g, b, d_z, d_R, line, j_override, mode, max_batch);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_apply(const EkfGeom& g, const EkfBuffers& b, int line, int j_override, int L_ub,
+                             cudaStream_t s) {
+  k_apply<<<blocks_for(3 + 2 * L_ub, 2048), EKF_BLOCK, 0, s>>>(g, b, line, j_override);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
+  k_flush_done<<<1, 32, 0, s>>>(b, next_line);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, cudaStream_t s) {
+  if (m <= 0) return cudaSuccess;
+  k_queue_all<<<blocks_for(m, 1024), EKF_BLOCK, 0, s>>>(g, b, m);
+  return cudaGetLastError();
+}
+int ekf_sweep_grid_ub(const EkfGeom& g, int L_ub) {
+  const int nl = 3 + 2 * L_ub;
+  const int T = (nl + EKF_TILE - 1) / EKF_TILE;
+  if (g.rank >= T) return 0;
+  const long long K = (T - g.rank + g.world - 1) / g.world;
+  const long long total = K * (long long)(T - g.rank) - (long long)g.world * K * (K - 1) / 2;
+  return (int)total;
+}
+cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* np_ptr, int np_ub, int L_ub,
+                             cudaStream_t s) {
+  const int grid = ekf_sweep_grid_ub(g, L_ub);
+  if (grid <= 0 || np_ub <= 0) return cudaSuccess;
+  if (np_ub <= 1) k_sweep<1><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
+  else if (np_ub <= 2) k_sweep<2><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
+  else if (np_ub <= 4) k_sweep<4><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
+  else k_sweep<8><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
+                                int m, int L_ub, cudaStream_t s) {
+  /* all blocks of phase A redo the (idempotent) no-match bookkeeping only in thread 0 of block 0's
+   * shared copy; to keep it race-free phase A runs as ONE block when it also has to write the pose */
+  k_end_scan_a<<<1, 1024, 0, s>>>(g, b, d_z, d_R, m);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (m > 0) {
+    const int cols_ub = 2 * ((m < g.cap) ? m : g.cap);
+    int rows_ub = 3 + 2 * L_ub + 2 * m;
+    if (rows_ub > g.n) rows_ub = g.n;
+    int gy = rows_ub / 8; if (gy < 1) gy = 1; if (gy > 2048) gy = 2048;
+    dim3 grid((cols_ub + EKF_BLOCK - 1) / EKF_BLOCK, gy);
+    k_end_scan_b<<<grid, EKF_BLOCK, 0, s>>>(g, b);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  k_end_scan_c<<<1, 1, 0, s>>>(g, b);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_assemble(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int c0, int nc,
+                                double* d_out, int ld_out, cudaStream_t s) {
+  k_assemble<<<blocks_for((long long)nr * nc, 148 * 16), EKF_BLOCK, 0, s>>>(g, b, r0, nr, c0, nc, d_out, ld_out);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_scatter(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int nl, const double* d_in,
+                               int ld_in, cudaStream_t s) {
+  k_scatter<<<blocks_for((long long)nr * nl, 148 * 16), EKF_BLOCK, 0, s>>>(g, b, r0, nr, nl, d_in, ld_in);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_cov_stats(const EkfGeom& g, const EkfBuffers& b, double* d_partials, int n_partials,
+                                 double* d_out3, cudaStream_t s) {
+  int grid = n_partials < 148 * 8 ? n_partials : 148 * 8;
+  if (grid < 1) grid = 1;
+  k_cov_rows<<<grid, EKF_BLOCK, 0, s>>>(g, b, d_partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_cov_fold<<<1, 32, 0, s>>>(b, d_partials, d_out3);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_zero_pending(const EkfGeom& g, const EkfBuffers& b, int m, int* d_np, cudaStream_t s) {
+  k_zero_pending<<<blocks_for((long long)m * g.ld, 148 * 8), EKF_BLOCK, 0, s>>>(g, b, m, d_np);
+  return cudaGetLastError();
+}
