@@ -136,6 +136,11 @@ int ekf_cov_stats(ekf_ctx* ctx, double* trace, double* sum, double* sumsq);
 int ekf_profile_enable(ekf_ctx* ctx, int on);
 int ekf_profile_read(ekf_ctx* ctx, int* n_sweeps, double* sweep_ms, double* sweep_bytes, long long* launches);
 
+/* Device-time bracket on the ctx stream (CUDA events): start records an event, stop records a second
+ * one, waits for it and returns the elapsed milliseconds.  This is how bench.py times K steps. */
+int ekf_timer_start(ekf_ctx* ctx);
+int ekf_timer_stop(ekf_ctx* ctx, double* ms);
+
 /* Stand-alone covariance sweep for the roofline measurement: applies `m` synthetic rank-2 terms
  * (K = KS = 0, so P is unchanged bit for bit) over the live part; reports device ms via events. */
 int ekf_sweep_probe(ekf_ctx* ctx, int m, int repeats, double* ms_each);

@@ -69,6 +69,7 @@ struct ekf_ctx {
   size_t ev_used;
   std::vector<double> ev_bytes;
   long long launches;
+  cudaEvent_t t0, t1;  /* ekf_timer_* */
   /* sharded */
   ncclComm_t comm;
   /* staging for download / upload / stats */
@@ -252,7 +253,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->err[0] = 0;
   ctx->stream = 0; ctx->max_lines = 0; ctx->d_in = 0; ctx->h_in = 0; ctx->h_jout = 0; ctx->h_st = 0;
   ctx->L_ub = 0; ctx->pend_ub = 0; ctx->scan_open = 0; ctx->cursor = 0;
-  ctx->prof = 0; ctx->ev_used = 0; ctx->launches = 0; ctx->comm = 0;
+  ctx->prof = 0; ctx->ev_used = 0; ctx->launches = 0; ctx->comm = 0; ctx->t0 = 0; ctx->t1 = 0;
   ctx->d_stage = 0; ctx->stage_elems = 0; ctx->d_partials = 0; ctx->d_out3 = 0;
   *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
   int ndev = 0;
@@ -381,6 +382,8 @@ int ekf_destroy(ekf_ctx* ctx) {
   cudaFree(ctx->d_stage); cudaFree(ctx->d_partials); cudaFree(ctx->d_out3);
   cudaFreeHost(ctx->h_st);
   for (size_t i = 0; i < ctx->ev.size(); ++i) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->t0) cudaEventDestroy(ctx->t0);
+  if (ctx->t1) cudaEventDestroy(ctx->t1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return EKF_OK;
@@ -722,6 +725,25 @@ int ekf_profile_read(ekf_ctx* ctx, int* n_sweeps, double* sweep_ms, double* swee
   if (sweep_bytes) *sweep_bytes = bytes;
   if (launches) *launches = ctx->launches;
   ctx->ev_used = 0; ctx->ev_bytes.clear(); ctx->launches = 0;
+  return EKF_OK;
+}
+
+int ekf_timer_start(ekf_ctx* ctx) {
+  if (!ctx) return EKF_EINVAL;
+  CU(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->t0) { CU(cudaEventCreate(&ctx->t0)); CU(cudaEventCreate(&ctx->t1)); }
+  CU(cudaEventRecord(ctx->t0, ctx->stream));
+  return EKF_OK;
+}
+
+int ekf_timer_stop(ekf_ctx* ctx, double* ms) {
+  if (!ctx || !ctx->t0) return EKF_EINVAL;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaEventRecord(ctx->t1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->t1));
+  float t = 0.f;
+  CU(cudaEventElapsedTime(&t, ctx->t0, ctx->t1));
+  if (ms) *ms = (double)t;
   return EKF_OK;
 }
 

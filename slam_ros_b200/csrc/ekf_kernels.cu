@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(EKF_BLOCK, 2) k_sweep(EkfGeom g, EkfBuffers b,
 /* ------------------------------------------------------------------------------------------------ */
 /* Robot.cpp:702-716 then :776-866 phase A (per unmatched line: world-frame parameters, P_ll, and the
  * rows 0..2 of its new columns -- all functions of the 3x3 robot block only). */
-__global__ void k_end_scan_a(EkfGeom g, EkfBuffers b, const double* __restrict__ z, const double* __restrict__ R, int m) {
+__global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, const double* __restrict__ z, const double* __restrict__ R, int m) {
   EkfDevState* st = b.st;
   __shared__ double s_pose[3];
   __shared__ double s_y01[2];
@@ -631,7 +631,7 @@ cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const dou
                                 int m, int L_ub, cudaStream_t s) {
   /* all blocks of phase A redo the (idempotent) no-match bookkeeping only in thread 0 of block 0's
    * shared copy; to keep it race-free phase A runs as ONE block when it also has to write the pose */
-  k_end_scan_a<<<1, 1024, 0, s>>>(g, b, d_z, d_R, m);
+  k_end_scan_a<<<1, 512, 0, s>>>(g, b, d_z, d_R, m);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (m > 0) {

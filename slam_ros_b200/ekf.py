@@ -40,7 +40,7 @@ SYMBOLS = [
     "ekf_default_config", "ekf_create", "ekf_destroy", "ekf_last_error", "ekf_predict", "ekf_associate",
     "ekf_update", "ekf_add_line", "ekf_end_scan", "ekf_scan", "ekf_scan_device", "ekf_sync", "ekf_get_state",
     "ekf_get_robot_cov", "ekf_get_ellipse", "ekf_download", "ekf_upload", "ekf_download_live",
-    "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_sweep_probe",
+    "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
     "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
     "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
 ]
@@ -85,6 +85,8 @@ def load_library():
     lib.ekf_profile_enable.argtypes = [vp, C.c_int]
     lib.ekf_profile_read.argtypes = [vp, _ip, _dp, _dp, C.POINTER(C.c_longlong)]
     lib.ekf_sweep_probe.argtypes = [vp, C.c_int, C.c_int, _dp]
+    lib.ekf_timer_start.argtypes = [vp]
+    lib.ekf_timer_stop.argtypes = [vp, _dp]
     lib.ekf_batch_create.argtypes = [C.POINTER(vp), C.POINTER(EkfConfig), C.c_int]
     lib.ekf_batch_destroy.argtypes = [vp]
     lib.ekf_batch_scan.argtypes = [vp, _dp, C.c_int, _dp, _dp, _ip, _dp]
@@ -275,6 +277,14 @@ class EkfFilter:
         ns = C.c_int(0); ms = C.c_double(0); by = C.c_double(0); ln = C.c_longlong(0)
         self._check(self._lib.ekf_profile_read(self._h, C.byref(ns), C.byref(ms), C.byref(by), C.byref(ln)), "ekf_profile_read")
         return {"sweeps": int(ns.value), "sweep_ms": ms.value, "sweep_bytes": by.value, "launches": int(ln.value)}
+
+    def timer_start(self):
+        self._check(self._lib.ekf_timer_start(self._h), "ekf_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        self._check(self._lib.ekf_timer_stop(self._h, C.byref(ms)), "ekf_timer_stop")
+        return ms.value
 
     def sweep_probe(self, m=1, repeats=10):
         ms = C.c_double(0)
