@@ -38,8 +38,10 @@ enum {
 };
 
 enum {
-  EKF_FLAG_EAGER_SWEEP = 1   /* sweep P after every matched line (one rank-2 pass per match, like the
+  EKF_FLAG_EAGER_SWEEP = 1,  /* sweep P after every matched line (one rank-2 pass per match, like the
                                 reference) instead of folding the scan's matches into one rank-2m pass */
+  EKF_FLAG_SWEEP_DIRECT = 2  /* use the plain load/compute/store sweep kernel instead of the TMA + mbarrier
+                                pipeline (same bits; kept for A/B measurement) */
 };
 
 typedef struct {

@@ -11,7 +11,9 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 m = 8
 scn = sc.map_scenario(N, steps, m=m, seed=1)
-f = EkfFilter(capacity_lines=N + 256)
+import os
+flags = int(os.environ.get("EKF_FLAGS", "0"))
+f = EkfFilter(capacity_lines=N + 256, flags=flags)
 t = time.time()
 rc, j, pose = f.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
 print("seed rc", rc, "L", f.lines, "%.3fs" % (time.time() - t), flush=True)

@@ -5,6 +5,7 @@
 #include "../../include/ekf.h"
 #include "ekf_internal.h"
 
+#include <cuda.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -70,6 +71,8 @@ struct ekf_ctx {
   std::vector<double> ev_bytes;
   long long launches;
   cudaEvent_t t0, t1;  /* ekf_timer_* */
+  CUtensorMap tmapP;   /* 2-D tiled view of this rank's P for the TMA sweep */
+  int num_sms;
   /* sharded */
   ncclComm_t comm;
   /* staging for download / upload / stats */
@@ -132,6 +135,37 @@ int ensure_lines(ekf_ctx* ctx, int m) {
   return EKF_OK;
 }
 
+/* cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency) */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_tensor_map(ekf_ctx* ctx, size_t p_rows) {
+  void* fn = 0;
+  cudaDriverEntryPointQueryResult q;
+  CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) { snprintf(ctx->err, sizeof ctx->err, "cuTensorMapEncodeTiled not available"); return EKF_ECUDA; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)ctx->g.ld, (cuuint64_t)p_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ctx->g.ld * sizeof(double)};
+  const cuuint32_t box[2] = {EKF_TILE, EKF_TILE};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = ((EncodeTiledFn)fn)(&ctx->tmapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->b.P, gdim, gstride, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(ctx->err, sizeof ctx->err, "cuTensorMapEncodeTiled failed: %d", (int)r); return EKF_ECUDA; }
+  return EKF_OK;
+}
+
+int launch_sweep(ekf_ctx* ctx, int np_ub) {
+  if (ctx->cfg.flags & EKF_FLAG_SWEEP_DIRECT) {
+    CU(ekf_launch_sweep(ctx->g, ctx->b, 0, np_ub, ctx->L_ub, ctx->stream));
+    ctx->launches++;
+  } else {
+    CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmapP, np_ub, ctx->L_ub, ctx->num_sms, ctx->stream));
+    ctx->launches += (np_ub + 7) / 8;
+  }
+  return EKF_OK;
+}
+
 int sweep_now(ekf_ctx* ctx, int np_ub) {
   if (np_ub <= 0) return EKF_OK;
   cudaEvent_t e0 = 0, e1 = 0;
@@ -142,8 +176,7 @@ int sweep_now(ekf_ctx* ctx, int np_ub) {
     e0 = ctx->ev[ctx->ev_used]; e1 = ctx->ev[ctx->ev_used + 1];
     CU(cudaEventRecord(e0, ctx->stream));
   }
-  CU(ekf_launch_sweep(ctx->g, ctx->b, 0, np_ub, ctx->L_ub, ctx->stream));
-  ctx->launches++;
+  { int rc = launch_sweep(ctx, np_ub); if (rc) return rc; }
   if (ctx->prof) {
     CU(cudaEventRecord(e1, ctx->stream));
     ctx->ev_used += 2;
@@ -282,6 +315,8 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMalloc(&ctx->b.colA, 2 * ld * sizeof(double)));
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
+  CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  { int rc = make_tensor_map(ctx, p_rows); if (rc) return rc; }
   CU(cudaMalloc(&ctx->d_partials, 3 * (size_t)g.n * sizeof(double)));
   CU(cudaMalloc(&ctx->d_out3, 3 * sizeof(double)));
   CU(cudaMemsetAsync(ctx->b.st, 0, sizeof(EkfDevState), ctx->stream));
@@ -752,18 +787,17 @@ int ekf_sweep_probe(ekf_ctx* ctx, int m, int repeats, double* ms_each) {
   if (ctx->scan_open) return EKF_ESTATE;
   CU(cudaSetDevice(ctx->cfg.device));
   CU(ekf_launch_zero_pending(ctx->g, ctx->b, m, &ctx->b.st->np, ctx->stream));
-  CU(ekf_launch_sweep(ctx->g, ctx->b, 0, m, ctx->L_ub, ctx->stream));       /* warm-up */
+  { int rc = launch_sweep(ctx, m); if (rc) return rc; }                        /* warm-up */
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   CU(cudaEventRecord(e0, ctx->stream));
-  for (int i = 0; i < repeats; ++i) CU(ekf_launch_sweep(ctx->g, ctx->b, 0, m, ctx->L_ub, ctx->stream));
+  for (int i = 0; i < repeats; ++i) { int rc = launch_sweep(ctx, m); if (rc) return rc; }
   CU(cudaEventRecord(e1, ctx->stream));
   CU(cudaMemsetAsync(&ctx->b.st->np, 0, sizeof(int), ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   float t = 0.f;
   CU(cudaEventElapsedTime(&t, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  ctx->launches += repeats + 2;
   if (ms_each) *ms_each = (double)t / repeats;
   return EKF_OK;
 }

@@ -90,6 +90,10 @@ cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, c
 /* np_ptr: device int holding the number of pending terms (NULL = st->np); np_ub: host upper bound (selects the template) */
 cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* np_ptr, int np_ub, int L_ub,
                              cudaStream_t s);
+/* pipelined (TMA + mbarrier) form of the sweep; tmap = CUtensorMap of this rank's P; one pass per 8 pending terms */
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int np_ub, int L_ub,
+                                 int num_sms, cudaStream_t s);
+size_t ekf_sweep_tma_smem(void);
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                 int m, int L_ub, cudaStream_t s);
 cudaError_t ekf_launch_assemble(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int c0, int nc,

@@ -10,6 +10,7 @@
  */
 #include "ekf_internal.h"
 #include "ekf_device.cuh"
+#include <cuda.h>
 
 #define EKF_BLOCK 256
 
@@ -371,6 +372,131 @@ __global__ void __launch_bounds__(EKF_BLOCK, 2) k_sweep(EkfGeom g, EkfBuffers b,
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* THE roofline kernel, pipelined form (the one the library launches).  Same arithmetic as k_sweep above,
+ * organised for Blackwell: a persistent grid (one CTA per SM), one producer warp that streams 64x64 fp64
+ * tiles of P (32 KB, TMA 2-D tensor copy) plus the matching 64-entry slices of the pending K and K S
+ * terms (1 KB bulk copies) into a 4-deep shared-memory ring guarded by full/empty mbarriers, and eight
+ * consumer warps that pull a tile into registers, apply the rank-2 terms in reference order and store
+ * the result straight back to HBM with streaming stores.  The ring keeps ~190 KB per SM in flight, so
+ * the fp64 work of a rank-2m update (m <= 8 per pass) hides under the HBM stream instead of serialising
+ * with it.  No masks (see k_sweep). */
+#define SW_STAGES 4
+#define SW_CW 8                       /* consumer warps */
+#define SW_THREADS ((SW_CW + 1) * 32)
+#define SW_C 8                        /* pending terms per pass */
+
+struct __align__(128) SweepStage {
+  double P[EKF_TILE * EKF_TILE];      /* 32768 B, row-major 64 x 64, written by TMA */
+  double2 K[SW_C][EKF_TILE];          /* 8 x 1024 B: K_c for the tile's columns */
+  double2 KS[SW_C][EKF_TILE];         /* 8 x 1024 B: (K S)_c for the tile's rows */
+};
+struct SweepShared {
+  SweepStage stage[SW_STAGES];
+  unsigned long long full[SW_STAGES];
+  unsigned long long empty[SW_STAGES];
+  int meta[SW_STAGES][4];             /* local tile row k, rb, cb, valid */
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, int col, int row, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(col), "r"(row) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+k_sweep_tma(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, int c0) {
+  extern __shared__ unsigned char sw_raw[];
+  /* TMA destinations want 128-byte alignment; the launcher over-allocates by 1 KB for this round-up */
+  SweepShared& sh = *reinterpret_cast<SweepShared*>(sw_raw + ((1024u - (smem_u32(sw_raw) & 1023u)) & 1023u));
+  const int np_all = b.st->np;
+  const int np = min(SW_C, np_all - c0);
+  if (np <= 0) return;
+  const int nl = 3 + 2 * b.st->L;
+  const int T = (nl + EKF_TILE - 1) / EKF_TILE;
+  if (g.rank >= T) return;
+  const long long K_rows = (T - g.rank + g.world - 1) / g.world;
+  const long long total = tiles_before(T, g.rank, g.world, K_rows);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SW_STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], SW_CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == SW_CW) {
+    /* ---------------- producer: one elected lane ---------------- */
+    if (lane == 0) {
+      const unsigned bytes = EKF_TILE * EKF_TILE * sizeof(double) + 2u * np * EKF_TILE * sizeof(double2);
+      int it = 0;
+      for (long long idx = blockIdx.x; idx < total; idx += gridDim.x, ++it) {
+        const int s = it % SW_STAGES;
+        const unsigned ph = (it / SW_STAGES) & 1;
+        mbar_wait(&sh.empty[s], ph ^ 1);
+        const TileId t = decode_tile(T, g.rank, g.world, idx);
+        sh.meta[s][0] = t.k; sh.meta[s][1] = t.rb; sh.meta[s][2] = t.cb; sh.meta[s][3] = 1;
+        mbar_expect_tx(&sh.full[s], bytes);
+        tma_load_tile(sh.stage[s].P, &tmapP, t.cb * EKF_TILE, t.k * EKF_TILE, &sh.full[s]);
+        for (int c = 0; c < np; ++c) {
+          bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(c0 + c) * g.ld + (size_t)t.cb * EKF_TILE, EKF_TILE * sizeof(double2), &sh.full[s]);
+          bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(c0 + c) * g.ld + (size_t)t.rb * EKF_TILE, EKF_TILE * sizeof(double2), &sh.full[s]);
+        }
+      }
+    }
+    return;
+  }
+  /* ---------------- consumers ---------------- */
+  int it = 0;
+  for (long long idx = blockIdx.x; idx < total; idx += gridDim.x, ++it) {
+    const int s = it % SW_STAGES;
+    const unsigned ph = (it / SW_STAGES) & 1;
+    mbar_wait(&sh.full[s], ph);
+    const SweepStage& st = sh.stage[s];
+    const int k = sh.meta[s][0], cb = sh.meta[s][2];
+    const int r0 = warp * 8;
+    double2 p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = *reinterpret_cast<const double2*>(&st.P[(r0 + i) * EKF_TILE + 2 * lane]);
+    for (int c = 0; c < np; ++c) {
+      const double2 kq0 = st.K[c][2 * lane], kq1 = st.K[c][2 * lane + 1];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double2 ks = st.KS[c][r0 + i];
+        p[i].x = sub_rn(p[i].x, rank2(ks, kq0));
+        p[i].y = sub_rn(p[i].y, rank2(ks, kq1));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sh.empty[s]);
+    double* Pt = b.P + ((size_t)k * EKF_TILE + r0) * g.ld + (size_t)cb * EKF_TILE + 2 * lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) __stcs(reinterpret_cast<double2*>(Pt + (size_t)i * g.ld), p[i]);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Robot.cpp:702-716 then :776-866 phase A (per unmatched line: world-frame parameters, P_ll, and the
  * rows 0..2 of its new columns -- all functions of the 3x3 robot block only). */
 __global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, const double* __restrict__ z, const double* __restrict__ R, int m) {
@@ -626,6 +752,28 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
   else if (np_ub <= 4) k_sweep<4><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
   else k_sweep<8><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
   return cudaGetLastError();
+}
+size_t ekf_sweep_tma_smem(void) { return sizeof(SweepShared) + 1024; }
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int np_ub, int L_ub,
+                                 int num_sms, cudaStream_t s) {
+  const int tiles = ekf_sweep_grid_ub(g, L_ub);
+  if (tiles <= 0 || np_ub <= 0) return cudaSuccess;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ekf_sweep_tma_smem());
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmap);
+  for (int c0 = 0; c0 < np_ub; c0 += SW_C) {
+    k_sweep_tma<<<grid, SW_THREADS, ekf_sweep_tma_smem(), s>>>(g, b, *m, c0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                 int m, int L_ub, cudaStream_t s) {
