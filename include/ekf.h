@@ -40,6 +40,8 @@ enum {
 enum {
   EKF_FLAG_EAGER_SWEEP = 1,  /* sweep P after every matched line (one rank-2 pass per match, like the
                                 reference) instead of folding the scan's matches into one rank-2m pass */
+  EKF_FLAG_PER_LINE_KERNELS = 4, /* ekf_scan launches associate / gain / apply per line instead of the single
+                                    cluster kernel that walks all lines (same bits; A/B measurement) */
   EKF_FLAG_SWEEP_DIRECT = 2  /* use the plain load/compute/store sweep kernel instead of the TMA + mbarrier
                                 pipeline (same bits; kept for A/B measurement) */
 };

@@ -73,6 +73,7 @@ struct ekf_ctx {
   cudaEvent_t t0, t1;  /* ekf_timer_* */
   CUtensorMap tmapP;   /* 2-D tiled view of this rank's P for the TMA sweep */
   int num_sms;
+  int cluster;         /* CTAs in the line-loop cluster */
   /* sharded */
   ncclComm_t comm;
   /* staging for download / upload / stats */
@@ -252,6 +253,24 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
   if (ctx->L_ub == 0) {
     CU(ekf_launch_queue_all(ctx->g, ctx->b, m, ctx->stream));
     if (m > 0) ctx->launches++;
+  } else if (ctx->g.world == 1 && !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS))) {
+    /* fused: all lines in one cluster launch; split only where the pending list would overflow */
+    int i0 = 0;
+    while (i0 < m) {
+      int cnt = ctx->cfg.max_batch - ctx->pend_ub;
+      if (cnt > m - i0) cnt = m - i0;
+      CU(ekf_launch_scan_lines(ctx->g, ctx->b, d_z, d_R, i0, i0 + cnt, ctx->cluster, ctx->stream));
+      ctx->launches++;
+      ctx->pend_ub += cnt;
+      i0 += cnt;
+      if (i0 < m) {
+        int rc = sweep_now(ctx, ctx->pend_ub);
+        if (rc) return rc;
+        CU(ekf_launch_flush_done(ctx->b, i0, ctx->stream));
+        ctx->launches++;
+        ctx->pend_ub = 0;
+      }
+    }
   } else {
     for (int i = 0; i < m; ++i) {
       CU(ekf_launch_associate(ctx->g, ctx->b, d_z, d_R, i, ctx->L_ub, ctx->stream));
@@ -312,11 +331,13 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMalloc(&ctx->b.matched, (size_t)g.cap * sizeof(int)));
   CU(cudaMalloc(&ctx->b.Kp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
   CU(cudaMalloc(&ctx->b.KSp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
+  CU(cudaMalloc(&ctx->b.gates, 16 * (size_t)g.cap * sizeof(double)));
   CU(cudaMalloc(&ctx->b.colA, 2 * ld * sizeof(double)));
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { int rc = make_tensor_map(ctx, p_rows); if (rc) return rc; }
+  ctx->cluster = 8;
   CU(cudaMalloc(&ctx->d_partials, 3 * (size_t)g.n * sizeof(double)));
   CU(cudaMalloc(&ctx->d_out3, 3 * sizeof(double)));
   CU(cudaMemsetAsync(ctx->b.st, 0, sizeof(EkfDevState), ctx->stream));
@@ -413,7 +434,7 @@ int ekf_destroy(ekf_ctx* ctx) {
   if (ctx->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(ctx->comm); }
   free_line_tables(ctx);
   cudaFree(ctx->b.st); cudaFree(ctx->b.y); cudaFree(ctx->b.top); cudaFree(ctx->b.diag); cudaFree(ctx->b.P);
-  cudaFree(ctx->b.matched); cudaFree(ctx->b.Kp); cudaFree(ctx->b.KSp); cudaFree(ctx->b.colA);
+  cudaFree(ctx->b.matched); cudaFree(ctx->b.Kp); cudaFree(ctx->b.KSp); cudaFree(ctx->b.colA); cudaFree(ctx->b.gates);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_partials); cudaFree(ctx->d_out3);
   cudaFreeHost(ctx->h_st);
   for (size_t i = 0; i < ctx->ev.size(); ++i) cudaEventDestroy(ctx->ev[i]);

@@ -63,6 +63,7 @@ struct EkfBuffers {
   int* matched;
   double2* Kp;
   double2* KSp;
+  double* gates;      /* [cap][16]: gate record (c,s,g,S,Sinv,v,d2) of every landmark that passed the current line's gate */
   double* colA;       /* sharded mode: exchanged H-column slices */
   double* colB;
   /* per-scan line tables, sized max_lines (+1 for the prefix counters) */
@@ -85,6 +86,9 @@ cudaError_t ekf_launch_gain(const EkfGeom& g, const EkfBuffers& b, const double*
                             int line, int j_override, int mode, int L_ub, int max_batch, cudaStream_t s);
 cudaError_t ekf_launch_apply(const EkfGeom& g, const EkfBuffers& b, int line, int j_override, int L_ub,
                              cudaStream_t s);
+/* all lines [line0, line1) of the open scan in one cluster launch (single-GPU path) */
+cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
+                                  int line0, int line1, int cluster, cudaStream_t s);
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s);
 cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, cudaStream_t s);
 /* np_ptr: device int holding the number of pending terms (NULL = st->np); np_ub: host upper bound (selects the template) */

@@ -10,7 +10,10 @@
  */
 #include "ekf_internal.h"
 #include "ekf_device.cuh"
+#include <string.h>
 #include <cuda.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #define EKF_BLOCK 256
 
@@ -279,6 +282,143 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, in
     b.jout[line] = j;
     b.pidx[line + 1] = nm + 1; b.eidx[line + 1] = b.eidx[line];
     st->np = np + 1;                                                  /* read only by the next sweep */
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* All observed lines of a scan in ONE launch (single-GPU path): a thread-block cluster walks the lines
+ * in order; within a line the three phases (gate every landmark + first-fit, gain rows, hot updates +
+ * bookkeeping) are separated by hardware cluster barriers instead of kernel boundaries.  The phases are
+ * the bodies of k_associate / k_gain(mode 0) / k_apply; the winner's gate record travels through
+ * b.gates so it is evaluated once, as in the reference (Robot.cpp:367-489 feeds :516-602). */
+#define FL_THREADS 512
+#define GATE_REC 16                   /* doubles per landmark in b.gates */
+
+__device__ __forceinline__ void gate_store(double* rec, const Gate& G) {
+  rec[0] = G.c; rec[1] = G.s; rec[2] = G.g;
+  for (int t = 0; t < 4; ++t) { rec[3 + t] = G.S[t]; rec[7 + t] = G.Si[t]; }
+  rec[11] = G.v[0]; rec[12] = G.v[1]; rec[13] = G.d2;
+}
+__device__ __forceinline__ void gate_load(const double* rec, Gate& G) {
+  G.c = rec[0]; G.s = rec[1]; G.g = rec[2];
+  for (int t = 0; t < 4; ++t) { G.S[t] = rec[3 + t]; G.Si[t] = rec[7 + t]; }
+  G.v[0] = rec[11]; G.v[1] = rec[12]; G.d2 = rec[13]; G.singular = 0;
+}
+
+__global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
+                                                              const double* __restrict__ R, int line0, int line1) {
+  cg::cluster_group cl = cg::this_cluster();
+  __shared__ int s_min[FL_THREADS / 32];
+  __shared__ Gate sG;
+  EkfDevState* st = b.st;
+  const int gtid = (int)cl.block_rank() * blockDim.x + threadIdx.x;
+  const int gstride = (int)cl.num_blocks() * blockDim.x;
+  const int L = st->L, nl = 3 + 2 * L, epoch = st->epoch;
+  for (int line = line0; line < line1; ++line) {
+    /* ---- phase A: Robot.cpp:313-501 ---- */
+    {
+      const double xp[3] = {st->x_pre[0], st->x_pre[1], st->x_pre[2]};
+      const double Rl[4] = {R[4 * line], R[4 * line + 1], R[4 * line + 2], R[4 * line + 3]};
+      const double z0 = z[2 * line], z1 = z[2 * line + 1];
+      int cand = EKF_NO_MATCH;
+      for (int j = gtid; j < L; j += gstride) {
+        if (b.matched[j] == epoch) continue;
+        Gate G;
+        eval_gate(g, b, xp, j, z0, z1, Rl, G);
+        if (G.singular) { atomicOr(&st->sticky, EKF_STICKY_SINGULAR); continue; }
+        if (!(sqrt(fabs(G.d2)) > g.gate)) { cand = j; gate_store(b.gates + (size_t)GATE_REC * j, G); break; }
+      }
+      cand = __reduce_min_sync(0xffffffffu, cand);
+      if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        int v = (threadIdx.x < FL_THREADS / 32) ? s_min[threadIdx.x] : EKF_NO_MATCH;
+        v = __reduce_min_sync(0xffffffffu, v);
+        if (threadIdx.x == 0 && v != EKF_NO_MATCH) atomicMin(&b.jbest[line], v);
+      }
+    }
+    cl.sync();
+    const int j = b.jbest[line];
+    const int nm = b.pidx[line];
+    const int np = nm - st->pbase;
+    if (j == EKF_NO_MATCH) {                                          /* :309 / :325 / :493 */
+      if (gtid == 0) {
+        const int e = b.eidx[line];
+        b.ext[e] = line;
+        b.eidx[line + 1] = e + 1; b.pidx[line + 1] = nm; b.jout[line] = -1;
+      }
+      continue;
+    }
+    /* ---- phase B: Robot.cpp:516-560 ---- */
+    if (threadIdx.x == 0) gate_load(b.gates + (size_t)GATE_REC * j, sG);
+    __syncthreads();
+    {
+      const int a = 3 + 2 * j, bb = a + 1;
+      for (int r = gtid; r < nl; r += gstride) {
+        const int lo_a = min(r, a), hi_a = max(r, a), lo_b = min(r, bb), hi_b = max(r, bb);
+        const double pa = is_hot(lo_a, hi_a) ? hot_value(g, b, lo_a, hi_a) : cold_value(g, b, lo_a, hi_a, np);
+        const double pb = is_hot(lo_b, hi_b) ? hot_value(g, b, lo_b, hi_b) : cold_value(g, b, lo_b, hi_b, np);
+        double p0, p1, p2;
+        if (r <= 2) {
+          p0 = b.top[(size_t)min(r, 0) * g.ld + max(r, 0)];
+          p1 = b.top[(size_t)min(r, 1) * g.ld + max(r, 1)];
+          p2 = b.top[(size_t)min(r, 2) * g.ld + max(r, 2)];
+        } else {
+          p0 = b.top[r]; p1 = b.top[(size_t)g.ld + r]; p2 = b.top[(size_t)2 * g.ld + r];
+        }
+        double2 Kr, KSr;
+        gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
+        b.Kp[(size_t)np * g.ld + r] = Kr;
+        b.KSp[(size_t)np * g.ld + r] = KSr;
+      }
+    }
+    cl.sync();
+    /* ---- phase C: Robot.cpp:564-602 on the hot elements ---- */
+    {
+      const double2* K = b.Kp + (size_t)np * g.ld;
+      const double2* KS = b.KSp + (size_t)np * g.ld;
+      const double v0 = sG.v[0], v1 = sG.v[1];
+      const double2 ks0 = KS[0], ks1 = KS[1], ks2 = KS[2];
+      for (int q = 3 + gtid; q < nl; q += gstride) {
+        const double2 kq = K[q];
+        b.top[q] = sub_rn(b.top[q], rank2(ks0, kq));
+        b.top[(size_t)g.ld + q] = sub_rn(b.top[(size_t)g.ld + q], rank2(ks1, kq));
+        b.top[(size_t)2 * g.ld + q] = sub_rn(b.top[(size_t)2 * g.ld + q], rank2(ks2, kq));
+        const double2 ksq = KS[q];
+        const int jj = (q - 3) >> 1;
+        if (q & 1) {
+          b.diag[4 * jj] = sub_rn(b.diag[4 * jj], rank2(ksq, kq));
+          b.diag[4 * jj + 1] = sub_rn(b.diag[4 * jj + 1], rank2(ksq, K[q + 1]));
+        } else {
+          b.diag[4 * jj + 2] = sub_rn(b.diag[4 * jj + 2], rank2(ksq, kq));
+        }
+        double t = 0.0;
+        axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
+        b.y[q] = add_rn(b.y[q], t);
+      }
+      if (gtid == 0) {
+        const double2 kk[3] = {K[0], K[1], K[2]};
+        const double2 ks[3] = {ks0, ks1, ks2};
+        for (int r = 0; r < 3; ++r)
+          for (int q = r; q < 3; ++q)
+            b.top[(size_t)r * g.ld + q] = sub_rn(b.top[(size_t)r * g.ld + q], rank2(ks[r], kk[q]));
+        double yn[3];
+        for (int r = 0; r < 3; ++r) {
+          double t = 0.0;
+          axpy_skip(t, kk[r].x, v0); axpy_skip(t, kk[r].y, v1);
+          yn[r] = add_rn(st->x_pre[r], t);
+        }
+        normalize_radian(yn[2]);
+        for (int r = 0; r < 3; ++r) { b.y[r] = yn[r]; st->pose[r] = yn[r]; st->x_pre[r] = yn[r]; }
+        st->v[0] = v0; st->v[1] = v1;
+        for (int t = 0; t < 4; ++t) st->S[t] = sG.S[t];
+        b.matched[j] = epoch;
+        b.jout[line] = j;
+        b.pidx[line + 1] = nm + 1; b.eidx[line + 1] = b.eidx[line];
+        st->np = np + 1;
+      }
+    }
+    cl.sync();
   }
 }
 
@@ -725,6 +865,18 @@ cudaError_t ekf_launch_apply(const EkfGeom& g, const EkfBuffers& b, int line, in
                              cudaStream_t s) {
   k_apply<<<blocks_for(3 + 2 * L_ub, 2048), EKF_BLOCK, 0, s>>>(g, b, line, j_override);
   return cudaGetLastError();
+}
+cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
+                                  int line0, int line1, int cluster, cudaStream_t s) {
+  if (line1 <= line0) return cudaSuccess;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(cluster); cfg.blockDim = dim3(FL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_scan_lines, g, b, d_z, d_R, line0, line1);
 }
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
   k_flush_done<<<1, 32, 0, s>>>(b, next_line);

@@ -14,6 +14,7 @@ _lib = None
 EKF_OK, EKF_EINVAL, EKF_ECAPACITY, EKF_ESINGULAR, EKF_ECUDA, EKF_ENCCL, EKF_ENOMEM, EKF_ESTATE = range(8)
 EKF_FLAG_EAGER_SWEEP = 1
 EKF_FLAG_SWEEP_DIRECT = 2
+EKF_FLAG_PER_LINE_KERNELS = 4
 _STATUS = {0: "OK", 1: "EINVAL", 2: "ECAPACITY", 3: "ESINGULAR", 4: "ECUDA", 5: "ENCCL", 6: "ENOMEM", 7: "ESTATE"}
 
 _dp = C.POINTER(C.c_double)

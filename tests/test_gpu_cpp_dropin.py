@@ -1,0 +1,57 @@
+"""The C++ host side (include/ekf_robot.hpp) compiled with g++ against libekfcuda.so and driven like the
+reference node drives Robot::localize; results checked against the CPU oracle."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from slam_ros_b200 import scenario as sc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def test_cpp_robot_dropin_matches_oracle(libekf):
+    from oracle.oracle import StructuredOracle
+    from slam_ros_b200 import library_path
+    steps = 150
+    room = sc.room_scenario(steps=steps, range_sigma=5e-5)
+    maxl = room["z"].shape[1]
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "dropin"); fin = os.path.join(d, "in.bin"); fout = os.path.join(d, "out.bin")
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), library_path(),
+                               "-Wl,-rpath," + os.path.dirname(library_path()), "-o", exe])
+        with open(fin, "wb") as f:
+            np.array([steps, maxl], dtype=np.int32).tofile(f)
+            room["count"].astype(np.int32).tofile(f)
+            room["u"].astype(np.float64).tofile(f)
+            room["z"].astype(np.float64).tofile(f)
+            room["R"].astype(np.float64).tofile(f)
+        subprocess.check_call([exe, fin, fout])
+        out = np.fromfile(fout, dtype=np.float64)
+    rec = out[:4 * steps].reshape(steps, 4)
+    ell = out[4 * steps:4 * steps + 4]
+    n = int(out[4 * steps + 4])
+    y = out[4 * steps + 5:4 * steps + 5 + n]
+    P = out[4 * steps + 5 + n:4 * steps + 5 + n + n * n].reshape(n, n)
+    n_intervals = int(out[-1])
+    so = StructuredOracle(100)
+    added = 0
+    for s in range(steps):
+        m = room["count"][s]
+        L0 = so.lines
+        enc = sc.encoder_for(so.pose, room["u"][s])
+        st, j = so.localize(room["z"][s, :m], room["R"][s, :m], enc)
+        assert so.lines == int(rec[s, 3]), "line count at step %d" % s
+        assert np.abs(so.pose - rec[s, :3]).max() < 1e-9, "pose at step %d" % s
+        added += int((j < 0).sum())
+    assert n == so.n
+    assert np.abs(y - so.y_full()).max() / np.abs(so.y_full()).max() < 1e-9
+    assert np.abs(P - so.P_full()).max() / np.abs(so.P_full()).max() < 1e-9
+    ok, ax, ang = so.get_ellipse()
+    assert ell[0] == 1.0 and np.allclose(ell[1:3], ax, rtol=1e-5)
+    assert n_intervals == 4 * added          # two end points (x, y) per appended line, Robot.cpp:869-879

@@ -148,21 +148,26 @@ def test_map_scenario_every_step(libekf, oracle_cls, N, steps, m, seed):
     print("min gate margin |d - 0.4| = %.3e over %d gates" % (stats["min_margin"], stats["gates"]))
 
 
-def test_eager_sweep_equals_deferred(libekf):
-    """One rank-2 sweep per match (reference-like) and one rank-2m sweep per scan give identical bits."""
+def test_all_launch_strategies_give_identical_bits(libekf):
+    """Deferred rank-2m sweep (default: cluster line-loop kernel + TMA-pipelined sweep) vs one rank-2 sweep
+    per match (reference-like), per-line kernels, the direct sweep kernel and forced mid-scan flushes."""
     from slam_ros_b200 import EkfFilter
-    from slam_ros_b200.ekf import EKF_FLAG_EAGER_SWEEP
+    from slam_ros_b200.ekf import EKF_FLAG_EAGER_SWEEP, EKF_FLAG_SWEEP_DIRECT, EKF_FLAG_PER_LINE_KERNELS
     scn = sc.map_scenario(80, 40, m=8, seed=9)
-    fa = EkfFilter(capacity_lines=128)
-    fb = EkfFilter(capacity_lines=128, flags=EKF_FLAG_EAGER_SWEEP)
-    fc = EkfFilter(capacity_lines=128, max_batch=3)       # forces mid-scan flushes
-    for f in (fa, fb, fc):
+    variants = [EkfFilter(capacity_lines=128),
+                EkfFilter(capacity_lines=128, flags=EKF_FLAG_EAGER_SWEEP),
+                EkfFilter(capacity_lines=128, max_batch=3),                      # forces mid-scan flushes
+                EkfFilter(capacity_lines=128, flags=EKF_FLAG_PER_LINE_KERNELS),
+                EkfFilter(capacity_lines=128, flags=EKF_FLAG_SWEEP_DIRECT),
+                EkfFilter(capacity_lines=128, flags=EKF_FLAG_PER_LINE_KERNELS | EKF_FLAG_SWEEP_DIRECT, max_batch=5)]
+    for f in variants:
         f.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
     for s in range(40):
-        outs = [f.scan(scn["u"][s], scn["z"][s], scn["R"][s]) for f in (fa, fb, fc)]
-        assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], outs[2][1])
-    ya, Pa, La = fa.download_live()
-    for f in (fb, fc):
+        outs = [f.scan(scn["u"][s], scn["z"][s], scn["R"][s]) for f in variants]
+        for o in outs[1:]:
+            assert np.array_equal(outs[0][1], o[1]) and np.array_equal(outs[0][2], o[2])
+    ya, Pa, La = variants[0].download_live()
+    for f in variants[1:]:
         y, P, L = f.download_live()
         assert L == La and np.array_equal(y, ya) and np.array_equal(P, Pa)
 
