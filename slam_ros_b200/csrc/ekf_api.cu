@@ -337,7 +337,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { int rc = make_tensor_map(ctx, p_rows); if (rc) return rc; }
-  ctx->cluster = 8;
+  ctx->cluster = ekf_pick_cluster();
   CU(cudaMalloc(&ctx->d_partials, 3 * (size_t)g.n * sizeof(double)));
   CU(cudaMalloc(&ctx->d_out3, 3 * sizeof(double)));
   CU(cudaMemsetAsync(ctx->b.st, 0, sizeof(EkfDevState), ctx->stream));

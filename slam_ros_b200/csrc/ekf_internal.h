@@ -86,6 +86,7 @@ cudaError_t ekf_launch_gain(const EkfGeom& g, const EkfBuffers& b, const double*
                             int line, int j_override, int mode, int L_ub, int max_batch, cudaStream_t s);
 cudaError_t ekf_launch_apply(const EkfGeom& g, const EkfBuffers& b, int line, int j_override, int L_ub,
                              cudaStream_t s);
+int ekf_pick_cluster(void);
 /* all lines [line0, line1) of the open scan in one cluster launch (single-GPU path) */
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                   int line0, int line1, int cluster, cudaStream_t s);

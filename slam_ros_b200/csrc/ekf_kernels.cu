@@ -305,39 +305,127 @@ __device__ __forceinline__ void gate_load(const double* rec, Gate& G) {
   G.v[0] = rec[11]; G.v[1] = rec[12]; G.d2 = rec[13]; G.singular = 0;
 }
 
+/* Hot update of the robot block replica (3x3 of P, pose) for the pending term `np`: Robot.cpp:564-568 on
+ * rows/cols 0..2 and :579-602.  Every CTA keeps an identical replica in shared memory. */
+__device__ __forceinline__ void update_robot_block(const EkfGeom& g, const EkfBuffers& b, int np, const double v[2],
+                                                   double A[3][3], double xp[3]) {
+  const double2* K = b.Kp + (size_t)np * g.ld;
+  const double2* KS = b.KSp + (size_t)np * g.ld;
+  const double2 kk[3] = {K[0], K[1], K[2]};
+  const double2 ks[3] = {KS[0], KS[1], KS[2]};
+  for (int r = 0; r < 3; ++r)
+    for (int q = r; q < 3; ++q) { A[r][q] = sub_rn(A[r][q], rank2(ks[r], kk[q])); A[q][r] = A[r][q]; }
+  double yn[3];
+  for (int r = 0; r < 3; ++r) {
+    double t = 0.0;
+    axpy_skip(t, kk[r].x, v[0]); axpy_skip(t, kk[r].y, v[1]);
+    yn[r] = add_rn(xp[r], t);
+  }
+  normalize_radian(yn[2]);
+  xp[0] = yn[0]; xp[1] = yn[1]; xp[2] = yn[2];
+}
+
 __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
                                                               const double* __restrict__ R, int line0, int line1) {
   cg::cluster_group cl = cg::this_cluster();
   __shared__ int s_min[FL_THREADS / 32];
-  __shared__ Gate sG;
+  __shared__ Gate sG;                 /* gate record of the most recent matched line */
+  __shared__ double s_A[3][3];        /* replica of P[0:3,0:3] (full, mirrored) */
+  __shared__ double s_xp[3];          /* replica of x_pre */
   EkfDevState* st = b.st;
   const int gtid = (int)cl.block_rank() * blockDim.x + threadIdx.x;
   const int gstride = (int)cl.num_blocks() * blockDim.x;
   const int L = st->L, nl = 3 + 2 * L, epoch = st->epoch;
-  for (int line = line0; line < line1; ++line) {
-    /* ---- phase A: Robot.cpp:313-501 ---- */
-    {
-      const double xp[3] = {st->x_pre[0], st->x_pre[1], st->x_pre[2]};
-      const double Rl[4] = {R[4 * line], R[4 * line + 1], R[4 * line + 2], R[4 * line + 3]};
-      const double z0 = z[2 * line], z1 = z[2 * line + 1];
-      int cand = EKF_NO_MATCH;
-      for (int j = gtid; j < L; j += gstride) {
-        if (b.matched[j] == epoch) continue;
-        Gate G;
-        eval_gate(g, b, xp, j, z0, z1, Rl, G);
-        if (G.singular) { atomicOr(&st->sticky, EKF_STICKY_SINGULAR); continue; }
-        if (!(sqrt(fabs(G.d2)) > g.gate)) { cand = j; gate_store(b.gates + (size_t)GATE_REC * j, G); break; }
+  if (threadIdx.x == 0) {
+    load_rr(g, b.top, s_A);
+    s_xp[0] = st->x_pre[0]; s_xp[1] = st->x_pre[1]; s_xp[2] = st->x_pre[2];
+  }
+  __syncthreads();
+  bool have_prev = false;             /* a matched line whose hot update has not been applied yet */
+  int np_prev = 0;
+  /* iteration `line1` only applies the last pending hot update */
+  for (int line = line0; line <= line1; ++line) {
+    const bool gating = line < line1;
+    if (!gating && !have_prev) break;
+    /* ---- phase C of the previous match fused with phase A of this line ---- */
+    if (have_prev) {
+      if (threadIdx.x == 0) {
+        double A[3][3], xp[3] = {s_xp[0], s_xp[1], s_xp[2]};
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) A[r][q] = s_A[r][q];
+        update_robot_block(g, b, np_prev, sG.v, A, xp);
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) s_A[r][q] = A[r][q];
+        s_xp[0] = xp[0]; s_xp[1] = xp[1]; s_xp[2] = xp[2];
+        if (gtid == 0) {              /* one writer publishes the replica */
+          for (int r = 0; r < 3; ++r) {
+            for (int q = r; q < 3; ++q) b.top[(size_t)r * g.ld + q] = A[r][q];
+            b.y[r] = xp[r]; st->pose[r] = xp[r]; st->x_pre[r] = xp[r];
+          }
+          st->v[0] = sG.v[0]; st->v[1] = sG.v[1];
+          for (int t = 0; t < 4; ++t) st->S[t] = sG.S[t];
+        }
       }
-      cand = __reduce_min_sync(0xffffffffu, cand);
-      if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
       __syncthreads();
-      if (threadIdx.x < 32) {
-        int v = (threadIdx.x < FL_THREADS / 32) ? s_min[threadIdx.x] : EKF_NO_MATCH;
-        v = __reduce_min_sync(0xffffffffu, v);
-        if (threadIdx.x == 0 && v != EKF_NO_MATCH) atomicMin(&b.jbest[line], v);
+    }
+    double A[3][3];
+    for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) A[r][q] = s_A[r][q];
+    const double xp[3] = {s_xp[0], s_xp[1], s_xp[2]};
+    double Rl[4] = {0, 0, 0, 0}, z0 = 0, z1 = 0;
+    if (gating) {
+      Rl[0] = R[4 * line]; Rl[1] = R[4 * line + 1]; Rl[2] = R[4 * line + 2]; Rl[3] = R[4 * line + 3];
+      z0 = z[2 * line]; z1 = z[2 * line + 1];
+    }
+    const double2* Kv = b.Kp + (size_t)np_prev * g.ld;
+    const double2* KSv = b.KSp + (size_t)np_prev * g.ld;
+    double2 ks0 = make_double2(0, 0), ks1 = ks0, ks2 = ks0;
+    double pv0 = 0, pv1 = 0;
+    if (have_prev) { ks0 = KSv[0]; ks1 = KSv[1]; ks2 = KSv[2]; pv0 = sG.v[0]; pv1 = sG.v[1]; }
+    int cand = EKF_NO_MATCH;
+    for (int j = gtid; j < L; j += gstride) {
+      const int a = 3 + 2 * j, bb = a + 1;
+      double t0a = b.top[a], t0b = b.top[bb];
+      double t1a = b.top[(size_t)g.ld + a], t1b = b.top[(size_t)g.ld + bb];
+      double t2a = b.top[(size_t)2 * g.ld + a], t2b = b.top[(size_t)2 * g.ld + bb];
+      double daa = b.diag[4 * j], dab = b.diag[4 * j + 1], dbb = b.diag[4 * j + 2];
+      double ya = b.y[a], yb = b.y[bb];
+      if (have_prev) {                                                /* Robot.cpp:564-589 on this landmark's hot elements */
+        const double2 ka = Kv[a], kb = Kv[bb], ksa = KSv[a], ksb = KSv[bb];
+        t0a = sub_rn(t0a, rank2(ks0, ka)); t0b = sub_rn(t0b, rank2(ks0, kb));
+        t1a = sub_rn(t1a, rank2(ks1, ka)); t1b = sub_rn(t1b, rank2(ks1, kb));
+        t2a = sub_rn(t2a, rank2(ks2, ka)); t2b = sub_rn(t2b, rank2(ks2, kb));
+        daa = sub_rn(daa, rank2(ksa, ka)); dab = sub_rn(dab, rank2(ksa, kb)); dbb = sub_rn(dbb, rank2(ksb, kb));
+        double ta = 0.0, tb = 0.0;
+        axpy_skip(ta, ka.x, pv0); axpy_skip(ta, ka.y, pv1);
+        axpy_skip(tb, kb.x, pv0); axpy_skip(tb, kb.y, pv1);
+        ya = add_rn(ya, ta); yb = add_rn(yb, tb);
+        b.top[a] = t0a; b.top[bb] = t0b;
+        b.top[(size_t)g.ld + a] = t1a; b.top[(size_t)g.ld + bb] = t1b;
+        b.top[(size_t)2 * g.ld + a] = t2a; b.top[(size_t)2 * g.ld + bb] = t2b;
+        b.diag[4 * j] = daa; b.diag[4 * j + 1] = dab; b.diag[4 * j + 2] = dbb;
+        b.y[a] = ya; b.y[bb] = yb;
+      }
+      if (gating && cand == EKF_NO_MATCH && b.matched[j] != epoch) {  /* Robot.cpp:313-501 */
+        double Cm[5][5];
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) Cm[r][q] = A[r][q];
+        Cm[0][3] = Cm[3][0] = t0a; Cm[0][4] = Cm[4][0] = t0b;
+        Cm[1][3] = Cm[3][1] = t1a; Cm[1][4] = Cm[4][1] = t1b;
+        Cm[2][3] = Cm[3][2] = t2a; Cm[2][4] = Cm[4][2] = t2b;
+        Cm[3][3] = daa; Cm[3][4] = Cm[4][3] = dab; Cm[4][4] = dbb;
+        Gate G;
+        gate_from_block(Cm, ya, yb, xp, z0, z1, Rl, G);
+        if (G.singular) atomicOr(&st->sticky, EKF_STICKY_SINGULAR);
+        else if (!(sqrt(fabs(G.d2)) > g.gate)) { cand = j; gate_store(b.gates + (size_t)GATE_REC * j, G); }
       }
     }
-    cl.sync();
+    if (!gating) break;
+    cand = __reduce_min_sync(0xffffffffu, cand);
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int v = (threadIdx.x < FL_THREADS / 32) ? s_min[threadIdx.x] : EKF_NO_MATCH;
+      v = __reduce_min_sync(0xffffffffu, v);
+      if (threadIdx.x == 0 && v != EKF_NO_MATCH) atomicMin(&b.jbest[line], v);
+    }
+    cl.sync();                                                        /* hot state current, winner known */
     const int j = b.jbest[line];
     const int nm = b.pidx[line];
     const int np = nm - st->pbase;
@@ -347,6 +435,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
         b.ext[e] = line;
         b.eidx[line + 1] = e + 1; b.pidx[line + 1] = nm; b.jout[line] = -1;
       }
+      have_prev = false;
       continue;
     }
     /* ---- phase B: Robot.cpp:516-560 ---- */
@@ -356,69 +445,26 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
       const int a = 3 + 2 * j, bb = a + 1;
       for (int r = gtid; r < nl; r += gstride) {
         const int lo_a = min(r, a), hi_a = max(r, a), lo_b = min(r, bb), hi_b = max(r, bb);
-        const double pa = is_hot(lo_a, hi_a) ? hot_value(g, b, lo_a, hi_a) : cold_value(g, b, lo_a, hi_a, np);
-        const double pb = is_hot(lo_b, hi_b) ? hot_value(g, b, lo_b, hi_b) : cold_value(g, b, lo_b, hi_b, np);
+        const double pa = is_hot(lo_a, hi_a) ? (hi_a <= 2 ? A[lo_a][hi_a] : hot_value(g, b, lo_a, hi_a)) : cold_value(g, b, lo_a, hi_a, np);
+        const double pb = is_hot(lo_b, hi_b) ? (hi_b <= 2 ? A[lo_b][hi_b] : hot_value(g, b, lo_b, hi_b)) : cold_value(g, b, lo_b, hi_b, np);
         double p0, p1, p2;
-        if (r <= 2) {
-          p0 = b.top[(size_t)min(r, 0) * g.ld + max(r, 0)];
-          p1 = b.top[(size_t)min(r, 1) * g.ld + max(r, 1)];
-          p2 = b.top[(size_t)min(r, 2) * g.ld + max(r, 2)];
-        } else {
-          p0 = b.top[r]; p1 = b.top[(size_t)g.ld + r]; p2 = b.top[(size_t)2 * g.ld + r];
-        }
+        if (r <= 2) { p0 = A[r][0]; p1 = A[r][1]; p2 = A[r][2]; }
+        else { p0 = b.top[r]; p1 = b.top[(size_t)g.ld + r]; p2 = b.top[(size_t)2 * g.ld + r]; }
         double2 Kr, KSr;
         gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
         b.Kp[(size_t)np * g.ld + r] = Kr;
         b.KSp[(size_t)np * g.ld + r] = KSr;
       }
-    }
-    cl.sync();
-    /* ---- phase C: Robot.cpp:564-602 on the hot elements ---- */
-    {
-      const double2* K = b.Kp + (size_t)np * g.ld;
-      const double2* KS = b.KSp + (size_t)np * g.ld;
-      const double v0 = sG.v[0], v1 = sG.v[1];
-      const double2 ks0 = KS[0], ks1 = KS[1], ks2 = KS[2];
-      for (int q = 3 + gtid; q < nl; q += gstride) {
-        const double2 kq = K[q];
-        b.top[q] = sub_rn(b.top[q], rank2(ks0, kq));
-        b.top[(size_t)g.ld + q] = sub_rn(b.top[(size_t)g.ld + q], rank2(ks1, kq));
-        b.top[(size_t)2 * g.ld + q] = sub_rn(b.top[(size_t)2 * g.ld + q], rank2(ks2, kq));
-        const double2 ksq = KS[q];
-        const int jj = (q - 3) >> 1;
-        if (q & 1) {
-          b.diag[4 * jj] = sub_rn(b.diag[4 * jj], rank2(ksq, kq));
-          b.diag[4 * jj + 1] = sub_rn(b.diag[4 * jj + 1], rank2(ksq, K[q + 1]));
-        } else {
-          b.diag[4 * jj + 2] = sub_rn(b.diag[4 * jj + 2], rank2(ksq, kq));
-        }
-        double t = 0.0;
-        axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
-        b.y[q] = add_rn(b.y[q], t);
-      }
-      if (gtid == 0) {
-        const double2 kk[3] = {K[0], K[1], K[2]};
-        const double2 ks[3] = {ks0, ks1, ks2};
-        for (int r = 0; r < 3; ++r)
-          for (int q = r; q < 3; ++q)
-            b.top[(size_t)r * g.ld + q] = sub_rn(b.top[(size_t)r * g.ld + q], rank2(ks[r], kk[q]));
-        double yn[3];
-        for (int r = 0; r < 3; ++r) {
-          double t = 0.0;
-          axpy_skip(t, kk[r].x, v0); axpy_skip(t, kk[r].y, v1);
-          yn[r] = add_rn(st->x_pre[r], t);
-        }
-        normalize_radian(yn[2]);
-        for (int r = 0; r < 3; ++r) { b.y[r] = yn[r]; st->pose[r] = yn[r]; st->x_pre[r] = yn[r]; }
-        st->v[0] = v0; st->v[1] = v1;
-        for (int t = 0; t < 4; ++t) st->S[t] = sG.S[t];
+      if (gtid == 0) {                                                /* :501-504 bookkeeping (read after the next barrier) */
         b.matched[j] = epoch;
         b.jout[line] = j;
         b.pidx[line + 1] = nm + 1; b.eidx[line + 1] = b.eidx[line];
         st->np = np + 1;
       }
     }
-    cl.sync();
+    cl.sync();                                                        /* K, K S complete */
+    have_prev = true;
+    np_prev = np;
   }
 }
 
@@ -865,6 +911,24 @@ cudaError_t ekf_launch_apply(const EkfGeom& g, const EkfBuffers& b, int line, in
                              cudaStream_t s) {
   k_apply<<<blocks_for(3 + 2 * L_ub, 2048), EKF_BLOCK, 0, s>>>(g, b, line, j_override);
   return cudaGetLastError();
+}
+/* largest cluster (16, else 8) the device can co-schedule for the line-loop kernel */
+int ekf_pick_cluster(void) {
+  cudaFuncSetAttribute(k_scan_lines, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  const int tries[2] = {16, 8};
+  for (int t = 0; t < 2; ++t) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(tries[t]); cfg.blockDim = dim3(FL_THREADS);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = tries[t]; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines, &cfg) == cudaSuccess && n >= 1) return tries[t];
+  }
+  (void)cudaGetLastError();
+  return 8;
 }
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                   int line0, int line1, int cluster, cudaStream_t s) {
