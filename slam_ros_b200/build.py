@@ -39,7 +39,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("EKF_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT, "-ldl"]
     env = dict(os.environ)
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)

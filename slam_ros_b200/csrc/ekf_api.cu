@@ -253,7 +253,7 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
   if (ctx->L_ub == 0) {
     CU(ekf_launch_queue_all(ctx->g, ctx->b, m, ctx->stream));
     if (m > 0) ctx->launches++;
-  } else if (ctx->g.world == 1 && !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS))) {
+  } else if (ctx->g.world == 1 && ctx->cfg.max_batch <= 64 && !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS))) {
     /* fused: all lines in one cluster launch; split only where the pending list would overflow */
     int i0 = 0;
     while (i0 < m) {

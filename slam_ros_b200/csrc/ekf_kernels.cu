@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, in
  * the bodies of k_associate / k_gain(mode 0) / k_apply; the winner's gate record travels through
  * b.gates so it is evaluated once, as in the reference (Robot.cpp:367-489 feeds :516-602). */
 #define FL_THREADS 512
+#define FL_MAXP 64                    /* upper bound of max_batch for the fused path */
 #define GATE_REC 16                   /* doubles per landmark in b.gates */
 
 __device__ __forceinline__ void gate_store(double* rec, const Gate& G) {
@@ -305,70 +306,121 @@ __device__ __forceinline__ void gate_load(const double* rec, Gate& G) {
   G.v[0] = rec[11]; G.v[1] = rec[12]; G.d2 = rec[13]; G.singular = 0;
 }
 
-/* Hot update of the robot block replica (3x3 of P, pose) for the pending term `np`: Robot.cpp:564-568 on
- * rows/cols 0..2 and :579-602.  Every CTA keeps an identical replica in shared memory. */
-__device__ __forceinline__ void update_robot_block(const EkfGeom& g, const EkfBuffers& b, int np, const double v[2],
+/* Hot update of the robot block (3x3 of P, pose) for one pending term: Robot.cpp:564-568 on rows/cols 0..2
+ * and :579-602.  Every thread of the line-loop kernel keeps its own identical copy in registers. */
+__device__ __forceinline__ void update_robot_block(const double2 kk[3], const double2 ks[3], double v0, double v1,
                                                    double A[3][3], double xp[3]) {
-  const double2* K = b.Kp + (size_t)np * g.ld;
-  const double2* KS = b.KSp + (size_t)np * g.ld;
-  const double2 kk[3] = {K[0], K[1], K[2]};
-  const double2 ks[3] = {KS[0], KS[1], KS[2]};
   for (int r = 0; r < 3; ++r)
     for (int q = r; q < 3; ++q) { A[r][q] = sub_rn(A[r][q], rank2(ks[r], kk[q])); A[q][r] = A[r][q]; }
   double yn[3];
   for (int r = 0; r < 3; ++r) {
     double t = 0.0;
-    axpy_skip(t, kk[r].x, v[0]); axpy_skip(t, kk[r].y, v[1]);
+    axpy_skip(t, kk[r].x, v0); axpy_skip(t, kk[r].y, v1);
     yn[r] = add_rn(xp[r], t);
   }
   normalize_radian(yn[2]);
   xp[0] = yn[0]; xp[1] = yn[1]; xp[2] = yn[2];
 }
 
+/* one row of the gain phase: everything that has to come from memory, issued as independent loads */
+struct GainRow {
+  double p0, p1, p2, pa, pb;
+  double2 v[8];          /* first chunk of the row's pending terms (K S row entries or K column entries) */
+  int kind;              /* 0: hot (no corrections), 1: column part (r < a), 2: row part (r > b) */
+};
+__device__ __forceinline__ void gain_row_load(const EkfGeom& g, const EkfBuffers& b, const double A[3][3], int r, int j,
+                                              int np, GainRow& d) {
+  const int a = 3 + 2 * j, bb = a + 1;
+  d.kind = 0;
+  if (r <= 2) {
+    d.p0 = A[r][0]; d.p1 = A[r][1]; d.p2 = A[r][2];
+    d.pa = b.top[(size_t)r * g.ld + a]; d.pb = b.top[(size_t)r * g.ld + bb];
+    return;
+  }
+  d.p0 = b.top[r]; d.p1 = b.top[(size_t)g.ld + r]; d.p2 = b.top[(size_t)2 * g.ld + r];
+  if (r == a) { d.pa = b.diag[4 * j]; d.pb = b.diag[4 * j + 1]; }
+  else if (r == bb) { d.pa = b.diag[4 * j + 1]; d.pb = b.diag[4 * j + 2]; }
+  else if (r < a) {                                                   /* column parts: P[r,a], P[r,b] */
+    const double* Pr = b.P + local_row(g, r) * g.ld;
+    d.pa = Pr[a]; d.pb = Pr[bb];
+    d.kind = 1;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) if (t < np) d.v[t] = b.KSp[(size_t)t * g.ld + r];
+  } else {                                                            /* row parts: P[a,r], P[b,r] */
+    d.pa = b.P[local_row(g, a) * g.ld + r]; d.pb = b.P[local_row(g, bb) * g.ld + r];
+    d.kind = 2;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) if (t < np) d.v[t] = b.Kp[(size_t)t * g.ld + r];
+  }
+}
+__device__ __forceinline__ void gain_row_finish(const EkfGeom& g, const EkfBuffers& b, const Gate& G, int r, int np,
+                                                GainRow& d, const double2* s_ka, const double2* s_kb,
+                                                const double2* s_ksa, const double2* s_ksb) {
+  if (d.kind == 1) {
+    for (int i0 = 0; i0 < np; i0 += 8) {
+      if (i0 > 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) if (i0 + t < np) d.v[t] = b.KSp[(size_t)(i0 + t) * g.ld + r];
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) if (i0 + t < np) {
+        d.pa = sub_rn(d.pa, rank2(d.v[t], s_ka[i0 + t]));
+        d.pb = sub_rn(d.pb, rank2(d.v[t], s_kb[i0 + t]));
+      }
+    }
+  } else if (d.kind == 2) {
+    for (int i0 = 0; i0 < np; i0 += 8) {
+      if (i0 > 0) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) if (i0 + t < np) d.v[t] = b.Kp[(size_t)(i0 + t) * g.ld + r];
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) if (i0 + t < np) {
+        d.pa = sub_rn(d.pa, rank2(s_ksa[i0 + t], d.v[t]));
+        d.pb = sub_rn(d.pb, rank2(s_ksb[i0 + t], d.v[t]));
+      }
+    }
+  }
+  double2 Kr, KSr;
+  gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Kr, KSr);
+  b.Kp[(size_t)np * g.ld + r] = Kr;
+  b.KSp[(size_t)np * g.ld + r] = KSr;
+}
+
+#ifdef EKF_LINE_TIMING
+__device__ unsigned long long g_line_ts[64 * 16];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TS(slot) do { if (gtid == 0 && line - line0 < 64) g_line_ts[(line - line0) * 16 + (slot)] = gtimer(); } while (0)
+#else
+#define TS(slot) do { } while (0)
+#endif
+
+/* Dependency chain per line: [landmark data + previous K] -> gate -> atomicMin -> barrier -> [winner]
+ * -> [gate record + row data] -> gain -> barrier: three memory round trips and two cluster barriers. */
 __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
                                                               const double* __restrict__ R, int line0, int line1) {
   cg::cluster_group cl = cg::this_cluster();
   __shared__ int s_min[FL_THREADS / 32];
-  __shared__ Gate sG;                 /* gate record of the most recent matched line */
-  __shared__ double s_A[3][3];        /* replica of P[0:3,0:3] (full, mirrored) */
-  __shared__ double s_xp[3];          /* replica of x_pre */
+  __shared__ double2 s_ka[FL_MAXP], s_kb[FL_MAXP], s_ksa[FL_MAXP], s_ksb[FL_MAXP];
   EkfDevState* st = b.st;
   const int gtid = (int)cl.block_rank() * blockDim.x + threadIdx.x;
   const int gstride = (int)cl.num_blocks() * blockDim.x;
-  const int L = st->L, nl = 3 + 2 * L, epoch = st->epoch;
-  if (threadIdx.x == 0) {
-    load_rr(g, b.top, s_A);
-    s_xp[0] = st->x_pre[0]; s_xp[1] = st->x_pre[1]; s_xp[2] = st->x_pre[2];
-  }
-  __syncthreads();
+  const int L = st->L, nl = 3 + 2 * L, epoch = st->epoch, pbase = st->pbase;
+  int nm = b.pidx[line0];             /* matches of this scan so far: tracked identically by every thread */
+  int ne = b.eidx[line0];
+  double A[3][3], xp[3];              /* every thread's own copy of P[0:3,0:3] (mirrored) and x_pre */
+  load_rr(g, b.top, A);
+  xp[0] = st->x_pre[0]; xp[1] = st->x_pre[1]; xp[2] = st->x_pre[2];
   bool have_prev = false;             /* a matched line whose hot update has not been applied yet */
   int np_prev = 0;
+  double pv0 = 0.0, pv1 = 0.0;        /* its innovation */
+  double pS[4] = {0, 0, 0, 0};
   /* iteration `line1` only applies the last pending hot update */
   for (int line = line0; line <= line1; ++line) {
     const bool gating = line < line1;
     if (!gating && !have_prev) break;
+    TS(0);
     /* ---- phase C of the previous match fused with phase A of this line ---- */
-    if (have_prev) {
-      if (threadIdx.x == 0) {
-        double A[3][3], xp[3] = {s_xp[0], s_xp[1], s_xp[2]};
-        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) A[r][q] = s_A[r][q];
-        update_robot_block(g, b, np_prev, sG.v, A, xp);
-        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) s_A[r][q] = A[r][q];
-        s_xp[0] = xp[0]; s_xp[1] = xp[1]; s_xp[2] = xp[2];
-        if (gtid == 0) {              /* one writer publishes the replica */
-          for (int r = 0; r < 3; ++r) {
-            for (int q = r; q < 3; ++q) b.top[(size_t)r * g.ld + q] = A[r][q];
-            b.y[r] = xp[r]; st->pose[r] = xp[r]; st->x_pre[r] = xp[r];
-          }
-          st->v[0] = sG.v[0]; st->v[1] = sG.v[1];
-          for (int t = 0; t < 4; ++t) st->S[t] = sG.S[t];
-        }
-      }
-      __syncthreads();
-    }
-    double A[3][3];
-    for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) A[r][q] = s_A[r][q];
-    const double xp[3] = {s_xp[0], s_xp[1], s_xp[2]};
     double Rl[4] = {0, 0, 0, 0}, z0 = 0, z1 = 0;
     if (gating) {
       Rl[0] = R[4 * line]; Rl[1] = R[4 * line + 1]; Rl[2] = R[4 * line + 2]; Rl[3] = R[4 * line + 3];
@@ -376,10 +428,12 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
     }
     const double2* Kv = b.Kp + (size_t)np_prev * g.ld;
     const double2* KSv = b.KSp + (size_t)np_prev * g.ld;
-    double2 ks0 = make_double2(0, 0), ks1 = ks0, ks2 = ks0;
-    double pv0 = 0, pv1 = 0;
-    if (have_prev) { ks0 = KSv[0]; ks1 = KSv[1]; ks2 = KSv[2]; pv0 = sG.v[0]; pv1 = sG.v[1]; }
+    double2 ks[3], kk[3];
+    if (have_prev) {
+      for (int r = 0; r < 3; ++r) { ks[r] = KSv[r]; kk[r] = Kv[r]; }
+    }
     int cand = EKF_NO_MATCH;
+    bool robot_done = !have_prev;
     for (int j = gtid; j < L; j += gstride) {
       const int a = 3 + 2 * j, bb = a + 1;
       double t0a = b.top[a], t0b = b.top[bb];
@@ -387,11 +441,12 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
       double t2a = b.top[(size_t)2 * g.ld + a], t2b = b.top[(size_t)2 * g.ld + bb];
       double daa = b.diag[4 * j], dab = b.diag[4 * j + 1], dbb = b.diag[4 * j + 2];
       double ya = b.y[a], yb = b.y[bb];
+      const int mt = b.matched[j];
       if (have_prev) {                                                /* Robot.cpp:564-589 on this landmark's hot elements */
         const double2 ka = Kv[a], kb = Kv[bb], ksa = KSv[a], ksb = KSv[bb];
-        t0a = sub_rn(t0a, rank2(ks0, ka)); t0b = sub_rn(t0b, rank2(ks0, kb));
-        t1a = sub_rn(t1a, rank2(ks1, ka)); t1b = sub_rn(t1b, rank2(ks1, kb));
-        t2a = sub_rn(t2a, rank2(ks2, ka)); t2b = sub_rn(t2b, rank2(ks2, kb));
+        t0a = sub_rn(t0a, rank2(ks[0], ka)); t0b = sub_rn(t0b, rank2(ks[0], kb));
+        t1a = sub_rn(t1a, rank2(ks[1], ka)); t1b = sub_rn(t1b, rank2(ks[1], kb));
+        t2a = sub_rn(t2a, rank2(ks[2], ka)); t2b = sub_rn(t2b, rank2(ks[2], kb));
         daa = sub_rn(daa, rank2(ksa, ka)); dab = sub_rn(dab, rank2(ksa, kb)); dbb = sub_rn(dbb, rank2(ksb, kb));
         double ta = 0.0, tb = 0.0;
         axpy_skip(ta, ka.x, pv0); axpy_skip(ta, ka.y, pv1);
@@ -403,7 +458,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
         b.diag[4 * j] = daa; b.diag[4 * j + 1] = dab; b.diag[4 * j + 2] = dbb;
         b.y[a] = ya; b.y[bb] = yb;
       }
-      if (gating && cand == EKF_NO_MATCH && b.matched[j] != epoch) {  /* Robot.cpp:313-501 */
+      if (!robot_done) { update_robot_block(kk, ks, pv0, pv1, A, xp); robot_done = true; }
+      if (gating && cand == EKF_NO_MATCH && mt != epoch) {            /* Robot.cpp:313-501 */
         double Cm[5][5];
         for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) Cm[r][q] = A[r][q];
         Cm[0][3] = Cm[3][0] = t0a; Cm[0][4] = Cm[4][0] = t0b;
@@ -416,7 +472,17 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
         else if (!(sqrt(fabs(G.d2)) > g.gate)) { cand = j; gate_store(b.gates + (size_t)GATE_REC * j, G); }
       }
     }
+    if (!robot_done) update_robot_block(kk, ks, pv0, pv1, A, xp);    /* threads without a landmark of their own */
+    if (have_prev && gtid == 0) {     /* one writer publishes the robot block */
+      for (int r = 0; r < 3; ++r) {
+        for (int q = r; q < 3; ++q) b.top[(size_t)r * g.ld + q] = A[r][q];
+        b.y[r] = xp[r]; st->pose[r] = xp[r]; st->x_pre[r] = xp[r];
+      }
+      st->v[0] = pv0; st->v[1] = pv1;
+      for (int t = 0; t < 4; ++t) st->S[t] = pS[t];
+    }
     if (!gating) break;
+    TS(1);
     cand = __reduce_min_sync(0xffffffffu, cand);
     if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
     __syncthreads();
@@ -425,46 +491,51 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
       v = __reduce_min_sync(0xffffffffu, v);
       if (threadIdx.x == 0 && v != EKF_NO_MATCH) atomicMin(&b.jbest[line], v);
     }
+    TS(2);
     cl.sync();                                                        /* hot state current, winner known */
+    TS(3);
     const int j = b.jbest[line];
-    const int nm = b.pidx[line];
-    const int np = nm - st->pbase;
+    const int np = nm - pbase;
     if (j == EKF_NO_MATCH) {                                          /* :309 / :325 / :493 */
-      if (gtid == 0) {
-        const int e = b.eidx[line];
-        b.ext[e] = line;
-        b.eidx[line + 1] = e + 1; b.pidx[line + 1] = nm; b.jout[line] = -1;
-      }
+      if (gtid == 0) { b.ext[ne] = line; b.eidx[line + 1] = ne + 1; b.pidx[line + 1] = nm; b.jout[line] = -1; }
+      ne += 1;
       have_prev = false;
       continue;
     }
     /* ---- phase B: Robot.cpp:516-560 ---- */
-    if (threadIdx.x == 0) gate_load(b.gates + (size_t)GATE_REC * j, sG);
-    __syncthreads();
-    {
-      const int a = 3 + 2 * j, bb = a + 1;
-      for (int r = gtid; r < nl; r += gstride) {
-        const int lo_a = min(r, a), hi_a = max(r, a), lo_b = min(r, bb), hi_b = max(r, bb);
-        const double pa = is_hot(lo_a, hi_a) ? (hi_a <= 2 ? A[lo_a][hi_a] : hot_value(g, b, lo_a, hi_a)) : cold_value(g, b, lo_a, hi_a, np);
-        const double pb = is_hot(lo_b, hi_b) ? (hi_b <= 2 ? A[lo_b][hi_b] : hot_value(g, b, lo_b, hi_b)) : cold_value(g, b, lo_b, hi_b, np);
-        double p0, p1, p2;
-        if (r <= 2) { p0 = A[r][0]; p1 = A[r][1]; p2 = A[r][2]; }
-        else { p0 = b.top[r]; p1 = b.top[(size_t)g.ld + r]; p2 = b.top[(size_t)2 * g.ld + r]; }
-        double2 Kr, KSr;
-        gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
-        b.Kp[(size_t)np * g.ld + r] = Kr;
-        b.KSp[(size_t)np * g.ld + r] = KSr;
-      }
-      if (gtid == 0) {                                                /* :501-504 bookkeeping (read after the next barrier) */
-        b.matched[j] = epoch;
-        b.jout[line] = j;
-        b.pidx[line + 1] = nm + 1; b.eidx[line + 1] = b.eidx[line];
-        st->np = np + 1;
-      }
+    const int a = 3 + 2 * j, bb = a + 1;
+    Gate G;
+    gate_load(b.gates + (size_t)GATE_REC * j, G);
+    /* the pending terms' entries at a and b are the same for every row: stage them once per CTA */
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+      s_ka[i] = b.Kp[(size_t)i * g.ld + a]; s_kb[i] = b.Kp[(size_t)i * g.ld + bb];
+      s_ksa[i] = b.KSp[(size_t)i * g.ld + a]; s_ksb[i] = b.KSp[(size_t)i * g.ld + bb];
     }
+    GainRow d;
+    int r = gtid;
+    TS(4);
+    if (r < nl) gain_row_load(g, b, A, r, j, np, d);
+    __syncthreads();
+    TS(5);
+    while (r < nl) {
+      gain_row_finish(g, b, G, r, np, d, s_ka, s_kb, s_ksa, s_ksb);
+      r += gstride;
+      if (r < nl) gain_row_load(g, b, A, r, j, np, d);
+    }
+    if (gtid == 0) {                                                  /* :501-504 bookkeeping (read after the next barrier) */
+      b.matched[j] = epoch;
+      b.jout[line] = j;
+      b.pidx[line + 1] = nm + 1; b.eidx[line + 1] = ne;
+      st->np = np + 1;
+    }
+    TS(6);
     cl.sync();                                                        /* K, K S complete */
+    TS(7);
     have_prev = true;
     np_prev = np;
+    nm += 1;
+    pv0 = G.v[0]; pv1 = G.v[1];
+    for (int t = 0; t < 4; ++t) pS[t] = G.S[t];
   }
 }
 
@@ -913,6 +984,11 @@ cudaError_t ekf_launch_apply(const EkfGeom& g, const EkfBuffers& b, int line, in
   return cudaGetLastError();
 }
 /* largest cluster (16, else 8) the device can co-schedule for the line-loop kernel */
+#ifdef EKF_LINE_TIMING
+extern "C" int ekf_debug_line_timing(unsigned long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_line_ts, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 int ekf_pick_cluster(void) {
   cudaFuncSetAttribute(k_scan_lines, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   const int tries[2] = {16, 8};
