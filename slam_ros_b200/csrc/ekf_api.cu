@@ -74,6 +74,7 @@ struct ekf_ctx {
   CUtensorMap tmapP;   /* 2-D tiled view of this rank's P for the TMA sweep */
   int num_sms;
   int cluster;         /* CTAs in the line-loop cluster */
+  int sweep_shape;     /* 0: 64x64 tiles, 1: 32x128, 2: 16x256 (EKF_SWEEP_SHAPE) */
   /* sharded */
   ncclComm_t comm;
   /* staging for download / upload / stats */
@@ -147,7 +148,9 @@ int make_tensor_map(ekf_ctx* ctx, size_t p_rows) {
   if (!fn || q != cudaDriverEntryPointSuccess) { snprintf(ctx->err, sizeof ctx->err, "cuTensorMapEncodeTiled not available"); return EKF_ECUDA; }
   const cuuint64_t gdim[2] = {(cuuint64_t)ctx->g.ld, (cuuint64_t)p_rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ctx->g.ld * sizeof(double)};
-  const cuuint32_t box[2] = {EKF_TILE, EKF_TILE};
+  int tr = 64, tc = 64;
+  ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
+  const cuuint32_t box[2] = {(cuuint32_t)tc, (cuuint32_t)tr};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = ((EncodeTiledFn)fn)(&ctx->tmapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->b.P, gdim, gstride, box, estr,
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -161,7 +164,7 @@ int launch_sweep(ekf_ctx* ctx, int np_ub) {
     CU(ekf_launch_sweep(ctx->g, ctx->b, 0, np_ub, ctx->L_ub, ctx->stream));
     ctx->launches++;
   } else {
-    CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmapP, np_ub, ctx->L_ub, ctx->num_sms, ctx->stream));
+    CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmapP, ctx->sweep_shape, np_ub, ctx->L_ub, ctx->num_sms, ctx->stream));
     ctx->launches += (np_ub + 7) / 8;
   }
   return EKF_OK;
@@ -317,7 +320,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   EkfGeom& g = ctx->g;
   g.cap = cfg->capacity_lines;
   g.n = 3 + 2 * g.cap;
-  g.ld = ((g.n + EKF_TILE - 1) / EKF_TILE) * EKF_TILE;
+  g.ld = ((g.n + EKF_LD_ALIGN - 1) / EKF_LD_ALIGN) * EKF_LD_ALIGN;
   g.rank = rank; g.world = world;
   g.gate = cfg->gate; g.enc_noise = cfg->encoder_noise; g.headroom = cfg->reset_headroom;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -336,6 +339,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || ctx->sweep_shape > 5 || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
   { int rc = make_tensor_map(ctx, p_rows); if (rc) return rc; }
   ctx->cluster = ekf_pick_cluster();
   CU(cudaMalloc(&ctx->d_partials, 3 * (size_t)g.n * sizeof(double)));

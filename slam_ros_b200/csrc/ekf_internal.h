@@ -1,7 +1,7 @@
 /* ekf_internal.h -- shared between the kernels (ekf_kernels.cu) and the C ABI (ekf_api.cu).
  *
- * HBM layout of one filter.  n = 3 + 2*capacity, ld = n rounded up to 64 doubles
- * (512 B) so every 64-column tile starts on a 512-byte boundary.
+ * HBM layout of one filter.  n = 3 + 2*capacity, ld = n rounded up to 256 doubles
+ * (2 KB) so every sweep tile (64, 128 or 256 columns wide) lies inside a row.
  *
  *   y     [ld]            state vector (Robot.h:26)
  *   top   [3][ld]         rows 0..2 of P (robot rows), upper part authoritative            -- "hot"
@@ -23,6 +23,7 @@
 #include <limits.h>
 
 #define EKF_TILE 64
+#define EKF_LD_ALIGN 256                /* ld is a multiple of the widest sweep tile (256 columns) */
 #define EKF_NO_MATCH INT_MAX
 #define EKF_STICKY_CAPACITY 1
 #define EKF_STICKY_SINGULAR 2
@@ -95,10 +96,11 @@ cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, c
 /* np_ptr: device int holding the number of pending terms (NULL = st->np); np_ub: host upper bound (selects the template) */
 cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* np_ptr, int np_ub, int L_ub,
                              cudaStream_t s);
-/* pipelined (TMA + mbarrier) form of the sweep; tmap = CUtensorMap of this rank's P; one pass per 8 pending terms */
-cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int np_ub, int L_ub,
+/* pipelined (TMA + mbarrier) form of the sweep; tmap = CUtensorMap of this rank's P with box (tc, tr) of
+ * ekf_sweep_shape(shape); one pass per 8 pending terms */
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int shape, int np_ub, int L_ub,
                                  int num_sms, cudaStream_t s);
-size_t ekf_sweep_tma_smem(void);
+void ekf_sweep_shape(int shape, int* tr, int* tc);
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                 int m, int L_ub, cudaStream_t s);
 cudaError_t ekf_launch_assemble(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int c0, int nc,

@@ -637,21 +637,20 @@ __global__ void __launch_bounds__(EKF_BLOCK, 2) k_sweep(EkfGeom g, EkfBuffers b,
  * the result straight back to HBM with streaming stores.  The ring keeps ~190 KB per SM in flight, so
  * the fp64 work of a rank-2m update (m <= 8 per pass) hides under the HBM stream instead of serialising
  * with it.  No masks (see k_sweep). */
-#define SW_STAGES 4
-#define SW_CW 8                       /* consumer warps */
-#define SW_THREADS ((SW_CW + 1) * 32)
 #define SW_C 8                        /* pending terms per pass */
 
+template <int TR, int TC>
 struct __align__(128) SweepStage {
-  double P[EKF_TILE * EKF_TILE];      /* 32768 B, row-major 64 x 64, written by TMA */
-  double2 K[SW_C][EKF_TILE];          /* 8 x 1024 B: K_c for the tile's columns */
-  double2 KS[SW_C][EKF_TILE];         /* 8 x 1024 B: (K S)_c for the tile's rows */
+  double P[TR * TC];                  /* 32768 B, row-major TR x TC, written by TMA */
+  double2 K[SW_C][TC];                /* K_c for the tile's columns */
+  double2 KS[SW_C][TR];               /* (K S)_c for the tile's rows */
 };
+template <int TR, int TC, int STAGES>
 struct SweepShared {
-  SweepStage stage[SW_STAGES];
-  unsigned long long full[SW_STAGES];
-  unsigned long long empty[SW_STAGES];
-  int meta[SW_STAGES][4];             /* local tile row k, rb, cb, valid */
+  SweepStage<TR, TC> stage[STAGES];
+  unsigned long long full[STAGES];
+  unsigned long long empty[STAGES];
+  int meta[STAGES][4];                /* first local row, first global row, first column, - */
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -684,72 +683,100 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 1)
-k_sweep_tma(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, int c0) {
+/* Tiles are TR rows x TC columns (TR*TC = 4096 doubles = 32 KB; TR <= 64 <= TC).  The upper triangle is
+ * covered by, for each 64-row ownership block gb (this rank's: gb = rank + world*k), the 64/TR sub-row
+ * blocks times the tile columns cb >= floor(64*gb / TC).  Tiles are numbered in that order; the
+ * producer walks its tiles in increasing order, so it decodes incrementally (no division, no sqrt). */
+template <int TR, int TC, int STAGES, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
+k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, int c0) {
+  typedef SweepShared<TR, TC, STAGES> Shared;
   extern __shared__ unsigned char sw_raw[];
   /* TMA destinations want 128-byte alignment; the launcher over-allocates by 1 KB for this round-up */
-  SweepShared& sh = *reinterpret_cast<SweepShared*>(sw_raw + ((1024u - (smem_u32(sw_raw) & 1023u)) & 1023u));
+  Shared& sh = *reinterpret_cast<Shared*>(sw_raw + ((1024u - (smem_u32(sw_raw) & 1023u)) & 1023u));
   const int np_all = b.st->np;
   const int np = min(SW_C, np_all - c0);
   if (np <= 0) return;
   const int nl = 3 + 2 * b.st->L;
-  const int T = (nl + EKF_TILE - 1) / EKF_TILE;
-  if (g.rank >= T) return;
-  const long long K_rows = (T - g.rank + g.world - 1) / g.world;
-  const long long total = tiles_before(T, g.rank, g.world, K_rows);
+  const int T64 = (nl + EKF_TILE - 1) / EKF_TILE;      /* 64-row ownership blocks in the live part */
+  const int Tc = (nl + TC - 1) / TC;                   /* tile columns */
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int SUB = EKF_TILE / TR;                   /* sub-row blocks per ownership block */
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SW_STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], SW_CW); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == SW_CW) {
+  if (warp == CW) {
     /* ---------------- producer: one elected lane ---------------- */
     if (lane == 0) {
-      const unsigned bytes = EKF_TILE * EKF_TILE * sizeof(double) + 2u * np * EKF_TILE * sizeof(double2);
+      const unsigned bytes = TR * TC * sizeof(double) + (unsigned)np * (TC + TR) * sizeof(double2);
+      int k = 0;                                        /* local ownership block */
+      int gb = g.rank;                                  /* its global index */
+      long long base = 0;                               /* index of the block's first tile */
+      int cb0 = (EKF_TILE * gb) / TC;
+      long long cnt = (gb < T64) ? (long long)SUB * (Tc - cb0) : 0;
       int it = 0;
-      for (long long idx = blockIdx.x; idx < total; idx += gridDim.x, ++it) {
-        const int s = it % SW_STAGES;
-        const unsigned ph = (it / SW_STAGES) & 1;
+      for (long long idx = blockIdx.x; gb < T64; idx += gridDim.x, ++it) {
+        while (gb < T64 && idx >= base + cnt) {
+          base += cnt; ++k; gb += g.world;
+          cb0 = (EKF_TILE * gb) / TC;
+          cnt = (gb < T64) ? (long long)SUB * (Tc - cb0) : 0;
+        }
+        if (gb >= T64) break;
+        const int rem = (int)(idx - base);
+        const int sub = rem / (Tc - cb0), cb = cb0 + rem % (Tc - cb0);
+        const int lrow0 = k * EKF_TILE + sub * TR, grow0 = gb * EKF_TILE + sub * TR, col0 = cb * TC;
+        const int s = it % STAGES;
+        const unsigned ph = (it / STAGES) & 1;
         mbar_wait(&sh.empty[s], ph ^ 1);
-        const TileId t = decode_tile(T, g.rank, g.world, idx);
-        sh.meta[s][0] = t.k; sh.meta[s][1] = t.rb; sh.meta[s][2] = t.cb; sh.meta[s][3] = 1;
+        sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
         mbar_expect_tx(&sh.full[s], bytes);
-        tma_load_tile(sh.stage[s].P, &tmapP, t.cb * EKF_TILE, t.k * EKF_TILE, &sh.full[s]);
+        tma_load_tile(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s]);
         for (int c = 0; c < np; ++c) {
-          bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(c0 + c) * g.ld + (size_t)t.cb * EKF_TILE, EKF_TILE * sizeof(double2), &sh.full[s]);
-          bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(c0 + c) * g.ld + (size_t)t.rb * EKF_TILE, EKF_TILE * sizeof(double2), &sh.full[s]);
+          bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(c0 + c) * g.ld + col0, TC * sizeof(double2), &sh.full[s]);
+          bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(c0 + c) * g.ld + grow0, TR * sizeof(double2), &sh.full[s]);
         }
       }
+      /* tell the consumers there is nothing more: a stage with valid = 0 */
+      const int s = it % STAGES;
+      const unsigned ph = (it / STAGES) & 1;
+      mbar_wait(&sh.empty[s], ph ^ 1);
+      sh.meta[s][3] = 0;
+      mbar_arrive(&sh.full[s]);
     }
     return;
   }
   /* ---------------- consumers ---------------- */
-  int it = 0;
-  for (long long idx = blockIdx.x; idx < total; idx += gridDim.x, ++it) {
-    const int s = it % SW_STAGES;
-    const unsigned ph = (it / SW_STAGES) & 1;
+  constexpr int WPR = TC / 64;                          /* warps across one tile row */
+  constexpr int RPP = CW / WPR;                         /* rows per pass */
+  constexpr int PT = TR / RPP;                          /* rows per thread */
+  const int ccol = ((warp % WPR) * 32 + lane) * 2;      /* this lane's two columns inside the tile */
+  const int crow = warp / WPR;
+  for (int it = 0;; ++it) {
+    const int s = it % STAGES;
+    const unsigned ph = (it / STAGES) & 1;
     mbar_wait(&sh.full[s], ph);
-    const SweepStage& st = sh.stage[s];
-    const int k = sh.meta[s][0], cb = sh.meta[s][2];
-    const int r0 = warp * 8;
-    double2 p[8];
+    if (!sh.meta[s][3]) break;
+    const SweepStage<TR, TC>& st = sh.stage[s];
+    const int lrow0 = sh.meta[s][0], col0 = sh.meta[s][2];
+    double2 p[PT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = *reinterpret_cast<const double2*>(&st.P[(r0 + i) * EKF_TILE + 2 * lane]);
+    for (int i = 0; i < PT; ++i) p[i] = *reinterpret_cast<const double2*>(&st.P[(crow + i * RPP) * TC + ccol]);
     for (int c = 0; c < np; ++c) {
-      const double2 kq0 = st.K[c][2 * lane], kq1 = st.K[c][2 * lane + 1];
+      const double2 kq0 = st.K[c][ccol], kq1 = st.K[c][ccol + 1];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const double2 ks = st.KS[c][r0 + i];
+      for (int i = 0; i < PT; ++i) {
+        const double2 ks = st.KS[c][crow + i * RPP];
         p[i].x = sub_rn(p[i].x, rank2(ks, kq0));
         p[i].y = sub_rn(p[i].y, rank2(ks, kq1));
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sh.empty[s]);
-    double* Pt = b.P + ((size_t)k * EKF_TILE + r0) * g.ld + (size_t)cb * EKF_TILE + 2 * lane;
+    double* Pt = b.P + ((size_t)lrow0 + crow) * g.ld + (size_t)col0 + ccol;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) __stcs(reinterpret_cast<double2*>(Pt + (size_t)i * g.ld), p[i]);
+    for (int i = 0; i < PT; ++i) __stcs(reinterpret_cast<double2*>(Pt + (size_t)(i * RPP) * g.ld), p[i]);
   }
 }
 
@@ -1045,27 +1072,40 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
   else k_sweep<8><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
   return cudaGetLastError();
 }
-size_t ekf_sweep_tma_smem(void) { return sizeof(SweepShared) + 1024; }
-cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int np_ub, int L_ub,
-                                 int num_sms, cudaStream_t s) {
-  const int tiles = ekf_sweep_grid_ub(g, L_ub);
-  if (tiles <= 0 || np_ub <= 0) return cudaSuccess;
+template <int TR, int TC, int STAGES, int CW>
+static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, int np_ub, int grid, cudaStream_t s) {
+  const size_t smem = sizeof(SweepShared<TR, TC, STAGES>) + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ekf_sweep_tma_smem());
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_pipe<TR, TC, STAGES, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmap);
   for (int c0 = 0; c0 < np_ub; c0 += SW_C) {
-    k_sweep_tma<<<grid, SW_THREADS, ekf_sweep_tma_smem(), s>>>(g, b, *m, c0);
+    k_sweep_pipe<TR, TC, STAGES, CW><<<grid, (CW + 1) * 32, smem, s>>>(g, b, *m, c0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+void ekf_sweep_shape(int shape, int* tr, int* tc) {
+  switch (shape % 4) { case 1: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }
+}
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int shape, int np_ub, int L_ub,
+                                 int num_sms, cudaStream_t s) {
+  const int tiles = ekf_sweep_grid_ub(g, L_ub);
+  if (tiles <= 0 || np_ub <= 0) return cudaSuccess;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmap);
+  switch (shape) {       /* shape % 4: tile shape; shape / 4: 0 = 8 consumer warps, 1 = 16 */
+    case 1: return launch_sweep_shape<32, 128, 4, 8>(g, b, m, np_ub, grid, s);
+    case 2: return launch_sweep_shape<16, 256, 3, 8>(g, b, m, np_ub, grid, s);
+    case 4: return launch_sweep_shape<64, 64, 4, 16>(g, b, m, np_ub, grid, s);
+    case 5: return launch_sweep_shape<32, 128, 4, 16>(g, b, m, np_ub, grid, s);
+    default: return launch_sweep_shape<64, 64, 4, 8>(g, b, m, np_ub, grid, s);
+  }
 }
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                 int m, int L_ub, cudaStream_t s) {
