@@ -317,3 +317,63 @@ def test_large_map_properties(libekf, oracle_cls):
     tr, sm, sq = f.cov_stats()
     assert abs(tr - np.trace(P_o)) / abs(np.trace(P_o)) < TOL
     assert abs(sq - (P_o * P_o).sum()) / (P_o * P_o).sum() < 1e-8
+
+
+def test_thousand_steps_every_step(libekf, oracle_cls):
+    """north_star: association bit-exact and state/P within 1e-9 relative after EACH step over 1k steps."""
+    N, steps, m = 120, 1000, 8
+    scn = sc.map_scenario(N, steps, m=m, seed=31)
+    f, so = seed_pair(N, N + 400, oracle_cls, scn)
+    worst_y = worst_P = 0.0
+    for s in range(steps):
+        rc, j, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        st, jo = so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        assert rc == st
+        assert np.array_equal(j, jo), "association differs at step %d" % s
+        y_o, P_o = so.live()
+        y_g, P_g, L_g = f.download_live()
+        assert L_g == so.lines
+        worst_y = max(worst_y, rel(y_g, y_o)); worst_P = max(worst_P, rel(P_g, P_o))
+        assert worst_y < TOL and worst_P < TOL, "step %d: y %.2e P %.2e" % (s, worst_y, worst_P)
+    st = so.stats()
+    print("1000 steps: worst rel err y %.2e, P %.2e; min gate margin %.3e over %d gates; %d matches"
+          % (worst_y, worst_P, st["min_margin"], st["gates"], st["matches"]))
+
+
+@pytest.mark.parametrize("m", [32, 64])
+def test_batched_multi_line_updates(libekf, oracle_cls, m):
+    """configs[2]: m = 32 / 64 observed lines per step folded into one deferred rank-2m sweep."""
+    N, steps = 700, 6
+    scn = sc.map_scenario(N, steps, m=m, seed=50 + m, stride=m + 3)
+    f, so = seed_pair(N, N + 128, oracle_cls, scn)
+    for s in range(steps):
+        rc, j, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        st, jo = so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        assert np.array_equal(j, jo), "step %d" % s
+        compare_state(f, so, "m=%d step %d" % (m, s))
+    assert so.stats()["matches"] > 0.8 * steps * m
+
+
+def test_empty_and_ragged_scans(libekf, oracle_cls):
+    """Edge cases: scans with no lines, one line, lines on an empty map, duplicated observations of one landmark."""
+    from slam_ros_b200 import EkfFilter
+    scn = sc.map_scenario(20, 8, m=6, seed=13)
+    f = EkfFilter(capacity_lines=64); so = oracle_cls(64)
+    for o in (0, 1):                                   # empty map, empty scan
+        rc, j, pose = f.scan(scn["u"][0], np.zeros((0, 2)), np.zeros((0, 4)))
+        so.scan(scn["u"][0], np.zeros((0, 2)), np.zeros((0, 4)))
+    compare_state(f, so, "empty")
+    rc, j, pose = f.scan(np.zeros(3), scn["seed_z"][:1], scn["seed_R"][:1])       # a single line on the empty map
+    so.scan(np.zeros(3), scn["seed_z"][:1], scn["seed_R"][:1])
+    rc, j, pose = f.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])               # the first line now matches landmark 0
+    st, jo = so.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
+    assert np.array_equal(j, jo) and j[0] == 0
+    compare_state(f, so, "seed after single")
+    for s in range(8):
+        k = s % 5 + 1
+        z = np.concatenate([scn["z"][s, :k], scn["z"][s, :1]])                     # ragged + a duplicated observation
+        R = np.concatenate([scn["R"][s, :k], scn["R"][s, :1]])
+        rc, j, pose = f.scan(scn["u"][s], z, R)
+        st, jo = so.scan(scn["u"][s], z, R)
+        assert np.array_equal(j, jo), "step %d" % s
+    compare_state(f, so, "ragged")
