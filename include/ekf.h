@@ -42,6 +42,7 @@ enum {
                                 reference) instead of folding the scan's matches into one rank-2m pass */
   EKF_FLAG_PER_LINE_KERNELS = 4, /* ekf_scan launches associate / gain / apply per line instead of the single
                                     cluster kernel that walks all lines (same bits; A/B measurement) */
+  EKF_FLAG_NO_OVERLAP = 8,   /* do not double-buffer P / overlap a scan's sweep with the next scan's line loop */
   EKF_FLAG_SWEEP_DIRECT = 2  /* use the plain load/compute/store sweep kernel instead of the TMA + mbarrier
                                 pipeline (same bits; kept for A/B measurement) */
 };

@@ -71,7 +71,21 @@ struct ekf_ctx {
   std::vector<double> ev_bytes;
   long long launches;
   cudaEvent_t t0, t1;  /* ekf_timer_* */
-  CUtensorMap tmapP;   /* 2-D tiled view of this rank's P for the TMA sweep */
+  /* overlapped pipeline: the sweep of scan s runs on `wstream` while scan s+1's line loop runs on `stream`.
+   * P is double-buffered; a sweep reads Pbuf[x] and writes Pbuf[x^1].  `rd` is the buffer the line loop
+   * reads; `pg_*` describe the previous scan's pending terms that are not folded into Pbuf[rd] yet. */
+  int overlap;
+  cudaStream_t wstream;
+  double* Pbuf[2];
+  CUtensorMap tmap2[2];
+  CUtensorMap tmapK[2];        /* [0]: K bands (box = tile columns x 8 slots), [1]: K S bands (box = tile rows x 8 slots) */
+  int rd, par, group;
+  int pg_valid, pg_slot0;
+  EkfScanView* d_view;        /* [2] */
+  unsigned long long* d_counters;   /* tile counters of the sweep passes: [0,16) line stream, [16,32) sweep stream */
+  cudaEvent_t evE, evF[2];
+  int evF_used[2];
+  struct { int *jbest, *jout, *pidx, *eidx, *ext; double* ext_cs; } tab[2];
   int num_sms;
   int cluster;         /* CTAs in the line-loop cluster */
   int sweep_shape;     /* 0: 64x64 tiles, 1: 32x128, 2: 16x256 (EKF_SWEEP_SHAPE) */
@@ -95,20 +109,33 @@ namespace {
   } while (0)
 
 const size_t kStageElems = (size_t)8 << 20;   /* 64 MiB staging for download/upload */
+static int line_sms() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : 12; if (v < 1 || v > 64) v = 12; } return v; }
+#define EKF_LINE_SMS line_sms()               /* SMs reserved for the line loop while a sweep is in flight */
 
 double* in_u(ekf_ctx* c) { return c->d_in; }
 double* in_x(ekf_ctx* c) { return c->d_in + 3; }
 double* in_z(ekf_ctx* c) { return c->d_in + 6; }
 double* in_R(ekf_ctx* c) { return c->d_in + 6 + 2 * (size_t)c->max_lines; }
 
+void use_tables(ekf_ctx* ctx, int t) {
+  ctx->b.jbest = ctx->tab[t].jbest; ctx->b.jout = ctx->tab[t].jout; ctx->b.pidx = ctx->tab[t].pidx;
+  ctx->b.eidx = ctx->tab[t].eidx; ctx->b.ext = ctx->tab[t].ext; ctx->b.ext_cs = ctx->tab[t].ext_cs;
+}
+
 int free_line_tables(ekf_ctx* ctx) {
-  cudaFree(ctx->b.jbest); cudaFree(ctx->b.jout); cudaFree(ctx->b.pidx); cudaFree(ctx->b.eidx);
-  cudaFree(ctx->b.ext); cudaFree(ctx->b.ext_cs); cudaFree(ctx->d_in);
+  for (int t = 0; t < 2; ++t) {
+    cudaFree(ctx->tab[t].jbest); cudaFree(ctx->tab[t].jout); cudaFree(ctx->tab[t].pidx); cudaFree(ctx->tab[t].eidx);
+    cudaFree(ctx->tab[t].ext); cudaFree(ctx->tab[t].ext_cs);
+    memset(&ctx->tab[t], 0, sizeof ctx->tab[t]);
+  }
+  cudaFree(ctx->d_in);
   cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_jout);
   ctx->b.jbest = ctx->b.jout = ctx->b.pidx = ctx->b.eidx = ctx->b.ext = 0; ctx->b.ext_cs = 0; ctx->d_in = 0;
   ctx->h_in = 0; ctx->h_jout = 0;
   return 0;
 }
+
+int drain(ekf_ctx* ctx);
 
 /* (re)allocate everything sized by the number of lines in a scan; only legal between scans */
 int ensure_lines(ekf_ctx* ctx, int m) {
@@ -117,23 +144,27 @@ int ensure_lines(ekf_ctx* ctx, int m) {
     snprintf(ctx->err, sizeof ctx->err, "scan has more than %d lines; raise it by calling ekf_scan once with m lines", ctx->max_lines);
     return EKF_EINVAL;
   }
+  { int rc = drain(ctx); if (rc) return rc; }
   CU(cudaStreamSynchronize(ctx->stream));
   free_line_tables(ctx);
   int cap = ctx->max_lines > 0 ? ctx->max_lines : 64;
   while (cap < m) cap *= 2;
   ctx->max_lines = cap;
   const size_t n1 = (size_t)cap + 1;
-  CU(cudaMalloc(&ctx->b.jbest, n1 * sizeof(int)));
-  CU(cudaMalloc(&ctx->b.jout, n1 * sizeof(int)));
-  CU(cudaMalloc(&ctx->b.pidx, n1 * sizeof(int)));
-  CU(cudaMalloc(&ctx->b.eidx, n1 * sizeof(int)));
-  CU(cudaMalloc(&ctx->b.ext, n1 * sizeof(int)));
-  CU(cudaMalloc(&ctx->b.ext_cs, 2 * n1 * sizeof(double)));
+  for (int t = 0; t < 2; ++t) {
+    CU(cudaMalloc(&ctx->tab[t].jbest, n1 * sizeof(int)));
+    CU(cudaMalloc(&ctx->tab[t].jout, n1 * sizeof(int)));
+    CU(cudaMalloc(&ctx->tab[t].pidx, n1 * sizeof(int)));
+    CU(cudaMalloc(&ctx->tab[t].eidx, n1 * sizeof(int)));
+    CU(cudaMalloc(&ctx->tab[t].ext, n1 * sizeof(int)));
+    CU(cudaMalloc(&ctx->tab[t].ext_cs, 2 * n1 * sizeof(double)));
+    CU(cudaMemsetAsync(ctx->tab[t].pidx, 0, n1 * sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->tab[t].eidx, 0, n1 * sizeof(int), ctx->stream));
+  }
+  use_tables(ctx, 0);
   CU(cudaMalloc(&ctx->d_in, (6 + 6 * (size_t)cap) * sizeof(double)));
   CU(cudaMallocHost(&ctx->h_in, (6 + 6 * (size_t)cap) * sizeof(double)));
   CU(cudaMallocHost(&ctx->h_jout, n1 * sizeof(int)));
-  CU(cudaMemsetAsync(ctx->b.pidx, 0, n1 * sizeof(int), ctx->stream));
-  CU(cudaMemsetAsync(ctx->b.eidx, 0, n1 * sizeof(int), ctx->stream));
   return EKF_OK;
 }
 
@@ -141,7 +172,7 @@ int ensure_lines(ekf_ctx* ctx, int m) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_tensor_map(ekf_ctx* ctx, size_t p_rows) {
+int make_tensor_map(ekf_ctx* ctx, size_t p_rows, double* base, CUtensorMap* out) {
   void* fn = 0;
   cudaDriverEntryPointQueryResult q;
   CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -152,10 +183,27 @@ int make_tensor_map(ekf_ctx* ctx, size_t p_rows) {
   ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
   const cuuint32_t box[2] = {(cuuint32_t)tc, (cuuint32_t)tr};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = ((EncodeTiledFn)fn)(&ctx->tmapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->b.P, gdim, gstride, box, estr,
+  const CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(ctx->err, sizeof ctx->err, "cuTensorMapEncodeTiled failed: %d", (int)r); return EKF_ECUDA; }
+  return EKF_OK;
+}
+
+/* 2-D views of the pending lists: row = slot, inner dimension = 2*ld doubles (ld double2 entries) */
+int make_band_map(ekf_ctx* ctx, double2* base, int box_entries, CUtensorMap* out) {
+  void* fn = 0;
+  cudaDriverEntryPointQueryResult q;
+  CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) { snprintf(ctx->err, sizeof ctx->err, "cuTensorMapEncodeTiled not available"); return EKF_ECUDA; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)2 * ctx->g.ld, (cuuint64_t)ctx->cfg.max_batch};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ctx->g.ld * sizeof(double2)};
+  const cuuint32_t box[2] = {(cuuint32_t)(2 * box_entries), 8};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(ctx->err, sizeof ctx->err, "cuTensorMapEncodeTiled (band) failed: %d", (int)r); return EKF_ECUDA; }
   return EKF_OK;
 }
 
@@ -164,7 +212,8 @@ int launch_sweep(ekf_ctx* ctx, int np_ub) {
     CU(ekf_launch_sweep(ctx->g, ctx->b, 0, np_ub, ctx->L_ub, ctx->stream));
     ctx->launches++;
   } else {
-    CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmapP, ctx->sweep_shape, np_ub, ctx->L_ub, ctx->num_sms, ctx->stream));
+    CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmap2[ctx->rd], &ctx->tmapK[0], &ctx->tmapK[1], ctx->b.P, 0, 0, ctx->d_counters, ctx->sweep_shape, np_ub,
+                            ctx->L_ub, ctx->num_sms, ctx->stream));
     ctx->launches += (np_ub + 7) / 8;
   }
   return EKF_OK;
@@ -238,7 +287,7 @@ int enqueue_end(ekf_ctx* ctx, const double* d_z, const double* d_R, int m) {
   int rc = sweep_now(ctx, ctx->pend_ub);
   if (rc) return rc;
   ctx->pend_ub = 0;
-  CU(ekf_launch_end_scan(ctx->g, ctx->b, d_z, d_R, m, ctx->L_ub, ctx->stream));
+  CU(ekf_launch_end_scan(ctx->g, ctx->b, d_z, d_R, m, ctx->L_ub, 0, 0, ctx->stream));
   ctx->launches += (m > 0) ? 3 : 2;
   long long lub = (long long)ctx->L_ub + m;
   ctx->L_ub = (int)(lub > ctx->g.cap ? ctx->g.cap : lub);
@@ -247,8 +296,75 @@ int enqueue_end(ekf_ctx* ctx, const double* d_z, const double* d_R, int m) {
   return EKF_OK;
 }
 
+/* Waits for every sweep in flight and makes Pbuf[rd] the one complete, in-place-updatable covariance.
+ * Everything except the overlapped ekf_scan path works on that view. */
+int drain(ekf_ctx* ctx) {
+  if (!ctx->overlap) return EKF_OK;
+  CU(cudaStreamSynchronize(ctx->wstream));
+  if (ctx->pg_valid) { ctx->rd ^= 1; ctx->pg_valid = 0; }
+  ctx->b.P = ctx->Pbuf[ctx->rd];
+  ctx->evF_used[0] = ctx->evF_used[1] = 0;
+  return EKF_OK;
+}
+
+/* Overlapped form of one Robot::localize (single GPU, m <= group): the line stream runs predict, the
+ * line-loop cluster kernel and the end-of-scan kernels against Pbuf[rd] plus the previous scan's still
+ * pending terms; the sweep of THIS scan is handed to the sweep stream, where it runs while the next
+ * scan's line loop already executes.  Buffers: sweep(s) reads X and writes X^1; the next line loop
+ * reads X (complete once sweep(s-1) is done) plus this scan's pending terms. */
+int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, const double* d_z, const double* d_R) {
+  const int par = ctx->par;
+  if (ctx->evF_used[par]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evF[par], 0));   /* sweep(s-2): slots, tables, X complete */
+  use_tables(ctx, par);
+  const int slot0 = par * ctx->group;
+  EkfBuffers b = ctx->b;
+  b.P = ctx->Pbuf[ctx->rd];
+  CU(ekf_launch_predict(ctx->g, b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
+  /* The line loop runs as EKF_LINE_SMS cooperative CTAs on the SMs the in-flight sweep leaves free (its
+   * persistent grid is num_sms - EKF_LINE_SMS): no register / FP64-issue sharing with the sweep. */
+  CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, 0, m, EKF_LINE_SMS, 1, slot0, ctx->pg_slot0,
+                           ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->stream));
+  const int tgt = ctx->pg_valid ? (ctx->rd ^ 1) : ctx->rd;      /* source of this scan's sweep */
+  EkfBuffers bt = ctx->b;
+  bt.P = ctx->Pbuf[tgt];
+  CU(ekf_launch_end_scan(ctx->g, bt, d_z, d_R, m, ctx->L_ub, slot0, &ctx->d_view[par], ctx->stream));
+  ctx->launches += 5;
+  CU(cudaEventRecord(ctx->evE, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->wstream, ctx->evE, 0));
+  cudaEvent_t e0 = 0, e1 = 0;
+  if (ctx->prof) {
+    if (ctx->ev_used + 2 > ctx->ev.size())
+      for (int i = 0; i < 64; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e); }
+    e0 = ctx->ev[ctx->ev_used]; e1 = ctx->ev[ctx->ev_used + 1];
+    CU(cudaEventRecord(e0, ctx->wstream));
+  }
+  long long lub = (long long)ctx->L_ub + m;
+  const int L_after_ub = (int)(lub > ctx->g.cap ? ctx->g.cap : lub);
+  CU(ekf_launch_sweep_tma(ctx->g, bt, &ctx->tmap2[tgt], &ctx->tmapK[0], &ctx->tmapK[1], ctx->Pbuf[tgt ^ 1], slot0, &ctx->d_view[par], ctx->d_counters + 16,
+                          ctx->sweep_shape, m, L_after_ub, ctx->num_sms - EKF_LINE_SMS, ctx->wstream));
+  ctx->launches += 1;
+  if (ctx->prof) {
+    CU(cudaEventRecord(e1, ctx->wstream));
+    ctx->ev_used += 2;
+    ctx->ev_bytes.push_back((double)m);
+  }
+  CU(cudaEventRecord(ctx->evF[par], ctx->wstream));
+  ctx->evF_used[par] = 1;
+  ctx->rd = tgt; ctx->pg_valid = 1; ctx->pg_slot0 = slot0;
+  ctx->par ^= 1;
+  ctx->L_ub = L_after_ub;
+  ctx->b.P = ctx->Pbuf[ctx->rd];
+  return EKF_OK;
+}
+
 /* the whole Robot::localize, enqueued without returning to the host */
 int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, const double* d_z, const double* d_R) {
+  if (ctx->overlap) {
+    if (m >= 1 && m <= 8 && ctx->L_ub > 0) return enqueue_scan_overlapped(ctx, d_u, d_x_t0, m, d_z, d_R);
+    int rc = drain(ctx);
+    if (rc) return rc;
+    use_tables(ctx, 0);
+  }
   CU(ekf_launch_predict(ctx->g, ctx->b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
   ctx->launches++;
   ctx->pend_ub = 0;
@@ -262,7 +378,7 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
     while (i0 < m) {
       int cnt = ctx->cfg.max_batch - ctx->pend_ub;
       if (cnt > m - i0) cnt = m - i0;
-      CU(ekf_launch_scan_lines(ctx->g, ctx->b, d_z, d_R, i0, i0 + cnt, ctx->cluster, ctx->stream));
+      CU(ekf_launch_scan_lines(ctx->g, ctx->b, d_z, d_R, i0, i0 + cnt, ctx->cluster, 0, 0, 0, 0, ctx->stream));
       ctx->launches++;
       ctx->pend_ub += cnt;
       i0 += cnt;
@@ -310,6 +426,9 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->L_ub = 0; ctx->pend_ub = 0; ctx->scan_open = 0; ctx->cursor = 0;
   ctx->prof = 0; ctx->ev_used = 0; ctx->launches = 0; ctx->comm = 0; ctx->t0 = 0; ctx->t1 = 0;
   ctx->d_stage = 0; ctx->stage_elems = 0; ctx->d_partials = 0; ctx->d_out3 = 0;
+  ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8;
+  ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
+  ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);
   *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -331,6 +450,21 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMalloc(&ctx->b.top, 3 * ld * sizeof(double)));
   CU(cudaMalloc(&ctx->b.diag, 4 * (size_t)g.cap * sizeof(double)));
   CU(cudaMalloc(&ctx->b.P, p_rows * ld * sizeof(double)));
+  ctx->Pbuf[0] = ctx->b.P; ctx->Pbuf[1] = 0;
+  ctx->overlap = (world == 1 && ctx->cfg.max_batch >= 16 &&
+                  !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS | EKF_FLAG_SWEEP_DIRECT | EKF_FLAG_NO_OVERLAP))) ? 1 : 0;
+  ctx->group = 8;
+  if (ctx->overlap) {
+    CU(cudaMalloc(&ctx->Pbuf[1], p_rows * ld * sizeof(double)));
+    CU(cudaMemsetAsync(ctx->Pbuf[1], 0, p_rows * ld * sizeof(double), ctx->stream));
+    CU(cudaStreamCreateWithFlags(&ctx->wstream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->evE, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->evF[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->evF[1], cudaEventDisableTiming));
+  }
+  CU(cudaMalloc(&ctx->d_counters, 32 * sizeof(unsigned long long)));
+  CU(cudaMalloc(&ctx->d_view, 2 * sizeof(EkfScanView)));
+  CU(cudaMemsetAsync(ctx->d_view, 0, 2 * sizeof(EkfScanView), ctx->stream));
   CU(cudaMalloc(&ctx->b.matched, (size_t)g.cap * sizeof(int)));
   CU(cudaMalloc(&ctx->b.Kp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
   CU(cudaMalloc(&ctx->b.KSp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
@@ -339,9 +473,14 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || ctx->sweep_shape > 5 || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
-  { int rc = make_tensor_map(ctx, p_rows); if (rc) return rc; }
+  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
+  { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
+  if (ctx->overlap) { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[1], &ctx->tmap2[1]); if (rc) return rc; }
+  { int tr = 64, tc = 64; ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
+    int rc = make_band_map(ctx, ctx->b.Kp, tc, &ctx->tmapK[0]); if (rc) return rc;
+    rc = make_band_map(ctx, ctx->b.KSp, tr, &ctx->tmapK[1]); if (rc) return rc; }
   ctx->cluster = ekf_pick_cluster();
+  if (ctx->overlap) ekf_prefer_max_smem_carveout();
   CU(cudaMalloc(&ctx->d_partials, 3 * (size_t)g.n * sizeof(double)));
   CU(cudaMalloc(&ctx->d_out3, 3 * sizeof(double)));
   CU(cudaMemsetAsync(ctx->b.st, 0, sizeof(EkfDevState), ctx->stream));
@@ -435,9 +574,15 @@ int ekf_destroy(ekf_ctx* ctx) {
   if (!ctx) return EKF_EINVAL;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->wstream) cudaStreamSynchronize(ctx->wstream);
   if (ctx->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(ctx->comm); }
   free_line_tables(ctx);
-  cudaFree(ctx->b.st); cudaFree(ctx->b.y); cudaFree(ctx->b.top); cudaFree(ctx->b.diag); cudaFree(ctx->b.P);
+  cudaFree(ctx->b.st); cudaFree(ctx->b.y); cudaFree(ctx->b.top); cudaFree(ctx->b.diag); cudaFree(ctx->Pbuf[0]); cudaFree(ctx->Pbuf[1]);
+  cudaFree(ctx->d_view); cudaFree(ctx->d_counters);
+  if (ctx->evE) cudaEventDestroy(ctx->evE);
+  if (ctx->evF[0]) cudaEventDestroy(ctx->evF[0]);
+  if (ctx->evF[1]) cudaEventDestroy(ctx->evF[1]);
+  if (ctx->wstream) cudaStreamDestroy(ctx->wstream);
   cudaFree(ctx->b.matched); cudaFree(ctx->b.Kp); cudaFree(ctx->b.KSp); cudaFree(ctx->b.colA); cudaFree(ctx->b.gates);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_partials); cudaFree(ctx->d_out3);
   cudaFreeHost(ctx->h_st);
@@ -499,6 +644,7 @@ int ekf_sync(ekf_ctx* ctx) {
   if (!ctx) return EKF_EINVAL;
   CU(cudaSetDevice(ctx->cfg.device));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->wstream) CU(cudaStreamSynchronize(ctx->wstream));
   return EKF_OK;
 }
 
@@ -507,6 +653,8 @@ int ekf_predict(ekf_ctx* ctx, const double x_t0[3], const double u[3], double x_
   if (!ctx || !u) return EKF_EINVAL;
   if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_predict: previous scan not ended"); return EKF_ESTATE; }
   CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
+  use_tables(ctx, 0);
   double* h = ctx->h_in;
   memcpy(h, u, 3 * sizeof(double));
   if (x_t0) memcpy(h + 3, x_t0, 3 * sizeof(double));
@@ -674,6 +822,7 @@ int ekf_download(ekf_ctx* ctx, double* y, double* P, int* n_lines) {
   if (!ctx) return EKF_EINVAL;
   if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_download inside an open scan"); return EKF_ESTATE; }
   CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
   int rc = read_state(ctx);
   if (rc) return rc;
   const int n = ctx->g.n, nl = 3 + 2 * ctx->h_st->L;
@@ -691,6 +840,7 @@ int ekf_download_live(ekf_ctx* ctx, double* y, double* P, int ldp, int max_n, in
   if (!ctx) return EKF_EINVAL;
   if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_download_live inside an open scan"); return EKF_ESTATE; }
   CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
   int rc = read_state(ctx);
   if (rc) return rc;
   const int nl = 3 + 2 * ctx->h_st->L;
@@ -708,6 +858,7 @@ int ekf_download_block(ekf_ctx* ctx, int r0, int c0, int nr, int nc, double* out
   if (!ctx || !out || r0 < 0 || c0 < 0 || nr < 0 || nc < 0 || r0 + nr > ctx->g.n || c0 + nc > ctx->g.n) return EKF_EINVAL;
   if (ctx->scan_open) return EKF_ESTATE;
   CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
   return download_rect(ctx, r0, c0, nr, nc, out, (size_t)nc);
 }
 
@@ -715,6 +866,7 @@ int ekf_upload(ekf_ctx* ctx, const double* y, const double* P, int n_lines) {
   if (!ctx || n_lines < 0 || n_lines > ctx->g.cap) return EKF_EINVAL;
   if (ctx->scan_open) return EKF_ESTATE;
   CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
   const int n = ctx->g.n, nl = 3 + 2 * n_lines;
   int rc = read_state(ctx);
   if (rc) return rc;
@@ -748,6 +900,7 @@ int ekf_cov_stats(ekf_ctx* ctx, double* trace, double* sum, double* sumsq) {
   if (!ctx) return EKF_EINVAL;
   if (ctx->scan_open) return EKF_ESTATE;
   CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
   CU(ekf_launch_cov_stats(ctx->g, ctx->b, ctx->d_partials, ctx->g.n, ctx->d_out3, ctx->stream));
   double o[3];
   CU(cudaMemcpyAsync(o, ctx->d_out3, sizeof o, cudaMemcpyDeviceToHost, ctx->stream));
@@ -769,6 +922,7 @@ int ekf_profile_enable(ekf_ctx* ctx, int on) {
 int ekf_profile_read(ekf_ctx* ctx, int* n_sweeps, double* sweep_ms, double* sweep_bytes, long long* launches) {
   if (!ctx) return EKF_EINVAL;
   CU(cudaSetDevice(ctx->cfg.device));
+  if (ctx->wstream) CU(cudaStreamSynchronize(ctx->wstream));
   int rc = read_state(ctx);
   if (rc) return rc;
   const double n = 3.0 + 2.0 * ctx->h_st->L;
@@ -799,6 +953,9 @@ int ekf_timer_start(ekf_ctx* ctx) {
 int ekf_timer_stop(ekf_ctx* ctx, double* ms) {
   if (!ctx || !ctx->t0) return EKF_EINVAL;
   CU(cudaSetDevice(ctx->cfg.device));
+  if (ctx->overlap) {          /* the sweeps in flight belong to the timed work */
+    for (int p = 0; p < 2; ++p) if (ctx->evF_used[p]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evF[p], 0));
+  }
   CU(cudaEventRecord(ctx->t1, ctx->stream));
   CU(cudaEventSynchronize(ctx->t1));
   float t = 0.f;
@@ -811,6 +968,7 @@ int ekf_sweep_probe(ekf_ctx* ctx, int m, int repeats, double* ms_each) {
   if (!ctx || m < 1 || m > ctx->cfg.max_batch || repeats < 1) return EKF_EINVAL;
   if (ctx->scan_open) return EKF_ESTATE;
   CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
   CU(ekf_launch_zero_pending(ctx->g, ctx->b, m, &ctx->b.st->np, ctx->stream));
   { int rc = launch_sweep(ctx, m); if (rc) return rc; }                        /* warm-up */
   cudaEvent_t e0, e1;

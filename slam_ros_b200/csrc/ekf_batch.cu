@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, dou
       for (int r = warp; r < nl; r += nw) {
         const double2 ks = KSs[r];
         double* Pr = Ps + (size_t)r * n;
-        for (int q = lane; q < nl; q += 32) Pr[q] = sub_rn(Pr[q], add_rn(0.0, rank2(ks, Ks[q])));
+        for (int q = lane; q < nl; q += 32) Pr[q] = sub_rank2(Pr[q], ks, Ks[q]);
       }
     }
     for (int r = 3 + tid; r < nl; r += nt) {                          /* :585-589 */

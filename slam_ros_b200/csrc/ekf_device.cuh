@@ -22,6 +22,20 @@ __device__ __forceinline__ double rank2(double2 ks, double2 k) {
   return add_rn(mul_rn(ks.x, k.x), mul_rn(ks.y, k.y));
 }
 
+/* p - (ks.x*k.x + ks.y*k.y): the per-element update of Robot.cpp:564-568.
+ * Default: two fused multiply-adds, p <- fma(-ks.y, k.y, fma(-ks.x, k.x, p)).  The reference (x86-64 GSL, no
+ * FMA) rounds ks.x*k.x, ks.y*k.y, their sum and the difference separately; the fused form differs from that by
+ * at most a few ulp of the products (orders of magnitude inside the 1e-9 bar) and halves the fp64 issue
+ * slots, which is what keeps the rank-2m sweep HBM-bound at m = 8.  Every kernel uses this one function, so
+ * all launch strategies stay bit-identical to each other.  -DEKF_EXACT_RANK2 restores the reference order. */
+__device__ __forceinline__ double sub_rank2(double p, double2 ks, double2 k) {
+#ifdef EKF_EXACT_RANK2
+  return sub_rn(p, rank2(ks, k));
+#else
+  return __fma_rn(-ks.y, k.y, __fma_rn(-ks.x, k.x, p));
+#endif
+}
+
 /* Robot.cpp:62-71 verbatim (C++ parses floor(..)*2.0*M_PI as (floor(..)*2.0)*M_PI) */
 __device__ __forceinline__ void normalize_radian(double& rad) {
   const double two_pi = 2.0 * EKF_PI;

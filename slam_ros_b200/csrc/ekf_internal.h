@@ -43,7 +43,8 @@ struct EkfDevState {          /* one per filter, in global memory */
   int pad;
 };
 
-struct EkfShard { int rank, world; };
+/* what a scan's (possibly later, possibly concurrent) sweep needs to know about that scan */
+struct EkfScanView { int cnt; int L; int pad[2]; };
 
 /* geometry handed to every kernel by value */
 struct EkfGeom {
@@ -88,9 +89,11 @@ cudaError_t ekf_launch_gain(const EkfGeom& g, const EkfBuffers& b, const double*
 cudaError_t ekf_launch_apply(const EkfGeom& g, const EkfBuffers& b, int line, int j_override, int L_ub,
                              cudaStream_t s);
 int ekf_pick_cluster(void);
+void ekf_prefer_max_smem_carveout(void);
 /* all lines [line0, line1) of the open scan in one cluster launch (single-GPU path) */
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
-                                  int line0, int line1, int cluster, cudaStream_t s);
+                                  int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
+                                  const int* prev_cnt_ptr, cudaStream_t s);
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s);
 cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, cudaStream_t s);
 /* np_ptr: device int holding the number of pending terms (NULL = st->np); np_ub: host upper bound (selects the template) */
@@ -98,11 +101,13 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
                              cudaStream_t s);
 /* pipelined (TMA + mbarrier) form of the sweep; tmap = CUtensorMap of this rank's P with box (tc, tr) of
  * ekf_sweep_shape(shape); one pass per 8 pending terms */
-cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int shape, int np_ub, int L_ub,
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmapK, const void* tmapKS,
+                                 double* dst, int slot0,
+                                 const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
                                  int num_sms, cudaStream_t s);
 void ekf_sweep_shape(int shape, int* tr, int* tc);
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
-                                int m, int L_ub, cudaStream_t s);
+                                int m, int L_ub, int slot0, EkfScanView* view, cudaStream_t s);
 cudaError_t ekf_launch_assemble(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int c0, int nc,
                                 double* d_out, int ld_out, cudaStream_t s);
 cudaError_t ekf_launch_scatter(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int nl, const double* d_in,

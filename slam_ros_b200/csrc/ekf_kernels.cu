@@ -38,7 +38,7 @@ __device__ __forceinline__ double hot_value(const EkfGeom& g, const EkfBuffers& 
 __device__ __forceinline__ double cold_value(const EkfGeom& g, const EkfBuffers& b, int r, int q, int np) {
   double p = b.P[local_row(g, r) * g.ld + q];
   for (int i = 0; i < np; ++i)
-    p = sub_rn(p, rank2(b.KSp[(size_t)i * g.ld + r], b.Kp[(size_t)i * g.ld + q]));
+    p = sub_rank2(p, b.KSp[(size_t)i * g.ld + r], b.Kp[(size_t)i * g.ld + q]);
   return p;
 }
 /* 3x3 robot block with the lower half mirrored from the authoritative upper half */
@@ -249,16 +249,16 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, in
   const double2 ks0 = KS[0], ks1 = KS[1], ks2 = KS[2];
   for (int q = 3 + gid; q < nl; q += stride) {
     const double2 kq = K[q];
-    b.top[q] = sub_rn(b.top[q], rank2(ks0, kq));                        /* :564-568 rows 0..2 */
-    b.top[(size_t)g.ld + q] = sub_rn(b.top[(size_t)g.ld + q], rank2(ks1, kq));
-    b.top[(size_t)2 * g.ld + q] = sub_rn(b.top[(size_t)2 * g.ld + q], rank2(ks2, kq));
+    b.top[q] = sub_rank2(b.top[q], ks0, kq);                        /* :564-568 rows 0..2 */
+    b.top[(size_t)g.ld + q] = sub_rank2(b.top[(size_t)g.ld + q], ks1, kq);
+    b.top[(size_t)2 * g.ld + q] = sub_rank2(b.top[(size_t)2 * g.ld + q], ks2, kq);
     const double2 ksq = KS[q];
     const int jj = (q - 3) >> 1;
     if (q & 1) {                                                      /* q = a: (a,a), (a,b) */
-      b.diag[4 * jj] = sub_rn(b.diag[4 * jj], rank2(ksq, kq));
-      b.diag[4 * jj + 1] = sub_rn(b.diag[4 * jj + 1], rank2(ksq, K[q + 1]));
+      b.diag[4 * jj] = sub_rank2(b.diag[4 * jj], ksq, kq);
+      b.diag[4 * jj + 1] = sub_rank2(b.diag[4 * jj + 1], ksq, K[q + 1]);
     } else {                                                          /* q = b: (b,b) */
-      b.diag[4 * jj + 2] = sub_rn(b.diag[4 * jj + 2], rank2(ksq, kq));
+      b.diag[4 * jj + 2] = sub_rank2(b.diag[4 * jj + 2], ksq, kq);
     }
     double t = 0.0;                                                   /* :585-589  y += K * delta */
     axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, in
     const double2 ks[3] = {ks0, ks1, ks2};
     for (int r = 0; r < 3; ++r)
       for (int q = r; q < 3; ++q)
-        b.top[(size_t)r * g.ld + q] = sub_rn(b.top[(size_t)r * g.ld + q], rank2(ks[r], kk[q]));
+        b.top[(size_t)r * g.ld + q] = sub_rank2(b.top[(size_t)r * g.ld + q], ks[r], kk[q]);
     double yn[3];
     for (int r = 0; r < 3; ++r) {                                     /* :579-589 */
       double t = 0.0;
@@ -291,7 +291,6 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, in
  * bookkeeping) are separated by hardware cluster barriers instead of kernel boundaries.  The phases are
  * the bodies of k_associate / k_gain(mode 0) / k_apply; the winner's gate record travels through
  * b.gates so it is evaluated once, as in the reference (Robot.cpp:367-489 feeds :516-602). */
-#define FL_THREADS 512
 #define FL_MAXP 64                    /* upper bound of max_batch for the fused path */
 #define GATE_REC 16                   /* doubles per landmark in b.gates */
 
@@ -311,7 +310,7 @@ __device__ __forceinline__ void gate_load(const double* rec, Gate& G) {
 __device__ __forceinline__ void update_robot_block(const double2 kk[3], const double2 ks[3], double v0, double v1,
                                                    double A[3][3], double xp[3]) {
   for (int r = 0; r < 3; ++r)
-    for (int q = r; q < 3; ++q) { A[r][q] = sub_rn(A[r][q], rank2(ks[r], kk[q])); A[q][r] = A[r][q]; }
+    for (int q = r; q < 3; ++q) { A[r][q] = sub_rank2(A[r][q], ks[r], kk[q]); A[q][r] = A[r][q]; }
   double yn[3];
   for (int r = 0; r < 3; ++r) {
     double t = 0.0;
@@ -322,14 +321,20 @@ __device__ __forceinline__ void update_robot_block(const double2 kk[3], const do
   xp[0] = yn[0]; xp[1] = yn[1]; xp[2] = yn[2];
 }
 
-/* one row of the gain phase: everything that has to come from memory, issued as independent loads */
+/* one row of the gain phase: everything that has to come from memory, issued as independent loads.
+ * The pending list seen by a line is [previous scan's terms whose sweep may still be in flight] followed by
+ * [this scan's terms]; s_slot[i] is the slot of the i-th pending term, npt their number. */
 struct GainRow {
   double p0, p1, p2, pa, pb;
   double2 v[8];          /* first chunk of the row's pending terms (K S row entries or K column entries) */
   int kind;              /* 0: hot (no corrections), 1: column part (r < a), 2: row part (r > b) */
 };
+struct PendingList {     /* i-th pending term lives in slot prev_slot0 + i (i < prev_cnt) or own_slot0 + i - prev_cnt */
+  int prev_cnt, prev_slot0, own_slot0;
+  __device__ __forceinline__ int slot(int i) const { return (i < prev_cnt) ? prev_slot0 + i : own_slot0 + (i - prev_cnt); }
+};
 __device__ __forceinline__ void gain_row_load(const EkfGeom& g, const EkfBuffers& b, const double A[3][3], int r, int j,
-                                              int np, GainRow& d) {
+                                              int npt, const PendingList& pl, GainRow& d) {
   const int a = 3 + 2 * j, bb = a + 1;
   d.kind = 0;
   if (r <= 2) {
@@ -345,46 +350,46 @@ __device__ __forceinline__ void gain_row_load(const EkfGeom& g, const EkfBuffers
     d.pa = Pr[a]; d.pb = Pr[bb];
     d.kind = 1;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) if (t < np) d.v[t] = b.KSp[(size_t)t * g.ld + r];
+    for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.KSp[(size_t)pl.slot(t) * g.ld + r];
   } else {                                                            /* row parts: P[a,r], P[b,r] */
     d.pa = b.P[local_row(g, a) * g.ld + r]; d.pb = b.P[local_row(g, bb) * g.ld + r];
     d.kind = 2;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) if (t < np) d.v[t] = b.Kp[(size_t)t * g.ld + r];
+    for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.Kp[(size_t)pl.slot(t) * g.ld + r];
   }
 }
-__device__ __forceinline__ void gain_row_finish(const EkfGeom& g, const EkfBuffers& b, const Gate& G, int r, int np,
-                                                GainRow& d, const double2* s_ka, const double2* s_kb,
-                                                const double2* s_ksa, const double2* s_ksb) {
+__device__ __forceinline__ void gain_row_finish(const EkfGeom& g, const EkfBuffers& b, const Gate& G, int r, int npt,
+                                                int out_slot, GainRow& d, const PendingList& pl, const double2* s_ka,
+                                                const double2* s_kb, const double2* s_ksa, const double2* s_ksb) {
   if (d.kind == 1) {
-    for (int i0 = 0; i0 < np; i0 += 8) {
+    for (int i0 = 0; i0 < npt; i0 += 8) {
       if (i0 > 0) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) if (i0 + t < np) d.v[t] = b.KSp[(size_t)(i0 + t) * g.ld + r];
+        for (int t = 0; t < 8; ++t) if (i0 + t < npt) d.v[t] = b.KSp[(size_t)pl.slot(i0 + t) * g.ld + r];
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) if (i0 + t < np) {
-        d.pa = sub_rn(d.pa, rank2(d.v[t], s_ka[i0 + t]));
-        d.pb = sub_rn(d.pb, rank2(d.v[t], s_kb[i0 + t]));
+      for (int t = 0; t < 8; ++t) if (i0 + t < npt) {
+        d.pa = sub_rank2(d.pa, d.v[t], s_ka[i0 + t]);
+        d.pb = sub_rank2(d.pb, d.v[t], s_kb[i0 + t]);
       }
     }
   } else if (d.kind == 2) {
-    for (int i0 = 0; i0 < np; i0 += 8) {
+    for (int i0 = 0; i0 < npt; i0 += 8) {
       if (i0 > 0) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) if (i0 + t < np) d.v[t] = b.Kp[(size_t)(i0 + t) * g.ld + r];
+        for (int t = 0; t < 8; ++t) if (i0 + t < npt) d.v[t] = b.Kp[(size_t)pl.slot(i0 + t) * g.ld + r];
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) if (i0 + t < np) {
-        d.pa = sub_rn(d.pa, rank2(s_ksa[i0 + t], d.v[t]));
-        d.pb = sub_rn(d.pb, rank2(s_ksb[i0 + t], d.v[t]));
+      for (int t = 0; t < 8; ++t) if (i0 + t < npt) {
+        d.pa = sub_rank2(d.pa, s_ksa[i0 + t], d.v[t]);
+        d.pb = sub_rank2(d.pb, s_ksb[i0 + t], d.v[t]);
       }
     }
   }
   double2 Kr, KSr;
   gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Kr, KSr);
-  b.Kp[(size_t)np * g.ld + r] = Kr;
-  b.KSp[(size_t)np * g.ld + r] = KSr;
+  b.Kp[(size_t)out_slot * g.ld + r] = Kr;
+  b.KSp[(size_t)out_slot * g.ld + r] = KSr;
 }
 
 #ifdef EKF_LINE_TIMING
@@ -397,14 +402,25 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 
 /* Dependency chain per line: [landmark data + previous K] -> gate -> atomicMin -> barrier -> [winner]
  * -> [gate record + row data] -> gain -> barrier: three memory round trips and two cluster barriers. */
-__global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
-                                                              const double* __restrict__ R, int line0, int line1) {
-  cg::cluster_group cl = cg::this_cluster();
+/* The 256-thread form is capped at 85 registers (3 CTAs/SM bound): measured on B200, a CTA of it is then
+ * co-scheduled next to a resident sweep CTA (105 regs x 288 threads, 148 KB); at 118+ registers it is not. */
+/* COOP = false: the CTAs form one thread-block cluster and synchronise with the hardware cluster barrier.
+ * COOP = true : the same CTAs are launched cooperatively and synchronise with a grid barrier instead, so
+ *               they need not sit in one GPC -- this is the form that runs on the SMs the overlapped sweep
+ *               leaves free (see enqueue_scan_overlapped). */
+template <int FL_THREADS, bool COOP>
+__global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_lines(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
+                                                              const double* __restrict__ R, int line0, int line1,
+                                                              int own_slot0, int prev_slot0, const int* __restrict__ prev_cnt_ptr) {
   __shared__ int s_min[FL_THREADS / 32];
   __shared__ double2 s_ka[FL_MAXP], s_kb[FL_MAXP], s_ksa[FL_MAXP], s_ksb[FL_MAXP];
+  const int prev_cnt = prev_cnt_ptr ? *prev_cnt_ptr : 0;   /* previous scan's terms not yet folded into b.P */
   EkfDevState* st = b.st;
-  const int gtid = (int)cl.block_rank() * blockDim.x + threadIdx.x;
-  const int gstride = (int)cl.num_blocks() * blockDim.x;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;      /* the grid is exactly one cluster / one co-resident group */
+  const int gstride = gridDim.x * blockDim.x;
+  auto group_sync = [] () {
+    if (COOP) cg::this_grid().sync(); else cg::this_cluster().sync();
+  };
   const int L = st->L, nl = 3 + 2 * L, epoch = st->epoch, pbase = st->pbase;
   int nm = b.pidx[line0];             /* matches of this scan so far: tracked identically by every thread */
   int ne = b.eidx[line0];
@@ -426,8 +442,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
       Rl[0] = R[4 * line]; Rl[1] = R[4 * line + 1]; Rl[2] = R[4 * line + 2]; Rl[3] = R[4 * line + 3];
       z0 = z[2 * line]; z1 = z[2 * line + 1];
     }
-    const double2* Kv = b.Kp + (size_t)np_prev * g.ld;
-    const double2* KSv = b.KSp + (size_t)np_prev * g.ld;
+    const double2* Kv = b.Kp + (size_t)(own_slot0 + np_prev) * g.ld;
+    const double2* KSv = b.KSp + (size_t)(own_slot0 + np_prev) * g.ld;
     double2 ks[3], kk[3];
     if (have_prev) {
       for (int r = 0; r < 3; ++r) { ks[r] = KSv[r]; kk[r] = Kv[r]; }
@@ -444,10 +460,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
       const int mt = b.matched[j];
       if (have_prev) {                                                /* Robot.cpp:564-589 on this landmark's hot elements */
         const double2 ka = Kv[a], kb = Kv[bb], ksa = KSv[a], ksb = KSv[bb];
-        t0a = sub_rn(t0a, rank2(ks[0], ka)); t0b = sub_rn(t0b, rank2(ks[0], kb));
-        t1a = sub_rn(t1a, rank2(ks[1], ka)); t1b = sub_rn(t1b, rank2(ks[1], kb));
-        t2a = sub_rn(t2a, rank2(ks[2], ka)); t2b = sub_rn(t2b, rank2(ks[2], kb));
-        daa = sub_rn(daa, rank2(ksa, ka)); dab = sub_rn(dab, rank2(ksa, kb)); dbb = sub_rn(dbb, rank2(ksb, kb));
+        t0a = sub_rank2(t0a, ks[0], ka); t0b = sub_rank2(t0b, ks[0], kb);
+        t1a = sub_rank2(t1a, ks[1], ka); t1b = sub_rank2(t1b, ks[1], kb);
+        t2a = sub_rank2(t2a, ks[2], ka); t2b = sub_rank2(t2b, ks[2], kb);
+        daa = sub_rank2(daa, ksa, ka); dab = sub_rank2(dab, ksa, kb); dbb = sub_rank2(dbb, ksb, kb);
         double ta = 0.0, tb = 0.0;
         axpy_skip(ta, ka.x, pv0); axpy_skip(ta, ka.y, pv1);
         axpy_skip(tb, kb.x, pv0); axpy_skip(tb, kb.y, pv1);
@@ -492,7 +508,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
       if (threadIdx.x == 0 && v != EKF_NO_MATCH) atomicMin(&b.jbest[line], v);
     }
     TS(2);
-    cl.sync();                                                        /* hot state current, winner known */
+    group_sync();                                                     /* hot state current, winner known */
     TS(3);
     const int j = b.jbest[line];
     const int np = nm - pbase;
@@ -507,20 +523,24 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
     Gate G;
     gate_load(b.gates + (size_t)GATE_REC * j, G);
     /* the pending terms' entries at a and b are the same for every row: stage them once per CTA */
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
-      s_ka[i] = b.Kp[(size_t)i * g.ld + a]; s_kb[i] = b.Kp[(size_t)i * g.ld + bb];
-      s_ksa[i] = b.KSp[(size_t)i * g.ld + a]; s_ksb[i] = b.KSp[(size_t)i * g.ld + bb];
+    const int npt = prev_cnt + np;
+    PendingList pl;
+    pl.prev_cnt = prev_cnt; pl.prev_slot0 = prev_slot0; pl.own_slot0 = own_slot0;
+    for (int i = threadIdx.x; i < npt; i += blockDim.x) {
+      const int slot = pl.slot(i);
+      s_ka[i] = b.Kp[(size_t)slot * g.ld + a]; s_kb[i] = b.Kp[(size_t)slot * g.ld + bb];
+      s_ksa[i] = b.KSp[(size_t)slot * g.ld + a]; s_ksb[i] = b.KSp[(size_t)slot * g.ld + bb];
     }
     GainRow d;
     int r = gtid;
     TS(4);
-    if (r < nl) gain_row_load(g, b, A, r, j, np, d);
+    if (r < nl) gain_row_load(g, b, A, r, j, npt, pl, d);
     __syncthreads();
     TS(5);
     while (r < nl) {
-      gain_row_finish(g, b, G, r, np, d, s_ka, s_kb, s_ksa, s_ksb);
+      gain_row_finish(g, b, G, r, npt, own_slot0 + np, d, pl, s_ka, s_kb, s_ksa, s_ksb);
       r += gstride;
-      if (r < nl) gain_row_load(g, b, A, r, j, np, d);
+      if (r < nl) gain_row_load(g, b, A, r, j, npt, pl, d);
     }
     if (gtid == 0) {                                                  /* :501-504 bookkeeping (read after the next barrier) */
       b.matched[j] = epoch;
@@ -529,7 +549,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines(EkfGeom g, EkfBuff
       st->np = np + 1;
     }
     TS(6);
-    cl.sync();                                                        /* K, K S complete */
+    group_sync();                                                     /* K, K S complete */
     TS(7);
     have_prev = true;
     np_prev = np;
@@ -617,8 +637,8 @@ __global__ void __launch_bounds__(EKF_BLOCK, 2) k_sweep(EkfGeom g, EkfBuffers b,
         for (int c = 0; c < C; ++c)
           if (c0 + c < np) {
             const double2 ks = __ldg(b.KSp + (size_t)(c0 + c) * g.ld + r_base + i);
-            p[i].x = sub_rn(p[i].x, rank2(ks, kq0[c]));
-            p[i].y = sub_rn(p[i].y, rank2(ks, kq1[c]));
+            p[i].x = sub_rank2(p[i].x, ks, kq0[c]);
+            p[i].y = sub_rank2(p[i].y, ks, kq1[c]);
           }
       }
     }
@@ -689,15 +709,19 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
  * producer walks its tiles in increasing order, so it decodes incrementally (no division, no sqrt). */
 template <int TR, int TC, int STAGES, int CW>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
-k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, int c0) {
+k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapK,
+             const __grid_constant__ CUtensorMap tmapKS, double* __restrict__ dst, int c0,
+             int slot0, const EkfScanView* __restrict__ view, unsigned long long* __restrict__ tile_counter) {
   typedef SweepShared<TR, TC, STAGES> Shared;
   extern __shared__ unsigned char sw_raw[];
   /* TMA destinations want 128-byte alignment; the launcher over-allocates by 1 KB for this round-up */
   Shared& sh = *reinterpret_cast<Shared*>(sw_raw + ((1024u - (smem_u32(sw_raw) & 1023u)) & 1023u));
-  const int np_all = b.st->np;
-  const int np = min(SW_C, np_all - c0);
-  if (np <= 0) return;
-  const int nl = 3 + 2 * b.st->L;
+  /* view != NULL: the scan's own snapshot (its sweep may run while the next scan already changes st);
+   * the out-of-place form (dst != source) must run even with no pending term: it is then a copy */
+  const int np_all = view ? view->cnt : b.st->np;
+  const int np = max(0, min(SW_C, np_all - c0));
+  if (np <= 0 && (dst == b.P || c0 > 0)) return;
+  const int nl = 3 + 2 * (view ? view->L : b.st->L);
   const int T64 = (nl + EKF_TILE - 1) / EKF_TILE;      /* 64-row ownership blocks in the live part */
   const int Tc = (nl + TC - 1) / TC;                   /* tile columns */
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -710,14 +734,21 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
   if (warp == CW) {
     /* ---------------- producer: one elected lane ---------------- */
     if (lane == 0) {
-      const unsigned bytes = TR * TC * sizeof(double) + (unsigned)np * (TC + TR) * sizeof(double2);
+      /* more than 4 pending terms: ONE 2-D TMA copy fetches the 8-slot band of K (resp. K S) for the tile's
+       * columns (rows) -- 3 TMA operations per tile instead of 17 */
+      const bool band = np > 4;
+      const unsigned bytes = TR * TC * sizeof(double) + (unsigned)(band ? SW_C : np) * (TC + TR) * sizeof(double2);
       int k = 0;                                        /* local ownership block */
       int gb = g.rank;                                  /* its global index */
       long long base = 0;                               /* index of the block's first tile */
       int cb0 = (EKF_TILE * gb) / TC;
       long long cnt = (gb < T64) ? (long long)SUB * (Tc - cb0) : 0;
       int it = 0;
-      for (long long idx = blockIdx.x; gb < T64; idx += gridDim.x, ++it) {
+      /* tiles are handed out by a global counter (zeroed before the launch): CTAs that share their SM with
+       * another kernel simply take fewer tiles.  The indices a CTA draws are increasing, which is all the
+       * incremental decode needs.  tile_counter == NULL: static round robin. */
+      for (long long idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : (long long)blockIdx.x; gb < T64;
+           idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : idx + gridDim.x, ++it) {
         while (gb < T64 && idx >= base + cnt) {
           base += cnt; ++k; gb += g.world;
           cb0 = (EKF_TILE * gb) / TC;
@@ -733,9 +764,14 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
         sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
         mbar_expect_tx(&sh.full[s], bytes);
         tma_load_tile(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s]);
-        for (int c = 0; c < np; ++c) {
-          bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(c0 + c) * g.ld + col0, TC * sizeof(double2), &sh.full[s]);
-          bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(c0 + c) * g.ld + grow0, TR * sizeof(double2), &sh.full[s]);
+        if (band) {
+          tma_load_tile(sh.stage[s].K, &tmapK, 2 * col0, slot0 + c0, &sh.full[s]);
+          tma_load_tile(sh.stage[s].KS, &tmapKS, 2 * grow0, slot0 + c0, &sh.full[s]);
+        } else {
+          for (int c = 0; c < np; ++c) {
+            bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(slot0 + c0 + c) * g.ld + col0, TC * sizeof(double2), &sh.full[s]);
+            bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(slot0 + c0 + c) * g.ld + grow0, TR * sizeof(double2), &sh.full[s]);
+          }
         }
       }
       /* tell the consumers there is nothing more: a stage with valid = 0 */
@@ -759,7 +795,7 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
     mbar_wait(&sh.full[s], ph);
     if (!sh.meta[s][3]) break;
     const SweepStage<TR, TC>& st = sh.stage[s];
-    const int lrow0 = sh.meta[s][0], col0 = sh.meta[s][2];
+    const int lrow0 = sh.meta[s][0], grow0 = sh.meta[s][1], col0 = sh.meta[s][2];
     double2 p[PT];
 #pragma unroll
     for (int i = 0; i < PT; ++i) p[i] = *reinterpret_cast<const double2*>(&st.P[(crow + i * RPP) * TC + ccol]);
@@ -768,22 +804,36 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
 #pragma unroll
       for (int i = 0; i < PT; ++i) {
         const double2 ks = st.KS[c][crow + i * RPP];
-        p[i].x = sub_rn(p[i].x, rank2(ks, kq0));
-        p[i].y = sub_rn(p[i].y, rank2(ks, kq1));
+        p[i].x = sub_rank2(p[i].x, ks, kq0);
+        p[i].y = sub_rank2(p[i].y, ks, kq1);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sh.empty[s]);
-    double* Pt = b.P + ((size_t)lrow0 + crow) * g.ld + (size_t)col0 + ccol;
+    double* Pt = dst + ((size_t)lrow0 + crow) * g.ld + (size_t)col0 + ccol;
+    if (grow0 + TR <= nl && col0 + TC <= nl) {
 #pragma unroll
-    for (int i = 0; i < PT; ++i) __stcs(reinterpret_cast<double2*>(Pt + (size_t)(i * RPP) * g.ld), p[i]);
+      for (int i = 0; i < PT; ++i) __stcs(reinterpret_cast<double2*>(Pt + (size_t)(i * RPP) * g.ld), p[i]);
+    } else {
+      /* edge tile: dead rows / columns are left alone -- the line stream may be appending landmarks there
+       * (augmentation) while this sweep is still in flight */
+      const int q = col0 + ccol;
+#pragma unroll
+      for (int i = 0; i < PT; ++i) {
+        if (grow0 + crow + i * RPP < nl) {
+          if (q + 1 < nl) __stcs(reinterpret_cast<double2*>(Pt + (size_t)(i * RPP) * g.ld), p[i]);
+          else if (q < nl) Pt[(size_t)(i * RPP) * g.ld] = p[i].x;
+        }
+      }
+    }
   }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* Robot.cpp:702-716 then :776-866 phase A (per unmatched line: world-frame parameters, P_ll, and the
  * rows 0..2 of its new columns -- all functions of the 3x3 robot block only). */
-__global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, const double* __restrict__ z, const double* __restrict__ R, int m) {
+__global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, const double* __restrict__ z, const double* __restrict__ R, int m,
+                                                    int slot0) {
   EkfDevState* st = b.st;
   __shared__ double s_pose[3];
   __shared__ double s_y01[2];
@@ -804,6 +854,16 @@ __global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, con
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->n_added = n_add;
     if (n_add < ne) atomicOr(&st->sticky, EKF_STICKY_CAPACITY);       /* the reference overruns y[] here (Q4) */
+  }
+  /* this scan's pending terms have no entry for the rows being appended: zero them, so that the (possibly
+   * later) sweep and the next scan's on-the-fly corrections see K = 0 there */
+  {
+    const int cnt = b.pidx[m] - st->pbase, r0 = 3 + 2 * L, r1 = 3 + 2 * (L + n_add);
+    for (int i = 0; i < cnt; ++i)
+      for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        b.Kp[(size_t)(slot0 + i) * g.ld + r] = make_double2(0.0, 0.0);
+        b.KSp[(size_t)(slot0 + i) * g.ld + r] = make_double2(0.0, 0.0);
+      }
   }
   double A[3][3];
   load_rr(g, b.top, A);
@@ -882,11 +942,12 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_end_scan_b(EkfGeom g, EkfBuffers 
 }
 
 /* ++savedLineCount (Robot.cpp:866) for every appended line, then the reset test (:893-904). */
-__global__ void k_end_scan_c(EkfGeom g, EkfBuffers b) {
+__global__ void k_end_scan_c(EkfGeom g, EkfBuffers b, int m, EkfScanView* view) {
   EkfDevState* st = b.st;
   int L = st->L + st->n_added;
   if (L > g.cap - g.headroom) { L = 0; st->resets += 1; }
   st->L = L;
+  if (view) { view->cnt = b.pidx[m] - st->pbase; view->L = L; }   /* what this scan's sweep will need */
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -1016,34 +1077,53 @@ extern "C" int ekf_debug_line_timing(unsigned long long* out, int n) {
   return (int)cudaMemcpyFromSymbol(out, g_line_ts, sizeof(unsigned long long) * (size_t)n);
 }
 #endif
+/* Kernels of the line stream must be able to share an SM with a resident sweep CTA (which runs with the
+ * maximum shared-memory carve-out): an SM cannot host kernels with different carve-outs at the same time. */
+void ekf_prefer_max_smem_carveout(void) {
+  const int c = cudaSharedmemCarveoutMaxShared;
+  cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines<512, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines<512, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_end_scan_a, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_end_scan_b, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_end_scan_c, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_queue_all, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  (void)cudaGetLastError();
+}
 int ekf_pick_cluster(void) {
-  cudaFuncSetAttribute(k_scan_lines, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_scan_lines<512, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   const int tries[2] = {16, 8};
   for (int t = 0; t < 2; ++t) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(tries[t]); cfg.blockDim = dim3(FL_THREADS);
+    cfg.gridDim = dim3(tries[t]); cfg.blockDim = dim3(512);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = tries[t]; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines, &cfg) == cudaSuccess && n >= 1) return tries[t];
+    if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines<512, false>, &cfg) == cudaSuccess && n >= 1) return tries[t];
   }
   (void)cudaGetLastError();
   return 8;
 }
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
-                                  int line0, int line1, int cluster, cudaStream_t s) {
+                                  int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
+                                  const int* prev_cnt_ptr, cudaStream_t s) {
   if (line1 <= line0) return cudaSuccess;
+  if (coop) {
+    void* args[] = {(void*)&g, (void*)&b, (void*)&d_z, (void*)&d_R, (void*)&line0, (void*)&line1, (void*)&own_slot0,
+                    (void*)&prev_slot0, (void*)&prev_cnt_ptr};
+    return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true>, dim3(ctas), dim3(512), args, 0, s);
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(cluster); cfg.blockDim = dim3(FL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_scan_lines, g, b, d_z, d_R, line0, line1);
+  return cudaLaunchKernelEx(&cfg, k_scan_lines<512, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
 }
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
   k_flush_done<<<1, 32, 0, s>>>(b, next_line);
@@ -1073,7 +1153,9 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
   return cudaGetLastError();
 }
 template <int TR, int TC, int STAGES, int CW>
-static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, int np_ub, int grid, cudaStream_t s) {
+static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, const CUtensorMap* mK,
+                                      const CUtensorMap* mKS, double* dst, int slot0,
+                                      const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s) {
   const size_t smem = sizeof(SweepShared<TR, TC, STAGES>) + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -1084,34 +1166,44 @@ static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, con
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   for (int c0 = 0; c0 < np_ub; c0 += SW_C) {
-    k_sweep_pipe<TR, TC, STAGES, CW><<<grid, (CW + 1) * 32, smem, s>>>(g, b, *m, c0);
+    k_sweep_pipe<TR, TC, STAGES, CW><<<grid, (CW + 1) * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / SW_C : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
 void ekf_sweep_shape(int shape, int* tr, int* tc) {
-  switch (shape % 4) { case 1: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }
+  switch (shape % 4) { case 1: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }   /* 8 % 4 == 0 */
 }
-cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, int shape, int np_ub, int L_ub,
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmapK, const void* tmapKS,
+                                 double* dst, int slot0,
+                                 const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
                                  int num_sms, cudaStream_t s) {
   const int tiles = ekf_sweep_grid_ub(g, L_ub);
   if (tiles <= 0 || np_ub <= 0) return cudaSuccess;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  if (dst != b.P && np_ub > SW_C) return cudaErrorInvalidValue;   /* out-of-place form: one pass only */
+  const int grid = tiles < num_sms ? tiles : num_sms;      /* num_sms: SMs this sweep may occupy */
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmap);
+  const CUtensorMap* mK = reinterpret_cast<const CUtensorMap*>(tmapK);
+  const CUtensorMap* mKS = reinterpret_cast<const CUtensorMap*>(tmapKS);
+  if (counters) {   /* one counter per pass */
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * ((np_ub + SW_C - 1) / SW_C), s);
+    if (e != cudaSuccess) return e;
+  }
   switch (shape) {       /* shape % 4: tile shape; shape / 4: 0 = 8 consumer warps, 1 = 16 */
-    case 1: return launch_sweep_shape<32, 128, 4, 8>(g, b, m, np_ub, grid, s);
-    case 2: return launch_sweep_shape<16, 256, 3, 8>(g, b, m, np_ub, grid, s);
-    case 4: return launch_sweep_shape<64, 64, 4, 16>(g, b, m, np_ub, grid, s);
-    case 5: return launch_sweep_shape<32, 128, 4, 16>(g, b, m, np_ub, grid, s);
-    default: return launch_sweep_shape<64, 64, 4, 8>(g, b, m, np_ub, grid, s);
+    case 1: return launch_sweep_shape<32, 128, 4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 2: return launch_sweep_shape<16, 256, 3, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 4: return launch_sweep_shape<64, 64, 4, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 5: return launch_sweep_shape<32, 128, 4, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 8: return launch_sweep_shape<64, 64, 3, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);   /* 148 KB: leaves room for a co-resident line-loop CTA */
+    default: return launch_sweep_shape<64, 64, 4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
   }
 }
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
-                                int m, int L_ub, cudaStream_t s) {
+                                int m, int L_ub, int slot0, EkfScanView* view, cudaStream_t s) {
   /* all blocks of phase A redo the (idempotent) no-match bookkeeping only in thread 0 of block 0's
    * shared copy; to keep it race-free phase A runs as ONE block when it also has to write the pose */
-  k_end_scan_a<<<1, 512, 0, s>>>(g, b, d_z, d_R, m);
+  k_end_scan_a<<<1, 512, 0, s>>>(g, b, d_z, d_R, m, slot0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (m > 0) {
@@ -1124,7 +1216,7 @@ cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const dou
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  k_end_scan_c<<<1, 1, 0, s>>>(g, b);
+  k_end_scan_c<<<1, 1, 0, s>>>(g, b, m, view);
   return cudaGetLastError();
 }
 cudaError_t ekf_launch_assemble(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int c0, int nc,

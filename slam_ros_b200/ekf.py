@@ -15,6 +15,7 @@ EKF_OK, EKF_EINVAL, EKF_ECAPACITY, EKF_ESINGULAR, EKF_ECUDA, EKF_ENCCL, EKF_ENOM
 EKF_FLAG_EAGER_SWEEP = 1
 EKF_FLAG_SWEEP_DIRECT = 2
 EKF_FLAG_PER_LINE_KERNELS = 4
+EKF_FLAG_NO_OVERLAP = 8
 _STATUS = {0: "OK", 1: "EINVAL", 2: "ECAPACITY", 3: "ESINGULAR", 4: "ECUDA", 5: "ENCCL", 6: "ENOMEM", 7: "ESTATE"}
 
 _dp = C.POINTER(C.c_double)

@@ -149,12 +149,14 @@ def test_map_scenario_every_step(libekf, oracle_cls, N, steps, m, seed):
 
 
 def test_all_launch_strategies_give_identical_bits(libekf):
-    """Deferred rank-2m sweep (default: cluster line-loop kernel + TMA-pipelined sweep) vs one rank-2 sweep
-    per match (reference-like), per-line kernels, the direct sweep kernel and forced mid-scan flushes."""
+    """Default (cluster line-loop kernel + TMA-pipelined sweep, each scan's sweep overlapped with the next
+    scan's line loop on a second stream over a double-buffered P) vs the same without overlap, one rank-2
+    sweep per match (reference-like), per-line kernels, the direct sweep kernel and forced mid-scan flushes."""
     from slam_ros_b200 import EkfFilter
-    from slam_ros_b200.ekf import EKF_FLAG_EAGER_SWEEP, EKF_FLAG_SWEEP_DIRECT, EKF_FLAG_PER_LINE_KERNELS
+    from slam_ros_b200.ekf import EKF_FLAG_EAGER_SWEEP, EKF_FLAG_SWEEP_DIRECT, EKF_FLAG_PER_LINE_KERNELS, EKF_FLAG_NO_OVERLAP
     scn = sc.map_scenario(80, 40, m=8, seed=9)
-    variants = [EkfFilter(capacity_lines=128),
+    variants = [EkfFilter(capacity_lines=128),                                  # overlapped two-stream pipeline
+                EkfFilter(capacity_lines=128, flags=EKF_FLAG_NO_OVERLAP),
                 EkfFilter(capacity_lines=128, flags=EKF_FLAG_EAGER_SWEEP),
                 EkfFilter(capacity_lines=128, max_batch=3),                      # forces mid-scan flushes
                 EkfFilter(capacity_lines=128, flags=EKF_FLAG_PER_LINE_KERNELS),
