@@ -280,9 +280,9 @@ def run_single_or_replicas(args, rank, world, local, sharded):
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "landmarks": N, "state_dim": n, "lines_per_scan": m,
                    "matched_per_step": mean_terms, "parallelism": ("row-sharded P x%d" % world) if sharded else ("independent filters x%d" % world),
-                   "l2": "working set %.2f GB >> 126 MB L2: no flush needed" % (8.0 * n * (n + 1) / 2 / 1e9),
+                   "l2": "per-step working set %.2f GB read + %.2f GB written >> 126 MB L2: no flush needed" % (8.0 * n * (n + 1) / 2 / 1e9, 8.0 * n * (n + 1) / 2 / 1e9),
                    "seed": seed},
-        "roofline": {"bound": "hbm", "kernel": "k_sweep (P -= (K S) K' over the upper triangle)",
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_pipe (P -= (K S) K' over the upper triangle; TMA + mbarrier ring, runs under the next scan's line loop)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "launch_ms": sweep_ms, "launches_timed": prof["sweeps"], "algorithmic_bytes_per_launch": bytes_per_sweep,

@@ -103,13 +103,13 @@ namespace {
   do {                                                                                        \
     cudaError_t e_ = (call);                                                                  \
     if (e_ != cudaSuccess) {                                                                  \
-      snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      snprintf(ctx->err, sizeof ctx->err, "%s:%d %.120s: %s", "ekf_api.cu", __LINE__, #call, cudaGetErrorString(e_)); \
       return EKF_ECUDA;                                                                       \
     }                                                                                         \
   } while (0)
 
 const size_t kStageElems = (size_t)8 << 20;   /* 64 MiB staging for download/upload */
-static int line_sms() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : 12; if (v < 1 || v > 64) v = 12; } return v; }
+static int line_sms() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : 8; if (v < 1 || v > 64) v = 8; } return v; }
 #define EKF_LINE_SMS line_sms()               /* SMs reserved for the line loop while a sweep is in flight */
 
 double* in_u(ekf_ctx* c) { return c->d_in; }

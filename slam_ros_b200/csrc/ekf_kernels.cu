@@ -698,6 +698,18 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(col), "r"(row) : "memory");
 }
+/* same, with an L2 eviction-priority hint: the covariance is streamed once per sweep (evict first), so that
+ * the small, constantly re-read hot state and pending lists are what stays in L2 */
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_tile_hint(void* dst, const CUtensorMap* map, int col, int row, unsigned long long* bar,
+                                                   unsigned long long policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(col), "r"(row), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -737,6 +749,7 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
       /* more than 4 pending terms: ONE 2-D TMA copy fetches the 8-slot band of K (resp. K S) for the tile's
        * columns (rows) -- 3 TMA operations per tile instead of 17 */
       const bool band = np > 4;
+      const unsigned long long pol = l2_policy_evict_first();
       const unsigned bytes = TR * TC * sizeof(double) + (unsigned)(band ? SW_C : np) * (TC + TR) * sizeof(double2);
       int k = 0;                                        /* local ownership block */
       int gb = g.rank;                                  /* its global index */
@@ -763,7 +776,7 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
         mbar_wait(&sh.empty[s], ph ^ 1);
         sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
         mbar_expect_tx(&sh.full[s], bytes);
-        tma_load_tile(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s]);
+        tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s], pol);
         if (band) {
           tma_load_tile(sh.stage[s].K, &tmapK, 2 * col0, slot0 + c0, &sh.full[s]);
           tma_load_tile(sh.stage[s].KS, &tmapKS, 2 * grow0, slot0 + c0, &sh.full[s]);
