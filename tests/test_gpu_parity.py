@@ -379,3 +379,42 @@ def test_empty_and_ragged_scans(libekf, oracle_cls):
         st, jo = so.scan(scn["u"][s], z, R)
         assert np.array_equal(j, jo), "step %d" % s
     compare_state(f, so, "ragged")
+
+
+def test_full_size_10k_landmarks_against_oracle(libekf, oracle_cls):
+    """BASELINE.json configs[2] at full size (P 20003^2 fp64 = 3.2 GB): a short prefix against the oracle
+    (association bit-exact; y exactly comparable; P compared on blocks spread over the matrix and through the
+    size-independent invariants trace / sum of squares), then invariants over more steps: the trace never
+    grows through an update scan beyond what prediction adds, and the read-out stays symmetric."""
+    N, steps, m = 10000, 4, 8
+    scn = sc.map_scenario(N, 12, m=m, seed=1)
+    f, so = seed_pair(N, N + 256, oracle_cls, scn, )
+    so._lib.ekfo_set_threads(so._h, 0)          # all host threads for the n^2 sweeps of the checker
+    for s in range(steps):
+        rc, j, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        st, jo = so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        assert rc == st == 0 and np.array_equal(j, jo), "step %d" % s
+    nl = 3 + 2 * so.lines
+    Pv = so.P_view()
+    pmax = float(np.abs(Pv[:nl, :nl]).max())
+    y_g = f.download_y()
+    assert rel(y_g, so.y_full()[:nl]) < TOL
+    rng = np.random.default_rng(0)
+    corners = [(0, 0), (0, nl - 80), (nl - 80, nl - 80), (3, 3)] + [tuple(rng.integers(0, nl - 80, 2)) for _ in range(12)]
+    for (r0, c0) in corners:
+        blk = f.download_block(int(r0), int(c0), 80, 80)
+        ref = Pv[r0:r0 + 80, c0:c0 + 80]
+        assert np.abs(blk - ref).max() / pmax < TOL, (r0, c0)
+        blk_t = f.download_block(int(c0), int(r0), 80, 80)
+        assert np.array_equal(blk, blk_t.T)                       # symmetric read-out
+    tr, sm, sq = f.cov_stats()
+    tr_o = float(np.trace(Pv[:nl, :nl]))
+    assert abs(tr - tr_o) / abs(tr_o) < TOL
+    sq_o = float(np.einsum("ij,ij->", Pv[:nl, :nl], Pv[:nl, :nl]))
+    assert abs(sq - sq_o) / sq_o < 1e-8
+    for s in range(steps, 12):                                     # invariants only (no CPU sweep)
+        tr_before = f.cov_stats()[0]
+        rc, j, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        tr_after = f.cov_stats()[0]
+        assert rc == 0 and (j >= 0).sum() >= m - 2
+        assert tr_after < tr_before + 1e-2                         # prediction adds <= 4q ~ 2e-3; updates only remove
