@@ -354,9 +354,9 @@ def run_monte_carlo(args, rank, world, local):
     if rank != 0:
         return None
     ms_max, e2e_max = float(t[0]), float(t[1])
-    n = 3 + 2 * cap
+    n = 3 + 2 * N                               # live dimension of every filter
     peak, peak_src = measured_peaks()
-    bytes_per_launch = 16.0 * n * n * B        # full n x n per filter read + written once per scan
+    bytes_per_launch = 8.0 * n * (n + 1) * B    # upper triangle of every filter read + written once per scan
     achieved = bytes_per_launch / (ms_max / K * 1e-3) / 1e9
     return {
         "metric": "EKF predict+update steps/s at N landmarks", "value": K / (ms_max / 1e3), "unit": "steps/s",
@@ -365,8 +365,8 @@ def run_monte_carlo(args, rank, world, local):
         "config": {"workload": w["desc"], "filters_total": B_total, "filters_per_gpu": B, "landmarks": N,
                    "lines_per_scan": m, "filter_steps_per_s": B_total * K / (ms_max / 1e3),
                    "parallelism": "independent filters, %d per GPU, no collective" % B,
-                   "l2": "batch state %.0f MB > 126 MB L2" % (B * n * n * 8 / 1e6)},
-        "roofline": {"bound": "hbm", "kernel": "k_batch_scan (whole localize, P staged in shared memory)",
+                   "l2": "batch state %.0f MB > 126 MB L2" % (B * (3 + 2 * cap) ** 2 * 8 / 1e6)},
+        "roofline": {"bound": "hbm", "kernel": "k_batch_scan (whole localize per CTA; hot state + pending gains in shared memory, one deferred sweep of the cold upper triangle)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "launch_ms": ms_max / K, "algorithmic_bytes_per_launch": bytes_per_launch, "traffic": None},
         "e2e": {"value": K / (e2e_max / 1e3), "unit": "steps/s", "h2d_bytes_per_step": (3 + 6 * m) * 8 * B,
