@@ -109,6 +109,18 @@ class Robot {
     return ok != 0;
   }
 
+  /* The `robotPosition` message of the node (slam_ros/main.cpp:150-169): translation = (x, y, theta),
+   * rotation.x / .y / .z = major axis, minor axis, angle of the 95 % ellipse.  Plain doubles: the caller
+   * copies them into geometry_msgs::Transform. */
+  struct RobotPosition { double tx, ty, tz, rx, ry, rz; bool ellipse_ok; };
+  RobotPosition robotPosition() {
+    RobotPosition msg = {xPos, yPos, thetaPos, 0.0, 0.0, 0.0, false};
+    float axii[2] = {0.f, 0.f}, angle = 0.f;
+    msg.ellipse_ok = getEllipse(axii, angle);
+    msg.rx = axii[1]; msg.ry = axii[0]; msg.rz = angle;
+    return msg;
+  }
+
   /* copies y and P_t0 back in the reference's layout (SLAMSIZE and SLAMSIZE^2 doubles) */
   void syncCovariance() {
     y.assign((size_t)n_, 0.0); P_t0.assign((size_t)n_ * n_, 0.0);

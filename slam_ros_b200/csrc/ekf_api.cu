@@ -109,6 +109,7 @@ namespace {
   } while (0)
 
 const size_t kStageElems = (size_t)8 << 20;   /* 64 MiB staging for download/upload */
+const int kOverlapMinN = 6000;                /* below this state dimension the synchronous path is used */
 static int line_sms() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : 8; if (v < 1 || v > 64) v = 8; } return v; }
 #define EKF_LINE_SMS line_sms()               /* SMs reserved for the line loop while a sweep is in flight */
 
@@ -360,7 +361,10 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
 /* the whole Robot::localize, enqueued without returning to the host */
 int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, const double* d_z, const double* d_R) {
   if (ctx->overlap) {
-    if (m >= 1 && m <= 8 && ctx->L_ub > 0) return enqueue_scan_overlapped(ctx, d_u, d_x_t0, m, d_z, d_R);
+    /* small maps: the sweep is a few microseconds, nothing to hide -- the in-place path with the 16-CTA
+     * cluster line loop is faster there (measured crossover: a few thousand state entries) */
+    if (m >= 1 && m <= 8 && ctx->L_ub > 0 && 3 + 2 * ctx->L_ub >= kOverlapMinN)
+      return enqueue_scan_overlapped(ctx, d_u, d_x_t0, m, d_z, d_R);
     int rc = drain(ctx);
     if (rc) return rc;
     use_tables(ctx, 0);

@@ -97,3 +97,9 @@ class Robot:
     def getEllipse(self):
         """Robot::getEllipse (Robot.cpp:73-124) -> (ok, (axis0, axis1), angle)."""
         return self._f.get_ellipse()
+
+    def robotPosition(self):
+        """The node's `robotPosition` message (slam_ros/main.cpp:150-169): translation (x, y, theta) and
+        rotation.x/.y/.z = major axis, minor axis, ellipse angle."""
+        ok, ax, ang = self.getEllipse()
+        return {"translation": (self.xPos, self.yPos, self.thetaPos), "rotation": (ax[1], ax[0], ang), "ellipse_ok": ok}
