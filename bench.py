@@ -11,6 +11,8 @@ sweep), augmentation.  Workloads (BASELINE.json `configs`):
     1k       configs[1]  single filter, 1 000 landmarks (P fits L2: launch-bound, not HBM-bound)
     40k      configs[4]  single filter, 40 000 landmarks (51 GB); with --gpus N > 1 row-sharded over N ranks
     mc       configs[3]  Monte-Carlo batch, 4096 independent filters x 50 landmarks, sharded over ranks
+    room     configs[0]  the reference-sized filter (LINESIZE=100) on the synthetic room; its CPU baseline /
+                         reference arm is the LITERAL reference (oracle/_ref: Robot.cpp compiled over the GSL shim)
 
 With --gpus N > 1 (launched by torchrun, one rank per GPU) the default workload runs N independent
 filters (replicas; the path needs no collective) -> "scaling": "weak"; `40k` runs ONE filter row-sharded
@@ -42,6 +44,7 @@ WORKLOADS = {
     "1k": dict(N=1000, m=8, headroom=512, desc="configs[1]: single filter, 1k line landmarks, m=8"),
     "40k": dict(N=40000, m=8, headroom=1024, desc="configs[4]: single filter, 40k line landmarks, m=8"),
     "mc": dict(N=50, m=8, headroom=14, filters=4096, desc="configs[3]: Monte-Carlo batch, 4096 filters x 50 landmarks, m=8"),
+    "room": dict(N=100, m=9, headroom=0, desc="configs[0]: the reference-sized filter (LINESIZE=100) on the synthetic 2-D room, 361-beam scans"),
 }
 
 
@@ -164,11 +167,87 @@ def cpu_run(workload, steps, warmup, budget_s, threads=None):
     return val, info
 
 
+def literal_run(steps, warmup, budget_s):
+    """configs[0] on the reference ITSELF: oracle/_ref/libslamref.so = slam_ros/Robot.cpp (Q1-patched on a pipe)
+    compiled -O2 over the GSL shim, single thread (the reference has none), std::cout disabled (Q14)."""
+    from oracle.oracle import LiteralReference, have_literal
+    from slam_ros_b200 import scenario as sc
+    if not have_literal():
+        return None, {"kind": "reference", "unavailable": "oracle/_ref/libslamref.so not present (built only where /root/reference exists)"}
+    room = sc.room_scenario(steps=warmup + steps, seed=7, range_sigma=5e-5)
+    lit = LiteralReference()
+    def step(s):
+        m = room["count"][s]
+        y, P, L, pose = lit.state()
+        lit.localize(room["z"][s, :m], room["R"][s, :m], sc.encoder_for(pose, room["u"][s]))
+    for s in range(warmup):
+        step(s)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(warmup, warmup + steps):
+        step(s)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    val = done / dt
+    return val, {"kind": "reference", "cores": 1, "value": val, "unit": "steps/s",
+                 "sample": "%d Robot::localize calls of the literal reference (LINESIZE=100, g++ -O2, GSL shim, cout disabled) on the room scenario, including its state read-back through the harness" % done}
+
+
+def run_room(args, rank, world, local):
+    """configs[0] on the GPU through the host-buffer call (the drop-in's real use: one small filter, 10 Hz node)."""
+    import torch
+    from slam_ros_b200 import EkfFilter, scenario as sc
+    K, W = args.steps, args.warmup
+    torch.cuda.set_device(local)
+    room = sc.room_scenario(steps=W + K, seed=7, range_sigma=5e-5)
+    f = EkfFilter(capacity_lines=100, device=local)
+    f.profile_enable(True)
+    for s in range(W):
+        m = room["count"][s]
+        f.scan(room["u"][s], room["z"][s, :m], room["R"][s, :m])
+    f.sync(); f.profile_read()
+    clocks = ClockSampler(local); clocks.start()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        m = room["count"][s]
+        f.scan(room["u"][s], room["z"][s, :m], room["R"][s, :m])
+    f.sync()
+    ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop()
+    prof = f.profile_read()
+    peak, peak_src = measured_peaks()
+    n = 203
+    val = K / (ms / 1e3)
+    sweep_ms = prof["sweep_ms"] / max(prof["sweeps"], 1)
+    bytes_per_sweep = 8.0 * n * (n + 1)
+    return {
+        "metric": "EKF predict+update steps/s at N landmarks", "value": val, "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS["room"]["desc"], "capacity_lines": 100, "lines_per_scan_mean": float(room["count"][W:W + K].mean()),
+                   "l2": "P is 330 KB: resident in L2, the path is launch / latency bound (value == e2e: host buffers every step)"},
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_pipe", "achieved": bytes_per_sweep / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
+                     "peak": peak, "unit": "GB/s", "frac": (bytes_per_sweep / (sweep_ms * 1e-3) / 1e9 / peak) if sweep_ms > 0 else 0.0,
+                     "peak_source": peak_src, "launch_ms": sweep_ms, "launches_timed": prof["sweeps"],
+                     "algorithmic_bytes_per_launch": bytes_per_sweep, "traffic": None,
+                     "note": "not an HBM-bound configuration: 330 KB per sweep"},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": (6 + 6 * 9) * 8, "d2h_bytes_per_step": 4 * 9 + 128, "ms_per_step": ms / K},
+        "gpu_launches": prof["launches"], "clocks": clk,
+    }
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    val, info = cpu_run(args.workload, args.steps, args.warmup, budget_s=150.0)
+    if args.workload == "room":
+        val, info = literal_run(args.steps, args.warmup, budget_s=150.0)
+        if val is None:
+            print(json.dumps({"impl": "reference", "unavailable": info["unavailable"]}), flush=True)
+            return
+    else:
+        val, info = cpu_run(args.workload, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "EKF predict+update steps/s at N landmarks", "value": val, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val,
@@ -396,12 +475,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- libekfcuda has no CPU fallback (use --impl reference for the CPU arm)")
     if args.workload == "mc":
         line = run_monte_carlo(args, rank, world, local)
+    elif args.workload == "room":
+        line = run_room(args, rank, world, local) if rank == 0 else None
     else:
         sharded = args.workload == "40k" and world > 1
         line = run_single_or_replicas(args, rank, world, local, sharded)
     if rank == 0 and line is not None:
         if world == 1 and not args.no_cpu_baseline:
-            val, info = cpu_run(args.workload, steps=1000, warmup=1, budget_s=args.cpu_budget)
+            if args.workload == "room":
+                val, info = literal_run(steps=1000, warmup=3, budget_s=args.cpu_budget)
+            else:
+                val, info = cpu_run(args.workload, steps=1000, warmup=1, budget_s=args.cpu_budget)
             line["cpu_baseline"] = info
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -418,3 +418,32 @@ def test_full_size_10k_landmarks_against_oracle(libekf, oracle_cls):
         tr_after = f.cov_stats()[0]
         assert rc == 0 and (j >= 0).sum() >= m - 2
         assert tr_after < tr_before + 1e-2                         # prediction adds <= 4q ~ 2e-3; updates only remove
+
+
+def test_overlapped_pipeline_interleaved_with_stepwise_calls(libekf, oracle_cls):
+    """A map large enough (n = 6203) for the overlapped two-stream path, with fused scans, step-wise scans,
+    downloads and sweep probes interleaved: every switch drains the sweep in flight."""
+    N, steps, m = 3100, 14, 8
+    scn = sc.map_scenario(N, steps, m=m, seed=23)
+    f, so = seed_pair(N, N + 64, oracle_cls, scn)
+    so._lib.ekfo_set_threads(so._h, 0)
+    for s in range(steps):
+        z, R, u = scn["z"][s], scn["R"][s], scn["u"][s]
+        if s % 4 == 2:                                   # step-wise scan in the middle of overlapped ones
+            f.predict(u); so.predict(u)
+            for i in range(m):
+                jg, _ = f.associate(z[i], R[i]); jo, _, _ = so.associate(z[i], R[i])
+                assert jg == jo
+                if jg >= 0:
+                    f.update(jg, z[i], R[i]); so.update(jo, z[i], R[i])
+                else:
+                    f.add_line(z[i], R[i]); so.queue(i)
+            rc, pose = f.end_scan(m); so.end(z, R)
+        else:
+            rc, j, pose = f.scan(u, z, R)
+            st, jo = so.scan(u, z, R)
+            assert np.array_equal(j, jo), "step %d" % s
+        if s % 5 == 4:
+            f.sweep_probe(m=3, repeats=1)               # forces a drain; must leave the state untouched
+            compare_state(f, so, "interleaved step %d" % s)
+    compare_state(f, so, "interleaved final")
