@@ -288,6 +288,12 @@ def run_single_or_replicas(args, rank, world, local, sharded):
     total_steps = W + K + K            # device-resident leg, then the host-buffer (e2e) leg
     scn = sc.map_scenario(N, total_steps, m=m, seed=seed)
     f = EkfFilter(capacity_lines=N + w["headroom"], device=local, shard=shard)
+    exchange = None
+    if shard is not None:
+        # fused exchange over NVLink peer memory inside the line-loop kernel (EKF_SHARD_NCCL=1 keeps the NCCL path)
+        from slam_ros_b200.parallel import connect_shards
+        fused = os.environ.get("EKF_SHARD_NCCL", "0") != "1" and connect_shards(f, dev)
+        exchange = "in-kernel NVLink stores (CUDA IPC peer memory)" if fused else "ncclAllReduce per matched line"
     rc, j, pose = f.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
     assert rc == 0 and f.lines == N, (rc, f.lines)
 
@@ -359,6 +365,7 @@ def run_single_or_replicas(args, rank, world, local, sharded):
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "landmarks": N, "state_dim": n, "lines_per_scan": m,
                    "matched_per_step": mean_terms, "parallelism": ("row-sharded P x%d" % world) if sharded else ("independent filters x%d" % world),
+                   "exchange": exchange,
                    "l2": "per-step working set %.2f GB read + %.2f GB written >> 126 MB L2: no flush needed" % (8.0 * n * (n + 1) / 2 / 1e9, 8.0 * n * (n + 1) / 2 / 1e9),
                    "seed": seed},
         "roofline": {"bound": "hbm", "kernel": "k_sweep_pipe (P -= (K S) K' over the upper triangle; TMA + mbarrier ring, runs under the next scan's line loop)",

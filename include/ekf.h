@@ -159,6 +159,18 @@ int ekf_nccl_unique_id(unsigned char id[128]);
 int ekf_create_sharded(ekf_ctx** out, const ekf_config* cfg, int rank, int world,
                        const unsigned char nccl_unique_id[128]);
 
+/* Fused exchange: after ekf_shard_connect the H-column slices no longer go through NCCL.  The line-loop kernel
+ * itself stores the slice entries a rank owns straight into every peer's exchange buffer over NVLink (peer memory
+ * mapped with CUDA IPC), publishes an arrival epoch with a system-scope release store and spins (bounded) on its
+ * own flags -- one NVLink round trip per matched line, no kernel boundary, and the scan's sweep then overlaps
+ * the next scan's line loop exactly as on one GPU.  ekf_shard_ipc_handle returns the 64-byte cudaIpcMemHandle_t
+ * of this rank's buffer; the host all-gathers the handles (rank order, world x 64 bytes) and hands them to
+ * ekf_shard_connect on every rank.  world <= 8 (one NVSwitch domain).  If a peer cannot be mapped the call
+ * returns EKF_ECUDA and the filter stays on the NCCL exchange.  A peer that never arrives makes the scan return
+ * EKF_ENCCL instead of hanging the GPU. */
+int ekf_shard_ipc_handle(ekf_ctx* ctx, unsigned char handle[64]);
+int ekf_shard_connect(ekf_ctx* ctx, const unsigned char* handles);
+
 /* --- independent filters (Monte-Carlo batch): no communication -------------------------------------
  * B filters of identical capacity on one device, one thread block per filter, covariance staged in
  * shared memory for the whole scan. */

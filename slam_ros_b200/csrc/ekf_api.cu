@@ -91,6 +91,10 @@ struct ekf_ctx {
   int sweep_shape;     /* 0: 64x64 tiles, 1: 32x128, 2: 16x256 (EKF_SWEEP_SHAPE) */
   /* sharded */
   ncclComm_t comm;
+  double* xchg;               /* this rank's exchange buffer: [2 halves][colA | colB][ld] doubles + 8 arrival flags */
+  void* peer_map[8];          /* the peers' buffers as mapped by cudaIpcOpenMemHandle (NULL for the local one) */
+  EkfPeers peers;
+  int peers_ok;               /* ekf_shard_connect succeeded: the H-column slices travel inside the line-loop kernel */
   /* staging for download / upload / stats */
   double* d_stage; size_t stage_elems;
   double* d_partials; double* d_out3;
@@ -324,7 +328,7 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
   /* The line loop runs as EKF_LINE_SMS cooperative CTAs on the SMs the in-flight sweep leaves free (its
    * persistent grid is num_sms - EKF_LINE_SMS): no register / FP64-issue sharing with the sweep. */
   CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, 0, m, EKF_LINE_SMS, 1, slot0, ctx->pg_slot0,
-                           ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->stream));
+                           ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->stream));
   const int tgt = ctx->pg_valid ? (ctx->rd ^ 1) : ctx->rd;      /* source of this scan's sweep */
   EkfBuffers bt = ctx->b;
   bt.P = ctx->Pbuf[tgt];
@@ -376,13 +380,17 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
   if (ctx->L_ub == 0) {
     CU(ekf_launch_queue_all(ctx->g, ctx->b, m, ctx->stream));
     if (m > 0) ctx->launches++;
-  } else if (ctx->g.world == 1 && ctx->cfg.max_batch <= 64 && !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS))) {
+  } else if ((ctx->g.world == 1 || ctx->peers_ok) && ctx->cfg.max_batch <= 64 &&
+             !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS))) {
     /* fused: all lines in one cluster launch; split only where the pending list would overflow */
     int i0 = 0;
     while (i0 < m) {
       int cnt = ctx->cfg.max_batch - ctx->pend_ub;
       if (cnt > m - i0) cnt = m - i0;
-      CU(ekf_launch_scan_lines(ctx->g, ctx->b, d_z, d_R, i0, i0 + cnt, ctx->cluster, 0, 0, 0, 0, ctx->stream));
+      /* row-sharded: the same kernel, launched cooperatively (its CTAs spin on the peers' arrival flags, so they
+       * must all be resident), exchanges the H-column slices over NVLink peer memory between its phases */
+      CU(ekf_launch_scan_lines(ctx->g, ctx->b, d_z, d_R, i0, i0 + cnt, ctx->cluster, ctx->peers_ok ? 1 : 0, 0, 0, 0,
+                               ctx->peers_ok ? &ctx->peers : 0, ctx->stream));
       ctx->launches++;
       ctx->pend_ub += cnt;
       i0 += cnt;
@@ -413,8 +421,30 @@ int read_state(ekf_ctx* ctx) {
 }
 
 int sticky_to_status(int sticky) {
+  if (sticky & EKF_STICKY_XCHG) return EKF_ENCCL;
   if (sticky & EKF_STICKY_CAPACITY) return EKF_ECAPACITY;
   if (sticky & EKF_STICKY_SINGULAR) return EKF_ESINGULAR;
+  return EKF_OK;
+}
+
+/* Second covariance buffer, sweep stream and events of the overlapped pipeline (enqueue_scan_overlapped). */
+int enable_overlap(ekf_ctx* ctx) {
+  if (ctx->overlap) return EKF_OK;
+  if (ctx->cfg.max_batch < 16 ||
+      (ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS | EKF_FLAG_SWEEP_DIRECT | EKF_FLAG_NO_OVERLAP)))
+    return EKF_OK;
+  const size_t bytes = (size_t)ekf_local_tile_rows(ctx->g) * EKF_TILE * (size_t)ctx->g.ld * sizeof(double);
+  CU(cudaMalloc(&ctx->Pbuf[1], bytes));
+  CU(cudaMemsetAsync(ctx->Pbuf[1], 0, bytes, ctx->stream));
+  CU(cudaStreamCreateWithFlags(&ctx->wstream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->evE, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->evF[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&ctx->evF[1], cudaEventDisableTiming));
+  { int rc = make_tensor_map(ctx, (size_t)ekf_local_tile_rows(ctx->g) * EKF_TILE, ctx->Pbuf[1], &ctx->tmap2[1]); if (rc) return rc; }
+  ekf_prefer_max_smem_carveout();
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->rd = 0; ctx->par = 0; ctx->pg_valid = 0;
+  ctx->overlap = 1;
   return EKF_OK;
 }
 
@@ -433,6 +463,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8;
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
   ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);
+  ctx->xchg = 0; ctx->peers_ok = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
   *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -455,17 +486,8 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMalloc(&ctx->b.diag, 4 * (size_t)g.cap * sizeof(double)));
   CU(cudaMalloc(&ctx->b.P, p_rows * ld * sizeof(double)));
   ctx->Pbuf[0] = ctx->b.P; ctx->Pbuf[1] = 0;
-  ctx->overlap = (world == 1 && ctx->cfg.max_batch >= 16 &&
-                  !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS | EKF_FLAG_SWEEP_DIRECT | EKF_FLAG_NO_OVERLAP))) ? 1 : 0;
+  ctx->overlap = 0;
   ctx->group = 8;
-  if (ctx->overlap) {
-    CU(cudaMalloc(&ctx->Pbuf[1], p_rows * ld * sizeof(double)));
-    CU(cudaMemsetAsync(ctx->Pbuf[1], 0, p_rows * ld * sizeof(double), ctx->stream));
-    CU(cudaStreamCreateWithFlags(&ctx->wstream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&ctx->evE, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx->evF[0], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx->evF[1], cudaEventDisableTiming));
-  }
   CU(cudaMalloc(&ctx->d_counters, 32 * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_view, 2 * sizeof(EkfScanView)));
   CU(cudaMemsetAsync(ctx->d_view, 0, 2 * sizeof(EkfScanView), ctx->stream));
@@ -479,12 +501,12 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
   { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
-  if (ctx->overlap) { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[1], &ctx->tmap2[1]); if (rc) return rc; }
   { int tr = 64, tc = 64; ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
     int rc = make_band_map(ctx, ctx->b.Kp, tc, &ctx->tmapK[0]); if (rc) return rc;
     rc = make_band_map(ctx, ctx->b.KSp, tr, &ctx->tmapK[1]); if (rc) return rc; }
   ctx->cluster = ekf_pick_cluster();
-  if (ctx->overlap) ekf_prefer_max_smem_carveout();
+  /* a row-sharded filter overlaps only once its peers are connected (ekf_shard_connect) */
+  if (world == 1) { int rc = enable_overlap(ctx); if (rc) return rc; }
   CU(cudaMalloc(&ctx->d_partials, 3 * (size_t)g.n * sizeof(double)));
   CU(cudaMalloc(&ctx->d_out3, 3 * sizeof(double)));
   CU(cudaMemsetAsync(ctx->b.st, 0, sizeof(EkfDevState), ctx->stream));
@@ -500,6 +522,11 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   if (rc) return rc;
   CU(ekf_launch_init(g, ctx->b, ctx->stream));
   if (world > 1) {
+    if (world <= 8) {     /* exchange buffer of the in-kernel NVLink path (mapped by the peers through CUDA IPC) */
+      const size_t xb = (4 * ld + 16) * sizeof(double);
+      CU(cudaMalloc(&ctx->xchg, xb));
+      CU(cudaMemsetAsync(ctx->xchg, 0, xb, ctx->stream));
+    }
     NcclApi* api = nccl_api();
     if (!api || !uid) { snprintf(ctx->err, sizeof ctx->err, "libnccl.so.2 could not be loaded"); return EKF_ENCCL; }
     ncclUniqueId id;
@@ -574,12 +601,53 @@ int ekf_create_sharded(ekf_ctx** out, const ekf_config* cfg, int rank, int world
   return create_common(out, cfg, rank, world, uid);
 }
 
+int ekf_shard_ipc_handle(ekf_ctx* ctx, unsigned char handle[64]) {
+  if (!ctx || !handle) return EKF_EINVAL;
+  if (!ctx->xchg) { snprintf(ctx->err, sizeof ctx->err, "not a row-sharded filter (or world > 8)"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->xchg));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  memcpy(handle, &h, 64);
+  return EKF_OK;
+}
+
+int ekf_shard_connect(ekf_ctx* ctx, const unsigned char* handles) {
+  if (!ctx || !handles) return EKF_EINVAL;
+  if (!ctx->xchg) { snprintf(ctx->err, sizeof ctx->err, "not a row-sharded filter (or world > 8)"); return EKF_ESTATE; }
+  if (ctx->scan_open) return EKF_ESTATE;
+  if (ctx->peers_ok) return EKF_OK;
+  CU(cudaSetDevice(ctx->cfg.device));
+  const int world = ctx->g.world, rank = ctx->g.rank;
+  memset(&ctx->peers, 0, sizeof ctx->peers);
+  ctx->peers.world = world; ctx->peers.rank = rank;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { ctx->peers.xchg[p] = ctx->xchg; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)p, 64);
+    void* ptr = 0;
+    const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      snprintf(ctx->err, sizeof ctx->err, "cudaIpcOpenMemHandle(rank %d): %s -- staying on the NCCL exchange", p, cudaGetErrorString(e));
+      for (int q = 0; q < p; ++q) if (ctx->peer_map[q]) { cudaIpcCloseMemHandle(ctx->peer_map[q]); ctx->peer_map[q] = 0; }
+      return EKF_ECUDA;
+    }
+    ctx->peer_map[p] = ptr;
+    ctx->peers.xchg[p] = (double*)ptr;
+  }
+  ctx->peers_ok = 1;
+  return enable_overlap(ctx);
+}
+
 int ekf_destroy(ekf_ctx* ctx) {
   if (!ctx) return EKF_EINVAL;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->wstream) cudaStreamSynchronize(ctx->wstream);
   if (ctx->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(ctx->comm); }
+  for (int p = 0; p < 8; ++p) if (ctx->peer_map[p]) cudaIpcCloseMemHandle(ctx->peer_map[p]);
+  cudaFree(ctx->xchg);
   free_line_tables(ctx);
   cudaFree(ctx->b.st); cudaFree(ctx->b.y); cudaFree(ctx->b.top); cudaFree(ctx->b.diag); cudaFree(ctx->Pbuf[0]); cudaFree(ctx->Pbuf[1]);
   cudaFree(ctx->d_view); cudaFree(ctx->d_counters);

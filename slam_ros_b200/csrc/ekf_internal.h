@@ -27,6 +27,7 @@
 #define EKF_NO_MATCH INT_MAX
 #define EKF_STICKY_CAPACITY 1
 #define EKF_STICKY_SINGULAR 2
+#define EKF_STICKY_XCHG 4               /* a peer never arrived at the cross-GPU exchange (row-sharded mode) */
 
 struct EkfDevState {          /* one per filter, in global memory */
   double pose[3];             /* xPos, yPos, thetaPos (Robot.h:54-56) */
@@ -40,11 +41,14 @@ struct EkfDevState {          /* one per filter, in global memory */
   int resets;                 /* map resets so far (Robot.cpp:893-904) */
   int pbase;                  /* matches of this scan already folded into P by a mid-scan flush */
   int np;                     /* pending rank-2 terms = pidx[line] - pbase */
-  int pad;
+  int xseq;                   /* row-sharded mode: matched lines exchanged over NVLink so far (same on every rank) */
 };
 
 /* what a scan's (possibly later, possibly concurrent) sweep needs to know about that scan */
 struct EkfScanView { int cnt; int L; int pad[2]; };
+
+/* row-sharded mode: every rank's exchange buffer as mapped into THIS process (CUDA IPC); [rank] is the local one */
+struct EkfPeers { double* xchg[8]; int world, rank; };
 
 /* geometry handed to every kernel by value */
 struct EkfGeom {
@@ -93,7 +97,7 @@ void ekf_prefer_max_smem_carveout(void);
 /* all lines [line0, line1) of the open scan in one cluster launch (single-GPU path) */
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                   int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
-                                  const int* prev_cnt_ptr, cudaStream_t s);
+                                  const int* prev_cnt_ptr, const EkfPeers* peers, cudaStream_t s);
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s);
 cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, cudaStream_t s);
 /* np_ptr: device int holding the number of pending terms (NULL = st->np); np_ub: host upper bound (selects the template) */

@@ -358,9 +358,10 @@ __device__ __forceinline__ void gain_row_load(const EkfGeom& g, const EkfBuffers
     for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.Kp[(size_t)pl.slot(t) * g.ld + r];
   }
 }
-__device__ __forceinline__ void gain_row_finish(const EkfGeom& g, const EkfBuffers& b, const Gate& G, int r, int npt,
-                                                int out_slot, GainRow& d, const PendingList& pl, const double2* s_ka,
-                                                const double2* s_kb, const double2* s_ksa, const double2* s_ksb) {
+/* applies the pending terms to the two cold entries of row r (d.pa, d.pb) */
+__device__ __forceinline__ void gain_row_correct(const EkfGeom& g, const EkfBuffers& b, int r, int npt, GainRow& d,
+                                                 const PendingList& pl, const double2* s_ka, const double2* s_kb,
+                                                 const double2* s_ksa, const double2* s_ksb) {
   if (d.kind == 1) {
     for (int i0 = 0; i0 < npt; i0 += 8) {
       if (i0 > 0) {
@@ -386,10 +387,45 @@ __device__ __forceinline__ void gain_row_finish(const EkfGeom& g, const EkfBuffe
       }
     }
   }
+}
+__device__ __forceinline__ void gain_row_emit(const EkfGeom& g, const EkfBuffers& b, const Gate& G, int r, int out_slot,
+                                              const GainRow& d) {
   double2 Kr, KSr;
   gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Kr, KSr);
   b.Kp[(size_t)out_slot * g.ld + r] = Kr;
   b.KSp[(size_t)out_slot * g.ld + r] = KSr;
+}
+
+/* ---- row-sharded mode: the H-column slices are exchanged INSIDE the line-loop kernel over NVLink peer memory.
+ * Every rank owns an exchange buffer [2 parities][colA | colB][ld] doubles followed by 8 arrival flags; peers map
+ * it (CUDA IPC) and store the slice entries they own straight into it, then publish an epoch in the flag word.
+ * No NCCL call, no kernel boundary: one NVLink round trip per matched line. ---- */
+__device__ __forceinline__ double* xchg_col(const EkfPeers& pe, const EkfGeom& g, int p, int par, int which) {
+  return pe.xchg[p] + ((size_t)(2 * par + which)) * g.ld;
+}
+__device__ __forceinline__ unsigned long long* xchg_flags(const EkfPeers& pe, const EkfGeom& g, int p) {
+  return reinterpret_cast<unsigned long long*>(pe.xchg[p] + (size_t)4 * g.ld);
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+/* called by ONE thread after a local barrier: tell every peer this rank's slice entries are in place, then wait
+ * for theirs.  Bounded spin: a missing peer raises a sticky error instead of hanging the GPU. */
+__device__ __forceinline__ void xgpu_exchange_barrier(const EkfPeers& pe, const EkfGeom& g, unsigned long long epoch, int* sticky) {
+  __threadfence_system();
+  for (int p = 0; p < pe.world; ++p) st_release_sys(xchg_flags(pe, g, p) + pe.rank, epoch);
+  const unsigned long long* mine = xchg_flags(pe, g, pe.rank);
+  for (int q = 0; q < pe.world; ++q) {
+    long long spins = 0;
+    while (ld_acquire_sys(mine + q) < epoch) {
+      if (++spins > 40000000LL) { atomicOr(sticky, EKF_STICKY_XCHG); break; }
+    }
+  }
 }
 
 #ifdef EKF_LINE_TIMING
@@ -408,10 +444,11 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
  * COOP = true : the same CTAs are launched cooperatively and synchronise with a grid barrier instead, so
  *               they need not sit in one GPC -- this is the form that runs on the SMs the overlapped sweep
  *               leaves free (see enqueue_scan_overlapped). */
-template <int FL_THREADS, bool COOP>
+template <int FL_THREADS, bool COOP, bool SHARD>
 __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_lines(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
                                                               const double* __restrict__ R, int line0, int line1,
-                                                              int own_slot0, int prev_slot0, const int* __restrict__ prev_cnt_ptr) {
+                                                              int own_slot0, int prev_slot0, const int* __restrict__ prev_cnt_ptr,
+                                                              EkfPeers pe) {
   __shared__ int s_min[FL_THREADS / 32];
   __shared__ double2 s_ka[FL_MAXP], s_kb[FL_MAXP], s_ksa[FL_MAXP], s_ksb[FL_MAXP];
   const int prev_cnt = prev_cnt_ptr ? *prev_cnt_ptr : 0;   /* previous scan's terms not yet folded into b.P */
@@ -424,6 +461,10 @@ __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_
   const int L = st->L, nl = 3 + 2 * L, epoch = st->epoch, pbase = st->pbase;
   int nm = b.pidx[line0];             /* matches of this scan so far: tracked identically by every thread */
   int ne = b.eidx[line0];
+  /* exchanges done so far over the life of the filter: numbers the arrival epochs and alternates the two halves
+   * of the exchange buffers (a per-scan count would let a fast rank overwrite a half a peer is still reading) */
+  const int xseq0 = SHARD ? st->xseq : 0;
+  int xdone = 0;
   double A[3][3], xp[3];              /* every thread's own copy of P[0:3,0:3] (mirrored) and x_pre */
   load_rr(g, b.top, A);
   xp[0] = st->x_pre[0]; xp[1] = st->x_pre[1]; xp[2] = st->x_pre[2];
@@ -534,13 +575,65 @@ __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_
     GainRow d;
     int r = gtid;
     TS(4);
-    if (r < nl) gain_row_load(g, b, A, r, j, npt, pl, d);
-    __syncthreads();
-    TS(5);
-    while (r < nl) {
-      gain_row_finish(g, b, G, r, npt, own_slot0 + np, d, pl, s_ka, s_kb, s_ksa, s_ksb);
-      r += gstride;
+    if (!SHARD) {
       if (r < nl) gain_row_load(g, b, A, r, j, npt, pl, d);
+      __syncthreads();
+      TS(5);
+      while (r < nl) {
+        gain_row_correct(g, b, r, npt, d, pl, s_ka, s_kb, s_ksa, s_ksb);
+        gain_row_emit(g, b, G, r, own_slot0 + np, d);
+        r += gstride;
+        if (r < nl) gain_row_load(g, b, A, r, j, npt, pl, d);
+      }
+    } else {
+      /* part 1: every rank computes the current value of the cold slice entries it OWNS (row owner) and stores
+       * them straight into every rank's exchange buffer over NVLink */
+      const int xpar = (xseq0 + xdone) & 1;
+      __syncthreads();
+      for (; r < nl; r += gstride) {
+        if (r <= 2 || r == a || r == bb) continue;                   /* hot entries are replicated */
+        const int own_a = owner_of_row(g, min(r, a)), own_b = owner_of_row(g, min(r, bb));
+        if (own_a != g.rank && own_b != g.rank) continue;
+        double pa = 0.0, pb = 0.0;
+        if (r < a) {                                                  /* P[r,a], P[r,b]: both in row r */
+          const double* Pr = b.P + local_row(g, r) * g.ld;
+          pa = Pr[a]; pb = Pr[bb];
+          for (int i = 0; i < npt; ++i) {
+            const double2 v = b.KSp[(size_t)pl.slot(i) * g.ld + r];
+            pa = sub_rank2(pa, v, s_ka[i]); pb = sub_rank2(pb, v, s_kb[i]);
+          }
+        } else {                                                      /* P[a,r] (owner of row a), P[b,r] (owner of row b) */
+          if (own_a == g.rank) pa = b.P[local_row(g, a) * g.ld + r];
+          if (own_b == g.rank) pb = b.P[local_row(g, bb) * g.ld + r];
+          for (int i = 0; i < npt; ++i) {
+            const double2 v = b.Kp[(size_t)pl.slot(i) * g.ld + r];
+            pa = sub_rank2(pa, s_ksa[i], v); pb = sub_rank2(pb, s_ksb[i], v);
+          }
+        }
+        for (int p = 0; p < pe.world; ++p) {
+          if (own_a == g.rank) xchg_col(pe, g, p, xpar, 0)[r] = pa;
+          if (own_b == g.rank) xchg_col(pe, g, p, xpar, 1)[r] = pb;
+        }
+      }
+      __threadfence_system();
+      group_sync();
+      if (gtid == 0) xgpu_exchange_barrier(pe, g, (unsigned long long)(xseq0 + xdone) + 1ull, &st->sticky);
+      xdone += 1;
+      group_sync();
+      /* part 2: every rank forms the full K, K S (replicated) from the gathered slices */
+      const double* cA = xchg_col(pe, g, g.rank, xpar, 0);
+      const double* cB = xchg_col(pe, g, g.rank, xpar, 1);
+      for (r = gtid; r < nl; r += gstride) {
+        GainRow e;
+        if (r <= 2) { e.p0 = A[r][0]; e.p1 = A[r][1]; e.p2 = A[r][2]; e.pa = b.top[(size_t)r * g.ld + a]; e.pb = b.top[(size_t)r * g.ld + bb]; }
+        else {
+          e.p0 = b.top[r]; e.p1 = b.top[(size_t)g.ld + r]; e.p2 = b.top[(size_t)2 * g.ld + r];
+          if (r == a) { e.pa = b.diag[4 * j]; e.pb = b.diag[4 * j + 1]; }
+          else if (r == bb) { e.pa = b.diag[4 * j + 1]; e.pb = b.diag[4 * j + 2]; }
+          else { e.pa = __ldcg(cA + r); e.pb = __ldcg(cB + r); }
+        }
+        gain_row_emit(g, b, G, r, own_slot0 + np, e);
+      }
     }
     if (gtid == 0) {                                                  /* :501-504 bookkeeping (read after the next barrier) */
       b.matched[j] = epoch;
@@ -557,6 +650,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_
     pv0 = G.v[0]; pv1 = G.v[1];
     for (int t = 0; t < 4; ++t) pS[t] = G.S[t];
   }
+  if (SHARD && gtid == 0) st->xseq = xseq0 + xdone;   /* every thread read xseq0 before the first barrier */
 }
 
 /* after a sweep in the middle of a scan: the pending list restarts empty */
@@ -1095,8 +1189,9 @@ extern "C" int ekf_debug_line_timing(unsigned long long* out, int n) {
 void ekf_prefer_max_smem_carveout(void) {
   const int c = cudaSharedmemCarveoutMaxShared;
   cudaFuncSetAttribute(k_predict, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(k_scan_lines<512, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(k_scan_lines<512, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines<512, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines<512, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines<512, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_a, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_b, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_c, cudaFuncAttributePreferredSharedMemoryCarveout, c);
@@ -1104,7 +1199,7 @@ void ekf_prefer_max_smem_carveout(void) {
   (void)cudaGetLastError();
 }
 int ekf_pick_cluster(void) {
-  cudaFuncSetAttribute(k_scan_lines<512, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_scan_lines<512, false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   const int tries[2] = {16, 8};
   for (int t = 0; t < 2; ++t) {
     cudaLaunchConfig_t cfg;
@@ -1115,19 +1210,25 @@ int ekf_pick_cluster(void) {
     attr[0].val.clusterDim.x = tries[t]; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines<512, false>, &cfg) == cudaSuccess && n >= 1) return tries[t];
+    if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines<512, false, false>, &cfg) == cudaSuccess && n >= 1) return tries[t];
   }
   (void)cudaGetLastError();
   return 8;
 }
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                   int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
-                                  const int* prev_cnt_ptr, cudaStream_t s) {
+                                  const int* prev_cnt_ptr, const EkfPeers* peers, cudaStream_t s) {
   if (line1 <= line0) return cudaSuccess;
+  EkfPeers pe;
+  memset(&pe, 0, sizeof pe);
+  pe.world = 1;
+  if (peers) pe = *peers;
   if (coop) {
     void* args[] = {(void*)&g, (void*)&b, (void*)&d_z, (void*)&d_R, (void*)&line0, (void*)&line1, (void*)&own_slot0,
-                    (void*)&prev_slot0, (void*)&prev_cnt_ptr};
-    return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true>, dim3(ctas), dim3(512), args, 0, s);
+                    (void*)&prev_slot0, (void*)&prev_cnt_ptr, (void*)&pe};
+    if (peers && peers->world > 1)
+      return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, true>, dim3(ctas), dim3(512), args, 0, s);
+    return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, false>, dim3(ctas), dim3(512), args, 0, s);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -1136,7 +1237,7 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_scan_lines<512, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
+  return cudaLaunchKernelEx(&cfg, k_scan_lines<512, false, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr, pe);
 }
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
   k_flush_done<<<1, 32, 0, s>>>(b, next_line);

@@ -44,7 +44,7 @@ SYMBOLS = [
     "ekf_update", "ekf_add_line", "ekf_end_scan", "ekf_scan", "ekf_scan_device", "ekf_sync", "ekf_get_state",
     "ekf_get_robot_cov", "ekf_get_ellipse", "ekf_download", "ekf_upload", "ekf_download_live",
     "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
-    "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
+    "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_shard_ipc_handle", "ekf_shard_connect", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
     "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
 ]
 
@@ -68,6 +68,8 @@ def load_library():
     lib.ekf_create.argtypes = [C.POINTER(vp), C.POINTER(EkfConfig)]
     lib.ekf_create_sharded.argtypes = [C.POINTER(vp), C.POINTER(EkfConfig), C.c_int, C.c_int, C.c_char_p]
     lib.ekf_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.ekf_shard_ipc_handle.argtypes = [vp, C.c_char_p]
+    lib.ekf_shard_connect.argtypes = [vp, C.c_char_p]
     lib.ekf_destroy.argtypes = [vp]
     lib.ekf_predict.argtypes = [vp, _dp, _dp, _dp]
     lib.ekf_associate.argtypes = [vp, _dp, _dp, _ip, _dp]
@@ -166,6 +168,23 @@ class EkfFilter:
     @property
     def handle(self):
         return self._h
+
+    # -- row-sharded mode: in-kernel NVLink exchange ------------------------------------------------
+    def shard_ipc_handle(self):
+        """64-byte CUDA IPC handle of this rank's exchange buffer."""
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.ekf_shard_ipc_handle(self._h, buf), "ekf_shard_ipc_handle")
+        return buf.raw
+
+    def shard_connect(self, handles):
+        """handles: the ranks' IPC handles in rank order (list of 64-byte strings).  Returns True when the peers
+        are mapped (fused exchange + overlapped sweep), False when the filter stays on the NCCL exchange."""
+        blob = b"".join(bytes(h) for h in handles)
+        rc = self._lib.ekf_shard_connect(self._h, blob)
+        if rc == EKF_ECUDA:
+            return False
+        self._check(rc, "ekf_shard_connect")
+        return True
 
     # -- step-wise path (one call per reference block) -----------------------------------------------
     def predict(self, u, x_t0=None):

@@ -47,6 +47,21 @@ def gather_filter_results(local_ids, local_values, n_filters, group=None):
     return out.numpy()
 
 
+def connect_shards(filt, device, group=None):
+    """Row-sharded filter: all-gather the ranks' CUDA IPC handles with torch.distributed and map the peers'
+    exchange buffers (ekf_shard_connect).  Returns True on every rank iff every rank connected."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.tensor(list(filt.shard_ipc_handle()), dtype=torch.uint8, device=device)
+    allh = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    ok = filt.shard_connect([bytes(h.cpu().tolist()) for h in allh])
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag[0]))
+
+
 def max_over_ranks(value, group=None):
     """Timing rule: a multi-GPU number is the max over ranks."""
     import torch

@@ -30,6 +30,10 @@ def main():
     dist.broadcast(uid, 0)
     cap = N + 64
     f = EkfFilter(capacity_lines=cap, device=local, shard=(rank, world, bytes(uid.cpu().tolist())))
+    mode = sys.argv[3] if len(sys.argv) > 3 else "fused"
+    if mode == "fused":                     # in-kernel NVLink exchange; "nccl" keeps the ncclAllReduce path
+        from slam_ros_b200.parallel import connect_shards
+        assert connect_shards(f, dev), "CUDA IPC peer mapping failed"
     so = StructuredOracle(cap)
     scn = sc.map_scenario(N, steps, m=8, seed=5)
     rc, j, pose = f.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
@@ -55,7 +59,7 @@ def main():
     assert abs(float(tt[0]) - np.trace(Po)) / abs(np.trace(Po)) < 1e-9
     ms = f.sweep_probe(m=8, repeats=3)
     if rank == 0:
-        print("sharded x%d OK: N=%d steps=%d  P rel err %.2e  local sweep %.3f ms" % (world, N, steps, err, ms), flush=True)
+        print("sharded x%d OK (%s): N=%d steps=%d  P rel err %.2e  local sweep %.3f ms" % (world, mode, N, steps, err, ms), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
