@@ -467,10 +467,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="10k", choices=sorted(WORKLOADS))
+    ap.add_argument("--lines", type=int, default=0, help="observed lines per scan (default: the workload's m = 8; "
+                    "configs[2] also names m = 32 and 64: one rank-2m sweep per scan)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
+    if args.lines > 0 and args.workload in ("10k", "1k", "40k"):
+        w = WORKLOADS[args.workload]
+        w["desc"] = w["desc"].replace("m=%d" % w["m"], "m=%d" % args.lines)
+        w["m"] = args.lines
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank, world, local = dist_env()

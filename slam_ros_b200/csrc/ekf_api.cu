@@ -219,7 +219,8 @@ int launch_sweep(ekf_ctx* ctx, int np_ub) {
   } else {
     CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmap2[ctx->rd], &ctx->tmapK[0], &ctx->tmapK[1], ctx->b.P, 0, 0, ctx->d_counters, ctx->sweep_shape, np_ub,
                             ctx->L_ub, ctx->num_sms, ctx->stream));
-    ctx->launches += (np_ub + 7) / 8;
+    const int per_pass = ekf_sweep_terms_per_pass(ctx->sweep_shape, np_ub);
+    ctx->launches += (np_ub + per_pass - 1) / per_pass;
   }
   return EKF_OK;
 }
@@ -367,7 +368,7 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
   if (ctx->overlap) {
     /* small maps: the sweep is a few microseconds, nothing to hide -- the in-place path with the 16-CTA
      * cluster line loop is faster there (measured crossover: a few thousand state entries) */
-    if (m >= 1 && m <= 8 && ctx->L_ub > 0 && 3 + 2 * ctx->L_ub >= kOverlapMinN)
+    if (m >= 1 && m <= ctx->group && ctx->L_ub > 0 && 3 + 2 * ctx->L_ub >= kOverlapMinN)
       return enqueue_scan_overlapped(ctx, d_u, d_x_t0, m, d_z, d_R);
     int rc = drain(ctx);
     if (rc) return rc;
@@ -487,7 +488,9 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMalloc(&ctx->b.P, p_rows * ld * sizeof(double)));
   ctx->Pbuf[0] = ctx->b.P; ctx->Pbuf[1] = 0;
   ctx->overlap = 0;
-  ctx->group = 8;
+  /* lines per overlapped scan: the pending-slot ring holds two scans' terms ([2][group] slots) and one out-of-place
+   * sweep pass folds at most 32 */
+  ctx->group = ctx->cfg.max_batch / 2 < 32 ? ctx->cfg.max_batch / 2 : 32;
   CU(cudaMalloc(&ctx->d_counters, 32 * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_view, 2 * sizeof(EkfScanView)));
   CU(cudaMemsetAsync(ctx->d_view, 0, 2 * sizeof(EkfScanView), ctx->stream));
@@ -500,6 +503,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
+  { const int cap = ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
   { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
   { int tr = 64, tc = 64; ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
     int rc = make_band_map(ctx, ctx->b.Kp, tc, &ctx->tmapK[0]); if (rc) return rc;

@@ -10,6 +10,7 @@
  */
 #include "ekf_internal.h"
 #include "ekf_device.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <cuda.h>
 #include <cooperative_groups.h>
@@ -753,15 +754,15 @@ __global__ void __launch_bounds__(EKF_BLOCK, 2) k_sweep(EkfGeom g, EkfBuffers b,
  * with it.  No masks (see k_sweep). */
 #define SW_C 8                        /* pending terms per pass */
 
-template <int TR, int TC>
+template <int TR, int TC, int C>
 struct __align__(128) SweepStage {
   double P[TR * TC];                  /* 32768 B, row-major TR x TC, written by TMA */
-  double2 K[SW_C][TC];                /* K_c for the tile's columns */
-  double2 KS[SW_C][TR];               /* (K S)_c for the tile's rows */
+  double2 K[C][TC];                   /* K_c for the tile's columns */
+  double2 KS[C][TR];                  /* (K S)_c for the tile's rows */
 };
-template <int TR, int TC, int STAGES>
+template <int TR, int TC, int STAGES, int C>
 struct SweepShared {
-  SweepStage<TR, TC> stage[STAGES];
+  SweepStage<TR, TC, C> stage[STAGES];
   unsigned long long full[STAGES];
   unsigned long long empty[STAGES];
   int meta[STAGES][4];                /* first local row, first global row, first column, - */
@@ -813,19 +814,22 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
  * covered by, for each 64-row ownership block gb (this rank's: gb = rank + world*k), the 64/TR sub-row
  * blocks times the tile columns cb >= floor(64*gb / TC).  Tiles are numbered in that order; the
  * producer walks its tiles in increasing order, so it decodes incrementally (no division, no sqrt). */
-template <int TR, int TC, int STAGES, int CW>
+/* C = pending terms applied per pass (8, 16 or 32).  Up to ~16 terms the pass stays HBM-bound (8 terms keep the
+ * fp64 pipe 34 % busy); 32 terms are fp64-issue-bound (~1.35x the HBM time) -- still far cheaper than four
+ * HBM-bound passes of 8.  The ring shrinks with C (4 / 3 / 2 stages) to stay inside 227 KB. */
+template <int TR, int TC, int STAGES, int CW, int C>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapK,
              const __grid_constant__ CUtensorMap tmapKS, double* __restrict__ dst, int c0,
              int slot0, const EkfScanView* __restrict__ view, unsigned long long* __restrict__ tile_counter) {
-  typedef SweepShared<TR, TC, STAGES> Shared;
+  typedef SweepShared<TR, TC, STAGES, C> Shared;
   extern __shared__ unsigned char sw_raw[];
   /* TMA destinations want 128-byte alignment; the launcher over-allocates by 1 KB for this round-up */
   Shared& sh = *reinterpret_cast<Shared*>(sw_raw + ((1024u - (smem_u32(sw_raw) & 1023u)) & 1023u));
   /* view != NULL: the scan's own snapshot (its sweep may run while the next scan already changes st);
    * the out-of-place form (dst != source) must run even with no pending term: it is then a copy */
   const int np_all = view ? view->cnt : b.st->np;
-  const int np = max(0, min(SW_C, np_all - c0));
+  const int np = max(0, min(C, np_all - c0));
   if (np <= 0 && (dst == b.P || c0 > 0)) return;
   const int nl = 3 + 2 * (view ? view->L : b.st->L);
   const int T64 = (nl + EKF_TILE - 1) / EKF_TILE;      /* 64-row ownership blocks in the live part */
@@ -843,8 +847,9 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
       /* more than 4 pending terms: ONE 2-D TMA copy fetches the 8-slot band of K (resp. K S) for the tile's
        * columns (rows) -- 3 TMA operations per tile instead of 17 */
       const bool band = np > 4;
+      const int nbands = (np + 7) / 8;
       const unsigned long long pol = l2_policy_evict_first();
-      const unsigned bytes = TR * TC * sizeof(double) + (unsigned)(band ? SW_C : np) * (TC + TR) * sizeof(double2);
+      const unsigned bytes = TR * TC * sizeof(double) + (unsigned)(band ? 8 * nbands : np) * (TC + TR) * sizeof(double2);
       int k = 0;                                        /* local ownership block */
       int gb = g.rank;                                  /* its global index */
       long long base = 0;                               /* index of the block's first tile */
@@ -872,8 +877,10 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
         mbar_expect_tx(&sh.full[s], bytes);
         tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s], pol);
         if (band) {
-          tma_load_tile(sh.stage[s].K, &tmapK, 2 * col0, slot0 + c0, &sh.full[s]);
-          tma_load_tile(sh.stage[s].KS, &tmapKS, 2 * grow0, slot0 + c0, &sh.full[s]);
+          for (int bi = 0; bi < nbands; ++bi) {
+            tma_load_tile(sh.stage[s].K[8 * bi], &tmapK, 2 * col0, slot0 + c0 + 8 * bi, &sh.full[s]);
+            tma_load_tile(sh.stage[s].KS[8 * bi], &tmapKS, 2 * grow0, slot0 + c0 + 8 * bi, &sh.full[s]);
+          }
         } else {
           for (int c = 0; c < np; ++c) {
             bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(slot0 + c0 + c) * g.ld + col0, TC * sizeof(double2), &sh.full[s]);
@@ -901,7 +908,7 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
     const unsigned ph = (it / STAGES) & 1;
     mbar_wait(&sh.full[s], ph);
     if (!sh.meta[s][3]) break;
-    const SweepStage<TR, TC>& st = sh.stage[s];
+    const SweepStage<TR, TC, C>& st = sh.stage[s];
     const int lrow0 = sh.meta[s][0], grow0 = sh.meta[s][1], col0 = sh.meta[s][2];
     double2 p[PT];
 #pragma unroll
@@ -1266,21 +1273,25 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
   else k_sweep<8><<<grid, EKF_BLOCK, 0, s>>>(g, b, np_ptr);
   return cudaGetLastError();
 }
-template <int TR, int TC, int STAGES, int CW>
+template <int TR, int TC, int STAGES, int CW, int C>
 static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, const CUtensorMap* mK,
                                       const CUtensorMap* mKS, double* dst, int slot0,
                                       const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s) {
-  const size_t smem = sizeof(SweepShared<TR, TC, STAGES>) + 1024;
+  const size_t smem = sizeof(SweepShared<TR, TC, STAGES, C>) + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep_pipe<TR, TC, STAGES, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_pipe<TR, TC, STAGES, CW, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  for (int c0 = 0; c0 < np_ub; c0 += SW_C) {
-    k_sweep_pipe<TR, TC, STAGES, CW><<<grid, (CW + 1) * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / SW_C : 0);
+  if (counters) {   /* one tile counter per pass */
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * ((np_ub + C - 1) / C), s);
+    if (e != cudaSuccess) return e;
+  }
+  for (int c0 = 0; c0 < np_ub; c0 += C) {
+    k_sweep_pipe<TR, TC, STAGES, CW, C><<<grid, (CW + 1) * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -1289,28 +1300,36 @@ static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, con
 void ekf_sweep_shape(int shape, int* tr, int* tc) {
   switch (shape % 4) { case 1: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }   /* 8 % 4 == 0 */
 }
+/* terms one pass of the sweep folds for a scan with np_ub pending terms */
+int ekf_sweep_terms_per_pass(int shape, int np_ub) {
+  if (shape != 0) return SW_C;
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("EKF_SWEEP_MAXC"); cap = e ? atoi(e) : 32; if (cap != 8 && cap != 16 && cap != 32) cap = 32; }
+  const int want = np_ub <= 8 ? 8 : (np_ub <= 16 ? 16 : 32);
+  return want < cap ? want : cap;
+}
 cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmapK, const void* tmapKS,
                                  double* dst, int slot0,
                                  const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
                                  int num_sms, cudaStream_t s) {
   const int tiles = ekf_sweep_grid_ub(g, L_ub);
   if (tiles <= 0 || np_ub <= 0) return cudaSuccess;
-  if (dst != b.P && np_ub > SW_C) return cudaErrorInvalidValue;   /* out-of-place form: one pass only */
+  const int C = ekf_sweep_terms_per_pass(shape, np_ub);
+  if (dst != b.P && np_ub > C) return cudaErrorInvalidValue;   /* out-of-place form: one pass only */
   const int grid = tiles < num_sms ? tiles : num_sms;      /* num_sms: SMs this sweep may occupy */
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmap);
   const CUtensorMap* mK = reinterpret_cast<const CUtensorMap*>(tmapK);
   const CUtensorMap* mKS = reinterpret_cast<const CUtensorMap*>(tmapKS);
-  if (counters) {   /* one counter per pass */
-    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * ((np_ub + SW_C - 1) / SW_C), s);
-    if (e != cudaSuccess) return e;
-  }
   switch (shape) {       /* shape % 4: tile shape; shape / 4: 0 = 8 consumer warps, 1 = 16 */
-    case 1: return launch_sweep_shape<32, 128, 4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 2: return launch_sweep_shape<16, 256, 3, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 4: return launch_sweep_shape<64, 64, 4, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 5: return launch_sweep_shape<32, 128, 4, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 8: return launch_sweep_shape<64, 64, 3, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);   /* 148 KB: leaves room for a co-resident line-loop CTA */
-    default: return launch_sweep_shape<64, 64, 4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 1: return launch_sweep_shape<32, 128, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 2: return launch_sweep_shape<16, 256, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 4: return launch_sweep_shape<64, 64, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 5: return launch_sweep_shape<32, 128, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    case 8: return launch_sweep_shape<64, 64, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);   /* 148 KB: leaves room for a co-resident line-loop CTA */
+    default:
+      if (C == 32) return launch_sweep_shape<64, 64, 2, 8, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (C == 16) return launch_sweep_shape<64, 64, 3, 8, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      return launch_sweep_shape<64, 64, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
   }
 }
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,

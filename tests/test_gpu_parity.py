@@ -356,6 +356,34 @@ def test_batched_multi_line_updates(libekf, oracle_cls, m):
     assert so.stats()["matches"] > 0.8 * steps * m
 
 
+@pytest.mark.parametrize("m", [16, 32])
+def test_overlapped_pipeline_with_large_line_groups(libekf, oracle_cls, m):
+    """m = 16 / 32 lines per scan on a map large enough (n = 6203) for the overlapped path: the scan's 16 / 32
+    pending terms are folded by ONE out-of-place sweep pass (16- / 32-term template) while the next scan's line loop
+    corrects its column reads with up to 2m pending terms.  Checked against the oracle and, bit for bit, against
+    the non-overlapped in-place path."""
+    from slam_ros_b200 import EkfFilter
+    from slam_ros_b200.ekf import EKF_FLAG_NO_OVERLAP
+    N, steps = 3100, 7
+    scn = sc.map_scenario(N, steps, m=m, seed=70 + m, stride=m + 3)
+    f, so = seed_pair(N, N + 128, oracle_cls, scn)
+    so._lib.ekfo_set_threads(so._h, 0)
+    g = EkfFilter(capacity_lines=N + 128, flags=EKF_FLAG_NO_OVERLAP)
+    g.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
+    for s in range(steps):
+        rc, j, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        rg, jg, pg = g.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        st, jo = so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        assert np.array_equal(j, jo) and np.array_equal(jg, jo), "step %d" % s
+        assert np.array_equal(pose, pg)
+        if s in (2, steps - 1):
+            compare_state(f, so, "m=%d step %d" % (m, s))
+    assert so.stats()["matches"] > 0.8 * steps * m
+    yf, Pf, Lf = f.download_live()
+    yg, Pg, Lg = g.download_live()
+    assert Lf == Lg and np.array_equal(yf, yg) and np.array_equal(Pf, Pg)
+
+
 def test_empty_and_ragged_scans(libekf, oracle_cls):
     """Edge cases: scans with no lines, one line, lines on an empty map, duplicated observations of one landmark."""
     from slam_ros_b200 import EkfFilter
