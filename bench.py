@@ -324,6 +324,7 @@ def run_single_or_replicas(args, rank, world, local, sharded):
     ms = f.timer_stop()
     torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
+    lprof = f.profile_read_lines()
     prof = f.profile_read()
     f.profile_enable(False)
     matched = int((d_j[W:W + K] >= 0).sum().item())
@@ -368,11 +369,12 @@ def run_single_or_replicas(args, rank, world, local, sharded):
                    "exchange": exchange,
                    "l2": "per-step working set %.2f GB read + %.2f GB written >> 126 MB L2: no flush needed" % (8.0 * n * (n + 1) / 2 / 1e9, 8.0 * n * (n + 1) / 2 / 1e9),
                    "seed": seed},
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_pipe (P -= (K S) K' over the upper triangle; TMA + mbarrier ring, runs under the next scan's line loop)",
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_quad (P -= (K S) K' over the upper triangle; TMA + mbarrier ring, 8x4 register tiles, runs under the next scan's line loop)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "launch_ms": sweep_ms, "launches_timed": prof["sweeps"], "algorithmic_bytes_per_launch": bytes_per_sweep,
                      "sweep_share_of_step": (prof["sweep_ms"] / ms) if ms > 0 else None,
+                     "line_stream_ms_per_step": (lprof["line_ms"] / lprof["scans"]) if lprof["scans"] else None,
                      "traffic": 3.16e9 if (N == 10000 and not sharded) else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r1_ncu_sweep_pipe.csv (10k workload)"},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": (6 + 2 * m) * 8 + 4 * m * 8,

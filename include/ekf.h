@@ -140,6 +140,10 @@ int ekf_cov_stats(ekf_ctx* ctx, double* trace, double* sum, double* sumsq);
  * launches = kernels launched by this ctx since the last read. */
 int ekf_profile_enable(ekf_ctx* ctx, int on);
 int ekf_profile_read(ekf_ctx* ctx, int* n_sweeps, double* sweep_ms, double* sweep_bytes, long long* launches);
+/* Same accounting for the OTHER half of a scan: device time between the start of the prediction and the end of
+ * the line loop (overlapped scans: the end of the augmentation kernels) -- i.e. how long the line stream is busy
+ * per scan, the quantity the sweep has to hide.  Call before ekf_profile_read (which leaves profiling on). */
+int ekf_profile_read_lines(ekf_ctx* ctx, int* n_scans, double* line_ms);
 
 /* Device-time bracket on the ctx stream (CUDA events): start records an event, stop records a second
  * one, waits for it and returns the elapsed milliseconds.  This is how bench.py times K steps. */

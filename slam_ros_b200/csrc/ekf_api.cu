@@ -69,6 +69,8 @@ struct ekf_ctx {
   std::vector<cudaEvent_t> ev;
   size_t ev_used;
   std::vector<double> ev_bytes;
+  std::vector<cudaEvent_t> lev;   /* event pairs around the line-stream part of each scan (predict .. line loop [.. end of scan]) */
+  size_t lev_used;
   long long launches;
   cudaEvent_t t0, t1;  /* ekf_timer_* */
   /* overlapped pipeline: the sweep of scan s runs on `wstream` while scan s+1's line loop runs on `stream`.
@@ -114,7 +116,7 @@ namespace {
 
 const size_t kStageElems = (size_t)8 << 20;   /* 64 MiB staging for download/upload */
 const int kOverlapMinN = 6000;                /* below this state dimension the synchronous path is used */
-static int line_sms() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : 8; if (v < 1 || v > 64) v = 8; } return v; }
+static int line_sms() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : 16; if (v < 1 || v > 64) v = 16; } return v; }
 #define EKF_LINE_SMS line_sms()               /* SMs reserved for the line loop while a sweep is in flight */
 
 double* in_u(ekf_ctx* c) { return c->d_in; }
@@ -313,6 +315,14 @@ int drain(ekf_ctx* ctx) {
   return EKF_OK;
 }
 
+int line_event(ekf_ctx* ctx) {
+  if (!ctx->prof) return EKF_OK;
+  if (ctx->lev_used + 1 > ctx->lev.size())
+    for (int i = 0; i < 64; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->lev.push_back(e); }
+  CU(cudaEventRecord(ctx->lev[ctx->lev_used++], ctx->stream));
+  return EKF_OK;
+}
+
 /* Overlapped form of one Robot::localize (single GPU, m <= group): the line stream runs predict, the
  * line-loop cluster kernel and the end-of-scan kernels against Pbuf[rd] plus the previous scan's still
  * pending terms; the sweep of THIS scan is handed to the sweep stream, where it runs while the next
@@ -325,6 +335,7 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
   const int slot0 = par * ctx->group;
   EkfBuffers b = ctx->b;
   b.P = ctx->Pbuf[ctx->rd];
+  { int rc = line_event(ctx); if (rc) return rc; }
   CU(ekf_launch_predict(ctx->g, b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
   /* The line loop runs as EKF_LINE_SMS cooperative CTAs on the SMs the in-flight sweep leaves free (its
    * persistent grid is num_sms - EKF_LINE_SMS): no register / FP64-issue sharing with the sweep. */
@@ -335,6 +346,7 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
   bt.P = ctx->Pbuf[tgt];
   CU(ekf_launch_end_scan(ctx->g, bt, d_z, d_R, m, ctx->L_ub, slot0, &ctx->d_view[par], ctx->stream));
   ctx->launches += 5;
+  { int rc = line_event(ctx); if (rc) return rc; }
   CU(cudaEventRecord(ctx->evE, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->wstream, ctx->evE, 0));
   cudaEvent_t e0 = 0, e1 = 0;
@@ -374,6 +386,7 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
     if (rc) return rc;
     use_tables(ctx, 0);
   }
+  { int rc = line_event(ctx); if (rc) return rc; }
   CU(ekf_launch_predict(ctx->g, ctx->b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
   ctx->launches++;
   ctx->pend_ub = 0;
@@ -411,6 +424,7 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
       if (rc) return rc;
     }
   }
+  { int rc = line_event(ctx); if (rc) return rc; }
   return enqueue_end(ctx, d_z, d_R, m);
 }
 
@@ -459,7 +473,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->err[0] = 0;
   ctx->stream = 0; ctx->max_lines = 0; ctx->d_in = 0; ctx->h_in = 0; ctx->h_jout = 0; ctx->h_st = 0;
   ctx->L_ub = 0; ctx->pend_ub = 0; ctx->scan_open = 0; ctx->cursor = 0;
-  ctx->prof = 0; ctx->ev_used = 0; ctx->launches = 0; ctx->comm = 0; ctx->t0 = 0; ctx->t1 = 0;
+  ctx->prof = 0; ctx->ev_used = 0; ctx->lev_used = 0; ctx->launches = 0; ctx->comm = 0; ctx->t0 = 0; ctx->t1 = 0;
   ctx->d_stage = 0; ctx->stage_elems = 0; ctx->d_partials = 0; ctx->d_out3 = 0;
   ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8;
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
@@ -502,7 +516,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
+  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
   { const int cap = ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
   { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
   { int tr = 64, tc = 64; ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
@@ -663,6 +677,7 @@ int ekf_destroy(ekf_ctx* ctx) {
   cudaFree(ctx->d_stage); cudaFree(ctx->d_partials); cudaFree(ctx->d_out3);
   cudaFreeHost(ctx->h_st);
   for (size_t i = 0; i < ctx->ev.size(); ++i) cudaEventDestroy(ctx->ev[i]);
+  for (size_t i = 0; i < ctx->lev.size(); ++i) cudaEventDestroy(ctx->lev[i]);
   if (ctx->t0) cudaEventDestroy(ctx->t0);
   if (ctx->t1) cudaEventDestroy(ctx->t1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -991,7 +1006,7 @@ int ekf_cov_stats(ekf_ctx* ctx, double* trace, double* sum, double* sumsq) {
 int ekf_profile_enable(ekf_ctx* ctx, int on) {
   if (!ctx) return EKF_EINVAL;
   ctx->prof = on ? 1 : 0;
-  ctx->ev_used = 0; ctx->ev_bytes.clear();
+  ctx->ev_used = 0; ctx->ev_bytes.clear(); ctx->lev_used = 0;
   return EKF_OK;
 }
 
@@ -1015,6 +1030,23 @@ int ekf_profile_read(ekf_ctx* ctx, int* n_sweeps, double* sweep_ms, double* swee
   if (sweep_bytes) *sweep_bytes = bytes;
   if (launches) *launches = ctx->launches;
   ctx->ev_used = 0; ctx->ev_bytes.clear(); ctx->launches = 0;
+  return EKF_OK;
+}
+
+int ekf_profile_read_lines(ekf_ctx* ctx, int* n_scans, double* line_ms) {
+  if (!ctx) return EKF_EINVAL;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  double ms = 0.0;
+  const size_t ns = ctx->lev_used / 2;
+  for (size_t i = 0; i < ns; ++i) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, ctx->lev[2 * i], ctx->lev[2 * i + 1]));
+    ms += t;
+  }
+  if (n_scans) *n_scans = (int)ns;
+  if (line_ms) *line_ms = ms;
+  ctx->lev_used = 0;
   return EKF_OK;
 }
 

@@ -810,6 +810,69 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/* The producer of both pipelined sweep kernels: ONE thread streams the CTA's tiles (and the matching slices of
+ * the pending lists) into the shared-memory ring. */
+template <int TR, int TC, int STAGES, int C>
+__device__ __forceinline__ void sweep_producer(SweepShared<TR, TC, STAGES, C>& sh, const EkfGeom& g, const EkfBuffers& b,
+                                               const CUtensorMap& tmapP, const CUtensorMap& tmapK, const CUtensorMap& tmapKS,
+                                               int c0, int slot0, int np, int nl, unsigned long long* tile_counter, int sentinels) {
+  const int T64 = (nl + EKF_TILE - 1) / EKF_TILE;      /* 64-row ownership blocks in the live part */
+  const int Tc = (nl + TC - 1) / TC;                   /* tile columns */
+  constexpr int SUB = EKF_TILE / TR;                   /* sub-row blocks per ownership block */
+  /* more than 4 pending terms: ONE 2-D TMA copy fetches the 8-slot band of K (resp. K S) for the tile's
+   * columns (rows) -- 3 TMA operations per tile instead of 17 */
+  const bool band = np > 4;
+  const int nbands = (np + 7) / 8;
+  const unsigned long long pol = l2_policy_evict_first();
+  const unsigned bytes = TR * TC * sizeof(double) + (unsigned)(band ? 8 * nbands : np) * (TC + TR) * sizeof(double2);
+  int k = 0;                                        /* local ownership block */
+  int gb = g.rank;                                  /* its global index */
+  long long base = 0;                               /* index of the block's first tile */
+  int cb0 = (EKF_TILE * gb) / TC;
+  long long cnt = (gb < T64) ? (long long)SUB * (Tc - cb0) : 0;
+  int it = 0;
+  /* tiles are handed out by a global counter (zeroed before the launch): CTAs that share their SM with
+   * another kernel simply take fewer tiles.  The indices a CTA draws are increasing, which is all the
+   * incremental decode needs.  tile_counter == NULL: static round robin. */
+  for (long long idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : (long long)blockIdx.x; gb < T64;
+       idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : idx + gridDim.x, ++it) {
+    while (gb < T64 && idx >= base + cnt) {
+      base += cnt; ++k; gb += g.world;
+      cb0 = (EKF_TILE * gb) / TC;
+      cnt = (gb < T64) ? (long long)SUB * (Tc - cb0) : 0;
+    }
+    if (gb >= T64) break;
+    const int rem = (int)(idx - base);
+    const int sub = rem / (Tc - cb0), cb = cb0 + rem % (Tc - cb0);
+    const int lrow0 = k * EKF_TILE + sub * TR, grow0 = gb * EKF_TILE + sub * TR, col0 = cb * TC;
+    const int s = it % STAGES;
+    const unsigned ph = (it / STAGES) & 1;
+    mbar_wait(&sh.empty[s], ph ^ 1);
+    sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
+    mbar_expect_tx(&sh.full[s], bytes);
+    tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s], pol);
+    if (band) {
+      for (int bi = 0; bi < nbands; ++bi) {
+        tma_load_tile(sh.stage[s].K[8 * bi], &tmapK, 2 * col0, slot0 + c0 + 8 * bi, &sh.full[s]);
+        tma_load_tile(sh.stage[s].KS[8 * bi], &tmapKS, 2 * grow0, slot0 + c0 + 8 * bi, &sh.full[s]);
+      }
+    } else {
+      for (int c = 0; c < np; ++c) {
+        bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(slot0 + c0 + c) * g.ld + col0, TC * sizeof(double2), &sh.full[s]);
+        bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(slot0 + c0 + c) * g.ld + grow0, TR * sizeof(double2), &sh.full[s]);
+      }
+    }
+  }
+  /* tell the consumers there is nothing more: `sentinels` stages with valid = 0 (one per consumer group) */
+  for (int e = 0; e < sentinels; ++e, ++it) {
+    const int s = it % STAGES;
+    const unsigned ph = (it / STAGES) & 1;
+    mbar_wait(&sh.empty[s], ph ^ 1);
+    sh.meta[s][3] = 0;
+    mbar_arrive(&sh.full[s]);
+  }
+}
+
 /* Tiles are TR rows x TC columns (TR*TC = 4096 doubles = 32 KB; TR <= 64 <= TC).  The upper triangle is
  * covered by, for each 64-row ownership block gb (this rank's: gb = rank + world*k), the 64/TR sub-row
  * blocks times the tile columns cb >= floor(64*gb / TC).  Tiles are numbered in that order; the
@@ -832,69 +895,14 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
   const int np = max(0, min(C, np_all - c0));
   if (np <= 0 && (dst == b.P || c0 > 0)) return;
   const int nl = 3 + 2 * (view ? view->L : b.st->L);
-  const int T64 = (nl + EKF_TILE - 1) / EKF_TILE;      /* 64-row ownership blocks in the live part */
-  const int Tc = (nl + TC - 1) / TC;                   /* tile columns */
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int SUB = EKF_TILE / TR;                   /* sub-row blocks per ownership block */
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (warp == CW) {
-    /* ---------------- producer: one elected lane ---------------- */
-    if (lane == 0) {
-      /* more than 4 pending terms: ONE 2-D TMA copy fetches the 8-slot band of K (resp. K S) for the tile's
-       * columns (rows) -- 3 TMA operations per tile instead of 17 */
-      const bool band = np > 4;
-      const int nbands = (np + 7) / 8;
-      const unsigned long long pol = l2_policy_evict_first();
-      const unsigned bytes = TR * TC * sizeof(double) + (unsigned)(band ? 8 * nbands : np) * (TC + TR) * sizeof(double2);
-      int k = 0;                                        /* local ownership block */
-      int gb = g.rank;                                  /* its global index */
-      long long base = 0;                               /* index of the block's first tile */
-      int cb0 = (EKF_TILE * gb) / TC;
-      long long cnt = (gb < T64) ? (long long)SUB * (Tc - cb0) : 0;
-      int it = 0;
-      /* tiles are handed out by a global counter (zeroed before the launch): CTAs that share their SM with
-       * another kernel simply take fewer tiles.  The indices a CTA draws are increasing, which is all the
-       * incremental decode needs.  tile_counter == NULL: static round robin. */
-      for (long long idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : (long long)blockIdx.x; gb < T64;
-           idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : idx + gridDim.x, ++it) {
-        while (gb < T64 && idx >= base + cnt) {
-          base += cnt; ++k; gb += g.world;
-          cb0 = (EKF_TILE * gb) / TC;
-          cnt = (gb < T64) ? (long long)SUB * (Tc - cb0) : 0;
-        }
-        if (gb >= T64) break;
-        const int rem = (int)(idx - base);
-        const int sub = rem / (Tc - cb0), cb = cb0 + rem % (Tc - cb0);
-        const int lrow0 = k * EKF_TILE + sub * TR, grow0 = gb * EKF_TILE + sub * TR, col0 = cb * TC;
-        const int s = it % STAGES;
-        const unsigned ph = (it / STAGES) & 1;
-        mbar_wait(&sh.empty[s], ph ^ 1);
-        sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
-        mbar_expect_tx(&sh.full[s], bytes);
-        tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s], pol);
-        if (band) {
-          for (int bi = 0; bi < nbands; ++bi) {
-            tma_load_tile(sh.stage[s].K[8 * bi], &tmapK, 2 * col0, slot0 + c0 + 8 * bi, &sh.full[s]);
-            tma_load_tile(sh.stage[s].KS[8 * bi], &tmapKS, 2 * grow0, slot0 + c0 + 8 * bi, &sh.full[s]);
-          }
-        } else {
-          for (int c = 0; c < np; ++c) {
-            bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(slot0 + c0 + c) * g.ld + col0, TC * sizeof(double2), &sh.full[s]);
-            bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(slot0 + c0 + c) * g.ld + grow0, TR * sizeof(double2), &sh.full[s]);
-          }
-        }
-      }
-      /* tell the consumers there is nothing more: a stage with valid = 0 */
-      const int s = it % STAGES;
-      const unsigned ph = (it / STAGES) & 1;
-      mbar_wait(&sh.empty[s], ph ^ 1);
-      sh.meta[s][3] = 0;
-      mbar_arrive(&sh.full[s]);
-    }
+    if (lane == 0) sweep_producer<TR, TC, STAGES, C>(sh, g, b, tmapP, tmapK, tmapKS, c0, slot0, np, nl, tile_counter, 1);
     return;
   }
   /* ---------------- consumers ---------------- */
@@ -937,6 +945,104 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
         if (grow0 + crow + i * RPP < nl) {
           if (q + 1 < nl) __stcs(reinterpret_cast<double2*>(Pt + (size_t)(i * RPP) * g.ld), p[i]);
           else if (q < nl) Pt[(size_t)(i * RPP) * g.ld] = p[i].x;
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* k_sweep_quad: the form of the pipelined sweep the library launches by default.  Same ring, same producer, same
+ * per-element arithmetic and order as k_sweep_pipe<64,64,...>; what changes is how the consumers hold a tile.
+ *
+ * ncu on k_sweep_pipe at 8 pending terms (profiles/r1_ncu_sweep_pipe.csv): the LSU data pipe is 92 % busy and
+ * shared-memory wavefronts are at 82 % of peak while DRAM sits at 74 % -- the kernel is bound by shared-memory
+ * operand delivery, not by HBM: each lane owns 8 rows x 2 columns, so every term costs 8 warp-uniform LDS.128
+ * (K S of a row: 2 wavefronts each) plus 2 LDS.128 of its columns' K that hit a 2-way bank conflict (stride
+ * 32 B), i.e. 34 wavefronts per 32 DFMA instructions.
+ *
+ * Here a lane owns 8 rows x 4 columns (two 16-byte column pairs 32 columns apart): a HALF-warp spans the 64
+ * columns of a tile row, the two halves of a warp take different rows, a warp covers 16 rows and FOUR warps
+ * cover the tile; the eight consumer warps form two groups that take alternate ring stages.  Per term and
+ * warp: 8 LDS.128 of K S (uniform per half-warp, each now feeding 8 DFMAs instead of 4) + 4 LDS.128 of K made
+ * conflict-free by letting lanes 4..7 of every 8 fetch their pair in the opposite order (then swapped back in
+ * registers): 24 wavefronts per 64 DFMA instructions -- 2.8x less shared-memory traffic per flop. */
+template <int STAGES, int C>
+__global__ void __launch_bounds__(9 * 32, 1)
+k_sweep_quad(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapK,
+             const __grid_constant__ CUtensorMap tmapKS, double* __restrict__ dst, int c0,
+             int slot0, const EkfScanView* __restrict__ view, unsigned long long* __restrict__ tile_counter) {
+  constexpr int TR = 64, TC = 64, CW = 8;
+  typedef SweepShared<TR, TC, STAGES, C> Shared;
+  extern __shared__ unsigned char sw_raw[];
+  Shared& sh = *reinterpret_cast<Shared*>(sw_raw + ((1024u - (smem_u32(sw_raw) & 1023u)) & 1023u));
+  const int np_all = view ? view->cnt : b.st->np;
+  const int np = max(0, min(C, np_all - c0));
+  if (np <= 0 && (dst == b.P || c0 > 0)) return;
+  const int nl = 3 + 2 * (view ? view->L : b.st->L);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CW / 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == CW) {
+    if (lane == 0) sweep_producer<TR, TC, STAGES, C>(sh, g, b, tmapP, tmapK, tmapKS, c0, slot0, np, nl, tile_counter, 2);
+    return;
+  }
+  /* ---------------- consumers: 2 groups x 4 warps ---------------- */
+  const int grp = warp >> 2;
+  const int l16 = lane & 15;
+  const int row0 = 16 * (warp & 3) + 8 * (lane >> 4);        /* this lane's 8 rows inside the tile */
+  const int cA = 2 * l16, cB = 32 + 2 * l16;                 /* its two column pairs */
+  const bool sw = (l16 & 4) != 0;                            /* fetch the pair's halves in the opposite order */
+  const int o0 = sw ? 1 : 0, o1 = sw ? 0 : 1;
+  for (int it = grp;; it += 2) {
+    const int s = it % STAGES;
+    const unsigned ph = (it / STAGES) & 1;
+    mbar_wait(&sh.full[s], ph);
+    if (!sh.meta[s][3]) break;
+    const SweepStage<TR, TC, C>& st = sh.stage[s];
+    const int lrow0 = sh.meta[s][0], grow0 = sh.meta[s][1], col0 = sh.meta[s][2];
+    double2 pa[8], pb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      pa[i] = *reinterpret_cast<const double2*>(&st.P[(row0 + i) * TC + cA]);
+      pb[i] = *reinterpret_cast<const double2*>(&st.P[(row0 + i) * TC + cB]);
+    }
+#pragma unroll 2
+    for (int c = 0; c < np; ++c) {
+      const double2 a0 = st.K[c][cA + o0], a1 = st.K[c][cA + o1];
+      const double2 b0 = st.K[c][cB + o0], b1 = st.K[c][cB + o1];
+      const double2 ka0 = sw ? a1 : a0, ka1 = sw ? a0 : a1;
+      const double2 kb0 = sw ? b1 : b0, kb1 = sw ? b0 : b1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double2 ks = st.KS[c][row0 + i];
+        pa[i].x = sub_rank2(pa[i].x, ks, ka0);
+        pa[i].y = sub_rank2(pa[i].y, ks, ka1);
+        pb[i].x = sub_rank2(pb[i].x, ks, kb0);
+        pb[i].y = sub_rank2(pb[i].y, ks, kb1);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sh.empty[s]);
+    double* Pt = dst + ((size_t)lrow0 + row0) * g.ld + (size_t)col0;
+    if (grow0 + TR <= nl && col0 + TC <= nl) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __stcs(reinterpret_cast<double2*>(Pt + (size_t)i * g.ld + cA), pa[i]);
+        __stcs(reinterpret_cast<double2*>(Pt + (size_t)i * g.ld + cB), pb[i]);
+      }
+    } else {
+      /* edge tile: dead rows / columns are left alone (see k_sweep_pipe) */
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (grow0 + row0 + i < nl) {
+          double* Pr = Pt + (size_t)i * g.ld;
+          const int qa = col0 + cA, qb = col0 + cB;
+          if (qa + 1 < nl) __stcs(reinterpret_cast<double2*>(Pr + cA), pa[i]); else if (qa < nl) Pr[cA] = pa[i].x;
+          if (qb + 1 < nl) __stcs(reinterpret_cast<double2*>(Pr + cB), pb[i]); else if (qb < nl) Pr[cB] = pb[i].x;
         }
       }
     }
@@ -1297,12 +1403,36 @@ static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, con
   }
   return cudaSuccess;
 }
+template <int STAGES, int C>
+static cudaError_t launch_sweep_quad(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, const CUtensorMap* mK,
+                                     const CUtensorMap* mKS, double* dst, int slot0,
+                                     const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s) {
+  const size_t smem = sizeof(SweepShared<64, 64, STAGES, C>) + 1024;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_quad<STAGES, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  if (counters) {   /* one tile counter per pass */
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * ((np_ub + C - 1) / C), s);
+    if (e != cudaSuccess) return e;
+  }
+  for (int c0 = 0; c0 < np_ub; c0 += C) {
+    k_sweep_quad<STAGES, C><<<grid, 9 * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
 void ekf_sweep_shape(int shape, int* tr, int* tc) {
-  switch (shape % 4) { case 1: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }   /* 8 % 4 == 0 */
+  switch (shape) { case 1: case 5: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }
 }
 /* terms one pass of the sweep folds for a scan with np_ub pending terms */
 int ekf_sweep_terms_per_pass(int shape, int np_ub) {
-  if (shape != 0) return SW_C;
+  if (shape != 0 && shape != 9) return SW_C;
   static int cap = -1;
   if (cap < 0) { const char* e = getenv("EKF_SWEEP_MAXC"); cap = e ? atoi(e) : 32; if (cap != 8 && cap != 16 && cap != 32) cap = 32; }
   const int want = np_ub <= 8 ? 8 : (np_ub <= 16 ? 16 : 32);
@@ -1326,10 +1456,14 @@ cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const vo
     case 4: return launch_sweep_shape<64, 64, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
     case 5: return launch_sweep_shape<32, 128, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
     case 8: return launch_sweep_shape<64, 64, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);   /* 148 KB: leaves room for a co-resident line-loop CTA */
-    default:
+    case 9:        /* the 8-rows x 2-columns-per-lane consumers (A/B against k_sweep_quad) */
       if (C == 32) return launch_sweep_shape<64, 64, 2, 8, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
       if (C == 16) return launch_sweep_shape<64, 64, 3, 8, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
       return launch_sweep_shape<64, 64, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+    default:
+      if (C == 32) return launch_sweep_quad<2, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (C == 16) return launch_sweep_quad<3, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      return launch_sweep_quad<4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
   }
 }
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,

@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libekfcuda.so")
+# EKF_LIB points diagnostics at an instrumented build of the same library (e.g. -DEKF_LINE_TIMING); default: in-tree
+_LIB_PATH = os.environ.get("EKF_LIB") or os.path.join(_HERE, "libekfcuda.so")
 _lib = None
 
 EKF_OK, EKF_EINVAL, EKF_ECAPACITY, EKF_ESINGULAR, EKF_ECUDA, EKF_ENCCL, EKF_ENOMEM, EKF_ESTATE = range(8)
@@ -43,7 +44,7 @@ SYMBOLS = [
     "ekf_default_config", "ekf_create", "ekf_destroy", "ekf_last_error", "ekf_predict", "ekf_associate",
     "ekf_update", "ekf_add_line", "ekf_end_scan", "ekf_scan", "ekf_scan_device", "ekf_sync", "ekf_get_state",
     "ekf_get_robot_cov", "ekf_get_ellipse", "ekf_download", "ekf_upload", "ekf_download_live",
-    "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
+    "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_profile_read_lines", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
     "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_shard_ipc_handle", "ekf_shard_connect", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
     "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
 ]
@@ -89,6 +90,7 @@ def load_library():
     lib.ekf_cov_stats.argtypes = [vp, _dp, _dp, _dp]
     lib.ekf_profile_enable.argtypes = [vp, C.c_int]
     lib.ekf_profile_read.argtypes = [vp, _ip, _dp, _dp, C.POINTER(C.c_longlong)]
+    lib.ekf_profile_read_lines.argtypes = [vp, _ip, _dp]
     lib.ekf_sweep_probe.argtypes = [vp, C.c_int, C.c_int, _dp]
     lib.ekf_timer_start.argtypes = [vp]
     lib.ekf_timer_stop.argtypes = [vp, _dp]
@@ -299,6 +301,11 @@ class EkfFilter:
         ns = C.c_int(0); ms = C.c_double(0); by = C.c_double(0); ln = C.c_longlong(0)
         self._check(self._lib.ekf_profile_read(self._h, C.byref(ns), C.byref(ms), C.byref(by), C.byref(ln)), "ekf_profile_read")
         return {"sweeps": int(ns.value), "sweep_ms": ms.value, "sweep_bytes": by.value, "launches": int(ln.value)}
+
+    def profile_read_lines(self):
+        ns = C.c_int(0); ms = C.c_double(0)
+        self._check(self._lib.ekf_profile_read_lines(self._h, C.byref(ns), C.byref(ms)), "ekf_profile_read_lines")
+        return {"scans": int(ns.value), "line_ms": ms.value}
 
     def timer_start(self):
         self._check(self._lib.ekf_timer_start(self._h), "ekf_timer_start")
