@@ -116,8 +116,13 @@ namespace {
 
 const size_t kStageElems = (size_t)8 << 20;   /* 64 MiB staging for download/upload */
 const int kOverlapMinN = 6000;                /* below this state dimension the synchronous path is used */
-static int line_sms() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : 16; if (v < 1 || v > 64) v = 16; } return v; }
-#define EKF_LINE_SMS line_sms()               /* SMs reserved for the line loop while a sweep is in flight */
+/* SMs reserved for the line loop while a sweep is in flight.  The line loop's time is inversely proportional to
+ * its SM count (measured, 10k and 40k landmarks), the sweep's grows only with the SMs it loses; 20 balances the
+ * two on one GPU at 10k landmarks.  A row-sharded filter sweeps 1/world of the triangle but still walks every
+ * landmark and every row per line, so there the line loop gets more (28 from 4 ranks up). */
+static int line_sms_env() { static int v = -2; if (v == -2) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : -1; if (v < 1 || v > 64) v = -1; } return v; }
+static int line_sms_for(int world) { const int e = line_sms_env(); return e > 0 ? e : (world >= 4 ? 28 : 20); }
+#define EKF_LINE_SMS line_sms_for(ctx->g.world)
 
 double* in_u(ekf_ctx* c) { return c->d_in; }
 double* in_x(ekf_ctx* c) { return c->d_in + 3; }

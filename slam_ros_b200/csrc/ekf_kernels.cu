@@ -412,14 +412,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 /* called by ONE thread after a local barrier: tell every peer this rank's slice entries are in place, then wait
  * for theirs.  Bounded spin: a missing peer raises a sticky error instead of hanging the GPU. */
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void xgpu_exchange_barrier(const EkfPeers& pe, const EkfGeom& g, unsigned long long epoch, int* sticky) {
+  /* ONE system-scope fence orders every slice store of this GPU (made visible to this thread by the grid barrier)
+   * before the flag stores, which can then be relaxed: a release store per peer would pay the fence 8 times */
   __threadfence_system();
-  for (int p = 0; p < pe.world; ++p) st_release_sys(xchg_flags(pe, g, p) + pe.rank, epoch);
+  for (int p = 0; p < pe.world; ++p) st_relaxed_sys(xchg_flags(pe, g, p) + pe.rank, epoch);
   const unsigned long long* mine = xchg_flags(pe, g, pe.rank);
   for (int q = 0; q < pe.world; ++q) {
     long long spins = 0;
@@ -616,11 +618,15 @@ __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_
           if (own_b == g.rank) xchg_col(pe, g, p, xpar, 1)[r] = pb;
         }
       }
+      TS(8);
       __threadfence_system();
       group_sync();
+      TS(9);
       if (gtid == 0) xgpu_exchange_barrier(pe, g, (unsigned long long)(xseq0 + xdone) + 1ull, &st->sticky);
       xdone += 1;
+      TS(10);
       group_sync();
+      TS(11);
       /* part 2: every rank forms the full K, K S (replicated) from the gathered slices */
       const double* cA = xchg_col(pe, g, g.rank, xpar, 0);
       const double* cB = xchg_col(pe, g, g.rank, xpar, 1);
