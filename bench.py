@@ -375,8 +375,8 @@ def run_single_or_replicas(args, rank, world, local, sharded):
                      "launch_ms": sweep_ms, "launches_timed": prof["sweeps"], "algorithmic_bytes_per_launch": bytes_per_sweep,
                      "sweep_share_of_step": (prof["sweep_ms"] / ms) if ms > 0 else None,
                      "line_stream_ms_per_step": (lprof["line_ms"] / lprof["scans"]) if lprof["scans"] else None,
-                     "traffic": 3.16e9 if (N == 10000 and not sharded) else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r1_ncu_sweep_pipe.csv (10k workload)"},
+                     "traffic": 3.167e9 if (N == 10000 and not sharded and m == 8) else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r1_ncu_sweep_quad.csv (10k workload, 8 terms: 1.615 GB read + 1.552 GB written)"},
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": (6 + 2 * m) * 8 + 4 * m * 8,
                 "d2h_bytes_per_step": 4 * m + 128, "ms_per_step": e2e_ms_max / K, "matched_per_step": e2e_matched / max(K, 1)},
         "gpu_launches": prof["launches"],

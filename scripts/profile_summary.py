@@ -9,7 +9,8 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.avg.per_second", "smsp__inst_executed.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second", "smsp__inst_executed.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
 
 
