@@ -96,6 +96,9 @@ inline gsl_matrix* gsl_matrix_alloc(size_t n1, size_t n2) {
   gsl_block* b = (gsl_block*)std::malloc(sizeof(gsl_block));
   b->size = n1 * n2;
   b->data = (double*)std::malloc(sizeof(double) * (n1 * n2 ? n1 * n2 : 1));
+#ifdef GSL_SHIM_ZERO_ALLOC   /* one legal instance of "indeterminate": used for the line-extraction reference build */
+  std::memset(b->data, 0, sizeof(double) * (n1 * n2 ? n1 * n2 : 1));
+#endif
   m->size1 = n1; m->size2 = n2; m->tda = n2; m->data = b->data; m->block = b; m->owner = 1;
   return m;
 }

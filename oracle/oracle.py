@@ -224,3 +224,58 @@ class LiteralReference:
 
     def range_errors(self):
         return int(self._lib.ref_range_errors())
+
+
+# ------------------------------------------------------------------------------------------------
+# line extraction: the restatement and the deterministic build of the reference itself
+# ------------------------------------------------------------------------------------------------
+_LINES_SO = os.path.join(_HERE, "liblinesoracle.so")
+_REF_LINES_SO = os.path.join(_HERE, "_ref", "libslamlines.so")
+_fp = C.POINTER(C.c_float)
+
+
+def have_literal_lines():
+    return os.path.exists(_REF_LINES_SO)
+
+
+def _extract(fn, payload, max_lines):
+    d = np.ascontiguousarray(np.asarray(payload, dtype=np.float32).reshape(-1))
+    out = np.zeros((max_lines, 10))
+    n = fn(d.size // 2, d.ctypes.data_as(_fp), max_lines, out.ctypes.data_as(_dp))
+    if n < 0:
+        raise RuntimeError("line extraction failed")
+    return out[:min(n, max_lines)].copy(), n
+
+
+class LinesOracle:
+    """oracle/lines_oracle.cpp: mapping_cb + LineExtraction (slam_ros/main.cpp:37-71, lineFitting.cpp:640-702).
+    extract(payload) -> (rows, n): rows[i] = alfa, r, C_AR[4], interval0 (alfa, r), interval1 (alfa, r)."""
+
+    def __init__(self):
+        if not os.path.exists(_LINES_SO):
+            build()
+        self._lib = C.CDLL(_LINES_SO)
+        self._lib.lxo_extract.argtypes = [C.c_int, _fp, C.c_int, _dp]
+        self._lib.lxo_fit.argtypes = [C.c_int, _dp, _dp, _dp]
+
+    def extract(self, payload, max_lines=128):
+        return _extract(self._lib.lxo_extract, payload, max_lines)
+
+    def fit(self, alfa, r):
+        a, ap = _d(alfa); rr, rp = _d(r); out = np.zeros(2)
+        self._lib.lxo_fit(int(a.size), ap, rp, out.ctypes.data_as(_dp))
+        return out
+
+
+class LiteralLineExtraction:
+    """oracle/_ref/libslamlines.so: the reference's own lineFitting.cpp / simplifyPath.cpp / vec2.cpp, built with
+    zero-initialised automatic variables and gsl_matrix_alloc storage (one deterministic instance of it)."""
+
+    def __init__(self):
+        if not have_literal_lines():
+            raise RuntimeError("oracle/_ref/libslamlines.so is not built (needs /root/reference: make -C oracle ref)")
+        self._lib = C.CDLL(_REF_LINES_SO)
+        self._lib.ref_extract_lines.argtypes = [C.c_int, _fp, C.c_int, _dp]
+
+    def extract(self, payload, max_lines=128):
+        return _extract(self._lib.ref_extract_lines, payload, max_lines)

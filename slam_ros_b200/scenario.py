@@ -183,6 +183,32 @@ def room_scenario(steps=1000, seed=7, beams=361, range_sigma=1e-3, max_range=10.
     return {"u": u, "z": z, "R": R, "count": cnt, "poses": poses, "seed": seed, "walls": walls}
 
 
+def room_scan(pose, beams=361, range_sigma=1e-3, max_range=10.0, rng=None):
+    """One `mappingPoints` payload as the node receives it (slam_ros/main.cpp:37-56): float32 pairs (r, angle),
+    angle in [0, 2 pi] at 1 degree steps (the reference subtracts pi), r = 0 for beams without a return."""
+    walls = room_walls()
+    angles = np.deg2rad(np.arange(beams, dtype=np.float64))
+    rng_, wall, hit = _raycast(walls, pose, angles - math.pi, max_range)
+    rr = np.where(hit, rng_, 0.0)
+    if rng is not None and range_sigma > 0:
+        rr = np.where(hit, rr + rng.standard_normal(beams) * range_sigma, 0.0)
+    out = np.empty((beams, 2), dtype=np.float32)
+    out[:, 0] = rr
+    out[:, 1] = angles
+    return out
+
+
+def room_scans(steps=20, seed=7, beams=361, range_sigma=1e-3, d=0.05):
+    """A short trajectory through the room: (S, beams, 2) float32 payloads plus the true poses."""
+    rng = np.random.default_rng(seed)
+    u = np.zeros((steps, 3))
+    u[:, 0] = d
+    u[:, 2] = 0.03 * np.sin(0.2 * np.arange(steps)) + 0.02
+    poses = true_trajectory(u)
+    scans = np.stack([room_scan(poses[s + 1], beams, range_sigma, rng=rng) for s in range(steps)])
+    return {"scans": scans, "poses": poses, "u": u}
+
+
 def encoder_for(pose_est, u):
     """The `encoder` argument that makes Robot.cpp:140-145 recover the intended odometry (Q5):
     u[2] = theta - enc[2], u[0] = |xy - enc_xy|."""

@@ -1,0 +1,58 @@
+"""Line extraction: the CPU restatement oracle/lines_oracle.cpp pinned
+(i) BITWISE against the reference's own lineFitting.cpp / simplifyPath.cpp (deterministic build,
+    oracle/_ref/libslamlines.so) -- only where /root/reference was available to build it, and
+(ii) against golden vectors that build produced (tests/golden/lines_literal.npz, make_golden_lines.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import LinesOracle, LiteralLineExtraction, have_literal_lines
+from slam_ros_b200 import scenario as sc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lines_literal.npz")
+
+
+def test_restatement_matches_golden_vectors_bitwise():
+    g = np.load(GOLD)
+    lo = LinesOracle()
+    for s in range(g["scans"].shape[0]):
+        rows, n = lo.extract(g["scans"][s], 64)
+        assert n == int(g["count"][s])
+        assert np.array_equal(rows, g["rows"][s, :n]), "scan %d" % s
+    assert g["count"].min() >= 15           # the room gives ~20 lines per scan
+
+
+@pytest.mark.skipif(not have_literal_lines(), reason="literal reference not built (no /root/reference)")
+def test_restatement_matches_literal_reference_bitwise():
+    lo = LinesOracle(); lit = LiteralLineExtraction()
+    S = sc.room_scans(steps=10, seed=29, range_sigma=2e-3)
+    for s in range(10):
+        a, n = lo.extract(S["scans"][s]); b, m = lit.extract(S["scans"][s])
+        assert n == m and np.array_equal(a, b), "scan %d" % s
+
+
+@pytest.mark.skipif(not have_literal_lines(), reason="literal reference not built (no /root/reference)")
+def test_edge_payloads_match_literal_reference():
+    lo = LinesOracle(); lit = LiteralLineExtraction()
+    S = sc.room_scans(steps=1, seed=5)
+    full = S["scans"][0]
+    cases = [full[:0], full[:1], full[:3], full[40:47], full[::7], np.concatenate([full[:90], full[200:260]])]
+    dead = full.copy(); dead[::2, 0] = 0.0                   # every other beam without a return (r <= 0.05 is dropped)
+    cases.append(dead)
+    for k, c in enumerate(cases):
+        a, n = lo.extract(c); b, m = lit.extract(c)
+        assert n == m and np.array_equal(a, b), "case %d" % k
+
+
+def test_lines_are_canonical_and_feed_the_filter_convention():
+    """(alfa, r) with r >= 0 and alfa in (-pi, pi], C_AR diagonal with positive variances below the 0.01 cut
+    (lineFitting.cpp:586-638, main.cpp:66-69) -- what Robot::localize consumes (simplifyPath.h:62-79)."""
+    lo = LinesOracle()
+    S = sc.room_scans(steps=3, seed=2)
+    for s in range(3):
+        rows, n = lo.extract(S["scans"][s])
+        assert n == len(rows) and n > 10
+        assert (rows[:, 1] >= 0).all() and (np.abs(rows[:, 0]) <= np.pi + 1e-12).all()
+        assert (rows[:, 3] == 0).all() and (rows[:, 4] == 0).all()
+        assert (rows[:, 2] >= 0).all() and (rows[:, 2] <= 0.01).all() and (rows[:, 5] >= 0).all()
