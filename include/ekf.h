@@ -190,6 +190,25 @@ int ekf_batch_sync(ekf_batch* b);
 int ekf_batch_download(ekf_batch* b, int filter, double* y, double* P, int* n_lines, double pose[3]);
 const char* ekf_batch_last_error(const ekf_batch* b);
 
+/* --- line extraction on the device -------------------------------------------------
+ * What the node does with one `mappingPoints` payload before Robot::localize: slam_ros/main.cpp:37-71
+ * (`mapping_cb`: (r, angle) float pairs, alfa = angle - pi, returns with r > 0.05 m, variance 0.01) and
+ * LineExtraction (slam_ros/lineFitting.cpp:640-702: sort, 0.5 m segmentation, recursive split, fit, finite-
+ * difference covariance, end points, LineConversion), then alfa += pi (main.cpp:66-69).  Output per line, in the
+ * reference's order: 10 doubles = alfa, r, C_AR[4] (row-major, off-diagonals 0), lineInterval[0] (alfa, r),
+ * lineInterval[1] (alfa, r) -- i.e. the `line` fields Robot::localize reads (simplifyPath.h:62-79).
+ * At most 1024 points per payload.  *n_lines may exceed max_lines (then only max_lines were written). */
+typedef struct ekf_lx ekf_lx;
+int ekf_lx_create(ekf_lx** out, int device, int max_lines);
+int ekf_lx_destroy(ekf_lx* lx);
+const char* ekf_lx_last_error(const ekf_lx* lx);
+int ekf_lx_extract(ekf_lx* lx, int n_pairs, const float* data, int* n_lines, double* lines);
+/* Asynchronous, payload already in HBM; the results stay there in the layout ekf_scan_device consumes:
+ * *d_z = max_lines x (alfa, r), *d_R = max_lines x 4, *d_count = the number of lines (device int). */
+int ekf_lx_extract_device(ekf_lx* lx, int n_pairs, const float* d_data, const double** d_z, const double** d_R,
+                          const int** d_count);
+int ekf_lx_sync(ekf_lx* lx);
+
 const char* ekf_version(void);
 
 #ifdef __cplusplus

@@ -4,5 +4,5 @@ The product is the CUDA shared library ``libekfcuda.so`` (C ABI: include/ekf.h).
 its sources (csrc/), the build script, a thin ctypes binding (ekf.py) and the host-side mirror of the
 reference's ``Robot`` class (robot.py).  There is no CPU fallback anywhere in this package.
 """
-from .ekf import EkfFilter, EkfBatch, EkfError, load_library, library_path  # noqa: F401
+from .ekf import EkfFilter, EkfBatch, EkfError, LineExtractor, load_library, library_path  # noqa: F401
 from .robot import Robot, Line  # noqa: F401

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libekfcuda.so")
-SOURCES = ["ekf_kernels.cu", "ekf_api.cu", "ekf_batch.cu"]
+SOURCES = ["ekf_kernels.cu", "ekf_api.cu", "ekf_batch.cu", "ekf_lines.cu"]
 HEADERS = ["ekf_internal.h", "ekf_device.cuh", os.path.join("..", "..", "include", "ekf.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

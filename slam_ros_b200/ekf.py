@@ -47,6 +47,7 @@ SYMBOLS = [
     "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_profile_read_lines", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
     "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_shard_ipc_handle", "ekf_shard_connect", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
     "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
+    "ekf_lx_create", "ekf_lx_destroy", "ekf_lx_last_error", "ekf_lx_extract", "ekf_lx_extract_device", "ekf_lx_sync",
 ]
 
 
@@ -100,6 +101,13 @@ def load_library():
     lib.ekf_batch_scan_device.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     lib.ekf_batch_sync.argtypes = [vp]
     lib.ekf_batch_download.argtypes = [vp, C.c_int, _dp, _dp, _ip, _dp]
+    lib.ekf_lx_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.ekf_lx_destroy.argtypes = [vp]
+    lib.ekf_lx_last_error.restype = C.c_char_p
+    lib.ekf_lx_last_error.argtypes = [vp]
+    lib.ekf_lx_extract.argtypes = [vp, C.c_int, C.POINTER(C.c_float), _ip, _dp]
+    lib.ekf_lx_extract_device.argtypes = [vp, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.ekf_lx_sync.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -386,3 +394,52 @@ class EkfBatch:
         y = np.zeros(self.n); P = np.zeros((self.n, self.n)); L = C.c_int(0); pose = np.zeros(3)
         self._check(self._lib.ekf_batch_download(self._h, int(f), _p(y), _p(P), C.byref(L), _p(pose)), "ekf_batch_download")
         return y, P, int(L.value), pose
+
+
+class LineExtractor:
+    """ekf_lx: the node's `mapping_cb` + LineExtraction (slam_ros/main.cpp:37-71, lineFitting.cpp:640-702) on the
+    device.  extract(payload) -> (rows, n): rows[i] = alfa, r, C_AR[4], interval0 (alfa, r), interval1 (alfa, r)."""
+
+    def __init__(self, device=0, max_lines=128):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.max_lines = int(max_lines)
+        rc = self._lib.ekf_lx_create(C.byref(self._h), int(device), self.max_lines)
+        if rc != EKF_OK:
+            msg = self._lib.ekf_lx_last_error(self._h).decode() if self._h else ""
+            if self._h:
+                self._lib.ekf_lx_destroy(self._h)
+                self._h = C.c_void_p()
+            raise EkfError(rc, "ekf_lx_create", msg)
+
+    def _check(self, rc, where):
+        if rc != EKF_OK:
+            raise EkfError(rc, where, self._lib.ekf_lx_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ekf_lx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, payload):
+        d = np.ascontiguousarray(np.asarray(payload, dtype=np.float32).reshape(-1))
+        out = np.zeros((self.max_lines, 10)); n = C.c_int(0)
+        self._check(self._lib.ekf_lx_extract(self._h, d.size // 2, d.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n),
+                                             _p(out)), "ekf_lx_extract")
+        return out[:min(n.value, self.max_lines)].copy(), int(n.value)
+
+    def extract_device(self, d_payload, n_pairs):
+        """Payload already in HBM (raw device address).  Returns the device addresses (z, R, count) of the result."""
+        z = C.c_void_p(); R = C.c_void_p(); cnt = C.c_void_p()
+        self._check(self._lib.ekf_lx_extract_device(self._h, int(n_pairs), C.c_void_p(d_payload), C.byref(z), C.byref(R),
+                                                    C.byref(cnt)), "ekf_lx_extract_device")
+        return z.value, R.value, cnt.value
+
+    def sync(self):
+        self._check(self._lib.ekf_lx_sync(self._h), "ekf_lx_sync")

@@ -1,0 +1,85 @@
+"""Line extraction on the device (ekf_lx_*) against the CPU restatement (oracle/lines_oracle.cpp,
+itself bitwise equal to the reference's own lineFitting.cpp) and the golden vectors the reference produced.
+
+Tolerances (floating point; the kernel evaluates the fit's pair sums in closed form and reduces in parallel):
+  number of lines and their order: exact;  (alfa, r): 1e-10 absolute;  lineInterval end points: 1e-8;
+  C_AR: 1e-4 relative -- the reference's own forward differences (eps = 1e-6) carry ~1e-7 relative rounding noise."""
+import os
+
+import numpy as np
+import pytest
+
+from slam_ros_b200 import scenario as sc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lines_literal.npz")
+
+
+def _compare(rows, n, ref, m, what):
+    assert n == m, "%s: %d lines vs %d" % (what, n, m)
+    if n == 0:
+        return
+    d = np.abs(rows[:, 0] - ref[:, 0])
+    d = np.minimum(d, np.abs(d - 2 * np.pi))                      # alfa = +-pi is one direction
+    assert d.max() < 1e-10, (what, d.max())
+    assert np.abs(rows[:, 1] - ref[:, 1]).max() < 1e-10, what
+    assert (rows[:, 3] == 0).all() and (rows[:, 4] == 0).all()
+    for c in (2, 5):
+        rel = np.abs(rows[:, c] - ref[:, c]) / np.maximum(np.abs(ref[:, c]), 1e-300)
+        assert rel.max() < 1e-4, (what, c, rel.max())
+    da = np.abs(rows[:, [6, 8]] - ref[:, [6, 8]])
+    da = np.minimum(da, np.abs(da - 2 * 3.14159265))
+    assert da.max() < 1e-8, (what, da.max())
+    assert np.abs(rows[:, [7, 9]] - ref[:, [7, 9]]).max() < 1e-8, what
+
+
+def test_golden_payloads_from_the_reference(libekf):
+    from slam_ros_b200 import LineExtractor
+    g = np.load(GOLD)
+    lx = LineExtractor(max_lines=64)
+    for s in range(g["scans"].shape[0]):
+        rows, n = lx.extract(g["scans"][s])
+        m = int(g["count"][s])
+        _compare(rows, n, g["rows"][s, :m], m, "golden scan %d" % s)
+
+
+def test_room_trajectory_against_the_oracle(libekf):
+    from slam_ros_b200 import LineExtractor
+    from oracle.oracle import LinesOracle
+    lo = LinesOracle(); lx = LineExtractor()
+    S = sc.room_scans(steps=40, seed=17, range_sigma=2e-3)
+    total = 0
+    for s in range(40):
+        rows, n = lx.extract(S["scans"][s]); ref, m = lo.extract(S["scans"][s])
+        _compare(rows, n, ref, m, "scan %d" % s)
+        total += n
+    assert total > 40 * 15
+
+
+def test_edge_payloads(libekf):
+    """Empty payload, fewer than two returns, tiny segments, dropped beams, and an UNSORTED payload (the reference
+    sorts by angle first, lineFitting.cpp:642)."""
+    from slam_ros_b200 import LineExtractor
+    from oracle.oracle import LinesOracle
+    lo = LinesOracle(); lx = LineExtractor()
+    full = sc.room_scans(steps=1, seed=5)["scans"][0]
+    dead = full.copy(); dead[::2, 0] = 0.0
+    rng = np.random.default_rng(3)
+    shuffled = full[rng.permutation(full.shape[0])]
+    cases = [full[:0], full[:1], full[:3], full[40:47], full[::7], np.concatenate([full[:90], full[200:260]]), dead, shuffled]
+    for k, c in enumerate(cases):
+        rows, n = lx.extract(c); ref, m = lo.extract(c)
+        _compare(rows, n, ref, m, "case %d" % k)
+
+
+def test_extracted_lines_drive_the_filter(libekf):
+    """The node's loop (slam_ros/main.cpp:139-147): payload -> lines -> Robot::localize, all on the device path."""
+    from slam_ros_b200 import LineExtractor, EkfFilter
+    lx = LineExtractor(); f = EkfFilter(capacity_lines=100)
+    S = sc.room_scans(steps=12, seed=9, range_sigma=1e-3)
+    for s in range(12):
+        rows, n = lx.extract(S["scans"][s])
+        m = min(n, 9)                                              # the reference cannot take more than 9 new lines per scan (Q4)
+        rc, j, pose = f.scan(S["u"][s], rows[:m, 0:2], rows[:m, 2:6])
+        assert rc == 0
+    assert f.lines >= 9 and np.isfinite(f.pose).all()
