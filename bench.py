@@ -13,6 +13,8 @@ sweep), augmentation.  Workloads (BASELINE.json `configs`):
     mc       configs[3]  Monte-Carlo batch, 4096 independent filters x 50 landmarks, sharded over ranks
     room     configs[0]  the reference-sized filter (LINESIZE=100) on the synthetic room; its CPU baseline /
                          reference arm is the LITERAL reference (oracle/_ref: Robot.cpp compiled over the GSL shim)
+    extract  (8f row 2)  line extraction of 361-beam scans (scans/s); CPU baseline = the reference's own
+                         lineFitting.cpp (oracle/_ref/libslamlines.so) where built, else the restatement
 
 With --gpus N > 1 (launched by torchrun, one rank per GPU) the default workload runs N independent
 filters (replicas; the path needs no collective) -> "scaling": "weak"; `40k` runs ONE filter row-sharded
@@ -45,6 +47,7 @@ WORKLOADS = {
     "40k": dict(N=40000, m=8, headroom=1024, desc="configs[4]: single filter, 40k line landmarks, m=8"),
     "mc": dict(N=50, m=8, headroom=14, filters=4096, desc="configs[3]: Monte-Carlo batch, 4096 filters x 50 landmarks, m=8"),
     "room": dict(N=100, m=9, headroom=0, desc="configs[0]: the reference-sized filter (LINESIZE=100) on the synthetic 2-D room, 361-beam scans"),
+    "extract": dict(N=0, m=0, headroom=0, desc="SURVEY 8f-2: line extraction (mapping_cb + LineExtraction) of 361-beam scans of the synthetic room"),
 }
 
 
@@ -237,10 +240,84 @@ def run_room(args, rank, world, local):
     }
 
 
+def lines_cpu_run(steps, budget_s):
+    """Line extraction on the host: the reference's own sources (deterministic build) when present, else the port."""
+    from oracle.oracle import LinesOracle, LiteralLineExtraction, have_literal_lines
+    from slam_ros_b200 import scenario as sc
+    kind = "reference" if have_literal_lines() else "port"
+    ex = LiteralLineExtraction() if kind == "reference" else LinesOracle()
+    S = sc.room_scans(steps=max(steps, 4), seed=17, range_sigma=2e-3)
+    ex.extract(S["scans"][0])
+    t0 = time.perf_counter(); done = 0
+    for s in range(steps):
+        ex.extract(S["scans"][s]); done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    what = ("LineExtraction of slam_ros/lineFitting.cpp itself (g++ -O2, GSL shim, zero-initialised locals; it also writes "
+            "three text files per call, as in the node)") if kind == "reference" else "oracle/lines_oracle.cpp (g++ -O2)"
+    return done / dt, {"kind": kind, "cores": 1, "value": done / dt, "unit": "scans/s",
+                       "sample": "%d scans of the same payloads through %s" % (done, what)}
+
+
+def run_extract(args, rank, world, local):
+    """payload -> lines.  value: payloads resident in HBM, results left in HBM (ekf_lx_extract_device,
+    K scans enqueued back to back); e2e: host payload in, host lines out, one sync per scan (ekf_lx_extract)."""
+    import torch
+    from slam_ros_b200 import LineExtractor, scenario as sc
+    K, W = args.steps, args.warmup
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    S = sc.room_scans(steps=W + K, seed=17, range_sigma=2e-3)
+    scans = S["scans"]; beams = scans.shape[1]
+    lx = LineExtractor(device=local)
+    d_scans = torch.tensor(scans, dtype=torch.float32, device=dev)
+    for s in range(W):
+        lx.extract_device(d_scans[s].data_ptr(), beams)
+    lx.sync(); torch.cuda.synchronize()
+    clocks = ClockSampler(local); clocks.start()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        lx.extract_device(d_scans[s].data_ptr(), beams)
+    lx.sync()
+    ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); nl = 0
+    for s in range(W, W + K):
+        rows, n = lx.extract(scans[s]); nl += n
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop()
+    peak, peak_src = measured_peaks()
+    bytes_per_scan = 8.0 * beams + 6 * 8.0 * beams + 10 * 8.0 * (nl / K)     # payload + point arrays + lines
+    return {
+        "metric": "line-extraction scans/s (361 beams -> (alfa, r, C_AR, end points) per line)", "value": K / (ms / 1e3), "unit": "scans/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS["extract"]["desc"], "beams": int(beams), "lines_per_scan_mean": nl / K,
+                   "l2": "a scan is 3 KB: the path is three small dependent kernels, launch / latency bound (no L2 flush applies)"},
+        "roofline": {"bound": "hbm", "kernel": "k_lx_segments (one thread block per 0.5 m segment: split recursion + finite-difference covariance)",
+                     "achieved": bytes_per_scan / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_per_scan / (ms / K * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_per_scan, "traffic": None,
+                     "note": "latency-bound by construction (25 KB per scan); reported for the contract, not a roofline claim"},
+        "e2e": {"value": K / (e2e_ms / 1e3), "unit": "scans/s", "h2d_bytes_per_step": int(8 * beams), "d2h_bytes_per_step": 4 + 80 * 128,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": 3 * 2 * K, "clocks": clk,
+    }
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
+    if args.workload == "extract":
+        val, info = lines_cpu_run(args.steps, budget_s=150.0)
+        print(json.dumps({"impl": "reference", "metric": "line-extraction scans/s (361 beams -> (alfa, r, C_AR, end points) per line)",
+                          "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": {"workload": w["desc"], "beams": 361}, "cpu_baseline": info,
+                          "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
     if args.workload == "room":
         val, info = literal_run(args.steps, args.warmup, budget_s=150.0)
         if val is None:
@@ -492,12 +569,16 @@ def main():
         line = run_monte_carlo(args, rank, world, local)
     elif args.workload == "room":
         line = run_room(args, rank, world, local) if rank == 0 else None
+    elif args.workload == "extract":
+        line = run_extract(args, rank, world, local) if rank == 0 else None
     else:
         sharded = args.workload == "40k" and world > 1
         line = run_single_or_replicas(args, rank, world, local, sharded)
     if rank == 0 and line is not None:
         if world == 1 and not args.no_cpu_baseline:
-            if args.workload == "room":
+            if args.workload == "extract":
+                val, info = lines_cpu_run(steps=200, budget_s=args.cpu_budget)
+            elif args.workload == "room":
                 val, info = literal_run(steps=1000, warmup=3, budget_s=args.cpu_budget)
             else:
                 val, info = cpu_run(args.workload, steps=1000, warmup=1, budget_s=args.cpu_budget)

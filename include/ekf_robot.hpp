@@ -144,5 +144,55 @@ class Robot {
   std::vector<double> z_, R_;
 };
 
+/* The device form of what `mapping_cb` does with one `mappingPoints` payload (slam_ros/main.cpp:37-71):
+ *     points from (r, angle) float pairs -> lines = LineExtraction(points) -> lin.alfa += M_PI (wrapped).
+ * `extract` fills any line type that has the reference's members (simplifyPath.h:62-79): .alfa, .r,
+ * .C_AR->data[0..3] and .lineInterval (two {alfa, r} entries).  The reference allocates C_AR with
+ * gsl_matrix_alloc(2, 2) inside Covariancia (lineFitting.cpp:384); here the caller passes the allocator
+ * (e.g. `[]{ return gsl_matrix_alloc(2, 2); }`), so ownership stays where the node expects it. */
+class LineExtractor {
+ public:
+  explicit LineExtractor(int device = 0, int max_lines = 128) : lx_(0), max_lines_(max_lines), rows_(10 * (size_t)max_lines) {
+    const int rc = ekf_lx_create(&lx_, device, max_lines);
+    if (rc != EKF_OK) {
+      std::string msg = lx_ ? ekf_lx_last_error(lx_) : "ekf_lx_create failed";
+      if (lx_) ekf_lx_destroy(lx_);
+      lx_ = 0;
+      throw std::runtime_error("libekfcuda: " + msg);
+    }
+  }
+  ~LineExtractor() { if (lx_) ekf_lx_destroy(lx_); }
+  LineExtractor(const LineExtractor&) = delete;
+  LineExtractor& operator=(const LineExtractor&) = delete;
+
+  /* data = msg.data, n_floats = msg.layout.dim[0].size (main.cpp:46).  Appends to `lines`; returns the count. */
+  template <class Line, class AllocCov>
+  int extract(const float* data, int n_floats, std::vector<Line>& lines, AllocCov alloc_cov) {
+    int n = 0;
+    const int rc = ekf_lx_extract(lx_, n_floats / 2, data, &n, rows_.data());
+    if (rc != EKF_OK) throw std::runtime_error(std::string("libekfcuda: ") + ekf_lx_last_error(lx_));
+    if (n > max_lines_) n = max_lines_;
+    for (int i = 0; i < n; ++i) {
+      const double* o = &rows_[10 * (size_t)i];
+      Line l;
+      l.alfa = o[0]; l.r = o[1];
+      l.C_AR = alloc_cov();
+      for (int t = 0; t < 4; ++t) l.C_AR->data[t] = o[2 + t];
+      for (int k = 0; k < 2; ++k) {
+        typename decltype(l.lineInterval)::value_type p;
+        p.alfa = o[6 + 2 * k]; p.r = o[7 + 2 * k];
+        l.lineInterval.push_back(p);
+      }
+      lines.push_back(l);
+    }
+    return n;
+  }
+
+ private:
+  ekf_lx* lx_;
+  int max_lines_;
+  std::vector<double> rows_;
+};
+
 }  // namespace ekfcuda
 #endif

@@ -13,6 +13,7 @@
  * shim's gsl_matrix_alloc zero-filling (-DGSL_SHIM_ZERO_ALLOC): both are behaviours the reference may legally
  * exhibit, and they are the ones its authors evidently intended.
  *
+ * WriteCov (lineFitting.cpp:53-59) prints rejected covariances with printf and cout; both are silenced for the call.
  * LineExtraction also writes dist.txt / p_data.txt / p_raw_data.txt into the working directory on every call;
  * the harness runs it inside a scratch directory.
  */
@@ -22,6 +23,8 @@
 #include <vector>
 #include <cmath>
 #include <unistd.h>
+#include <fcntl.h>
+#include <cstdio>
 #include "LineXtraction.h"
 
 extern "C" {
@@ -39,7 +42,10 @@ int ref_extract_lines(int n_pairs, const float* data, int max_lines, double* out
   }
   if (chdir(scratch) != 0) return -1;
   std::ios_base::iostate old = std::cout.rdstate();
-  std::cout.setstate(std::ios_base::failbit);                /* lineFitting prints from WriteCov */
+  std::cout.setstate(std::ios_base::failbit);                /* lineFitting prints from WriteCov: cout ... */
+  std::fflush(stdout);                                       /* ... and printf: park fd 1 on /dev/null for the call */
+  const int saved_fd = dup(1), null_fd = open("/dev/null", O_WRONLY);
+  if (saved_fd >= 0 && null_fd >= 0) dup2(null_fd, 1);
   std::vector<polar_point> points;
   polar_point temp;
   for (int i = 0; i < 2 * n_pairs; i += 2) {                 /* main.cpp:46-62 */
@@ -56,6 +62,9 @@ int ref_extract_lines(int n_pairs, const float* data, int max_lines, double* out
     lin.alfa += M_PI;
     lin.alfa = lin.alfa > M_PI ? lin.alfa - 2.0 * M_PI : lin.alfa;
   }
+  std::fflush(stdout);
+  if (saved_fd >= 0) { dup2(saved_fd, 1); close(saved_fd); }
+  if (null_fd >= 0) close(null_fd);
   std::cout.clear(old);
   if (chdir(cwd) != 0) return -1;
   const int n = (int)lines.size();

@@ -55,3 +55,38 @@ def test_cpp_robot_dropin_matches_oracle(libekf):
     ok, ax, ang = so.get_ellipse()
     assert ell[0] == 1.0 and np.allclose(ell[1:3], ax, rtol=1e-5)
     assert n_intervals == 4 * added          # two end points (x, y) per appended line, Robot.cpp:869-879
+
+
+def test_cpp_line_extractor_feeds_robot(libekf):
+    """ekfcuda::LineExtractor + ekfcuda::Robot compiled with g++ and driven like the node's callback and loop
+    (slam_ros/main.cpp:37-71, 139-174); the extracted lines are checked against the CPU oracle."""
+    from oracle.oracle import LinesOracle
+    from slam_ros_b200 import library_path
+    steps = 6
+    S = sc.room_scans(steps=steps, seed=21, range_sigma=1e-3)
+    beams = S["scans"].shape[1]
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "lines"); fin = os.path.join(d, "in.bin"); fout = os.path.join(d, "out.bin")
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "tests", "cpp", "lines_main.cpp"), library_path(),
+                               "-Wl,-rpath," + os.path.dirname(library_path()), "-o", exe])
+        with open(fin, "wb") as f:
+            np.array([steps, beams], dtype=np.int32).tofile(f)
+            S["scans"].astype(np.float32).tofile(f)
+            S["u"].astype(np.float64).tofile(f)
+        subprocess.check_call([exe, fin, fout])
+        out = np.fromfile(fout, dtype=np.float64)
+    lo = LinesOracle()
+    k = 0
+    for s in range(steps):
+        n = int(out[k]); k += 1
+        rows = out[k:k + 10 * n].reshape(n, 10); k += 10 * n
+        pose = out[k:k + 4]; k += 4
+        ref, m = lo.extract(S["scans"][s])
+        assert n == m
+        assert np.abs(rows[:, :2] - ref[:, :2]).max() < 1e-10
+        assert (np.abs(rows[:, [2, 5]] - ref[:, [2, 5]]) / ref[:, [2, 5]]).max() < 1e-4
+        assert np.abs(rows[:, 6:] - ref[:, 6:]).max() < 1e-8
+        assert np.isfinite(pose).all() and pose[3] >= 9
+    assert k == out.size
