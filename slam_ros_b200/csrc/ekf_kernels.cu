@@ -769,7 +769,7 @@ struct __align__(128) SweepStage {
 template <int TR, int TC, int STAGES, int C>
 struct SweepShared {
   SweepStage<TR, TC, C> stage[STAGES];
-  unsigned long long full[STAGES];
+  unsigned long long full[STAGES][2];  /* [stage][consumer group]: a group only ever waits on its own barrier (see k_sweep_quad) */
   unsigned long long empty[STAGES];
   int meta[STAGES][4];                /* first local row, first global row, first column, - */
 };
@@ -855,17 +855,18 @@ __device__ __forceinline__ void sweep_producer(SweepShared<TR, TC, STAGES, C>& s
     const unsigned ph = (it / STAGES) & 1;
     mbar_wait(&sh.empty[s], ph ^ 1);
     sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
-    mbar_expect_tx(&sh.full[s], bytes);
-    tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, &sh.full[s], pol);
+    unsigned long long* fullb = &sh.full[s][sentinels > 1 ? (it & 1) : 0];     /* the barrier of the group that consumes tile `it` */
+    mbar_expect_tx(fullb, bytes);
+    tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, fullb, pol);
     if (band) {
       for (int bi = 0; bi < nbands; ++bi) {
-        tma_load_tile(sh.stage[s].K[8 * bi], &tmapK, 2 * col0, slot0 + c0 + 8 * bi, &sh.full[s]);
-        tma_load_tile(sh.stage[s].KS[8 * bi], &tmapKS, 2 * grow0, slot0 + c0 + 8 * bi, &sh.full[s]);
+        tma_load_tile(sh.stage[s].K[8 * bi], &tmapK, 2 * col0, slot0 + c0 + 8 * bi, fullb);
+        tma_load_tile(sh.stage[s].KS[8 * bi], &tmapKS, 2 * grow0, slot0 + c0 + 8 * bi, fullb);
       }
     } else {
       for (int c = 0; c < np; ++c) {
-        bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(slot0 + c0 + c) * g.ld + col0, TC * sizeof(double2), &sh.full[s]);
-        bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(slot0 + c0 + c) * g.ld + grow0, TR * sizeof(double2), &sh.full[s]);
+        bulk_load(sh.stage[s].K[c], b.Kp + (size_t)(slot0 + c0 + c) * g.ld + col0, TC * sizeof(double2), fullb);
+        bulk_load(sh.stage[s].KS[c], b.KSp + (size_t)(slot0 + c0 + c) * g.ld + grow0, TR * sizeof(double2), fullb);
       }
     }
   }
@@ -875,7 +876,7 @@ __device__ __forceinline__ void sweep_producer(SweepShared<TR, TC, STAGES, C>& s
     const unsigned ph = (it / STAGES) & 1;
     mbar_wait(&sh.empty[s], ph ^ 1);
     sh.meta[s][3] = 0;
-    mbar_arrive(&sh.full[s]);
+    mbar_arrive(&sh.full[s][sentinels > 1 ? (it & 1) : 0]);
   }
 }
 
@@ -903,7 +904,7 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
   const int nl = 3 + 2 * (view ? view->L : b.st->L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CW); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s][0], 1); mbar_init(&sh.empty[s], CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -920,7 +921,7 @@ k_sweep_pipe(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
   for (int it = 0;; ++it) {
     const int s = it % STAGES;
     const unsigned ph = (it / STAGES) & 1;
-    mbar_wait(&sh.full[s], ph);
+    mbar_wait(&sh.full[s][0], ph);
     if (!sh.meta[s][3]) break;
     const SweepStage<TR, TC, C>& st = sh.stage[s];
     const int lrow0 = sh.meta[s][0], grow0 = sh.meta[s][1], col0 = sh.meta[s][2];
@@ -988,7 +989,7 @@ k_sweep_quad(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
   const int nl = 3 + 2 * (view ? view->L : b.st->L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], CW / 2); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s][0], 1); mbar_init(&sh.full[s][1], 1); mbar_init(&sh.empty[s], CW / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1003,10 +1004,15 @@ k_sweep_quad(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
   const int cA = 2 * l16, cB = 32 + 2 * l16;                 /* its two column pairs */
   const bool sw = (l16 & 4) != 0;                            /* fetch the pair's halves in the opposite order */
   const int o0 = sw ? 1 : 0, o1 = sw ? 0 : 1;
+  /* Each (stage, group) pair has its OWN full barrier.  mbarrier waits see only a phase PARITY; with an odd ring a
+   * stage alternates between the groups, and a group that ran ahead could mistake the other group's not-yet-landed
+   * tile for its own (same parity) if they shared the barrier.  With its own barrier a group observes every phase
+   * of it in order: the k-th use of (stage, group) is tile k * PERIOD + ... , PERIOD = lcm(STAGES, 2). */
+  constexpr int PERIOD = (STAGES % 2) ? 2 * STAGES : STAGES;
   for (int it = grp;; it += 2) {
     const int s = it % STAGES;
-    const unsigned ph = (it / STAGES) & 1;
-    mbar_wait(&sh.full[s], ph);
+    const unsigned ph = (it / PERIOD) & 1;
+    mbar_wait(&sh.full[s][grp], ph);
     if (!sh.meta[s][3]) break;
     const SweepStage<TR, TC, C>& st = sh.stage[s];
     const int lrow0 = sh.meta[s][0], grow0 = sh.meta[s][1], col0 = sh.meta[s][2];

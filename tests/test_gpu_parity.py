@@ -3,12 +3,15 @@
 Bar (BASELINE.json north_star): association indices bit-exact; state and P within 1e-9 relative after
 every step, P measured as max|dP| / max|P| (the reference's P is not symmetric to the ulp).
 """
+import os
+
 import numpy as np
 import pytest
 
 from slam_ros_b200 import scenario as sc
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOL = 1e-9   # relative; north_star
 
@@ -475,3 +478,30 @@ def test_overlapped_pipeline_interleaved_with_stepwise_calls(libekf, oracle_cls)
             f.sweep_probe(m=3, repeats=1)               # forces a drain; must leave the state untouched
             compare_state(f, so, "interleaved step %d" % s)
     compare_state(f, so, "interleaved final")
+
+
+@pytest.mark.parametrize("maxc", [8, 16, 32])
+def test_sweep_ring_for_every_pending_count_and_pass_width(libekf, maxc):
+    """The stand-alone sweep for every pending-term count 1..64 and every pass width (EKF_SWEEP_MAXC), state
+    untouched bit for bit.  Regression: with a 3-stage ring shared by the two consumer groups, a group that ran
+    ahead mistook the other group's tile for its own (mbarrier waits only see a phase parity) -- found as a launch
+    failure at 17 terms with 16-term passes; each (stage, group) now has its own full barrier."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from slam_ros_b200 import EkfFilter, scenario as sc\n"
+        "N = 1500\n"
+        "scn = sc.map_scenario(N, 1, m=8, seed=1)\n"
+        "f = EkfFilter(capacity_lines=N + 64)\n"
+        "f.scan(np.zeros(3), scn['seed_z'], scn['seed_R'])\n"
+        "s0 = f.cov_stats()\n"
+        "for mm in range(1, 65):\n"
+        "    f.sweep_probe(m=mm, repeats=2)\n"
+        "assert f.cov_stats() == s0\n"
+        "print('all counts ok')\n"
+    ) % ROOT
+    env = dict(os.environ, EKF_SWEEP_MAXC=str(maxc))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "all counts ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
