@@ -1022,7 +1022,7 @@ k_sweep_quad(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
       pa[i] = *reinterpret_cast<const double2*>(&st.P[(row0 + i) * TC + cA]);
       pb[i] = *reinterpret_cast<const double2*>(&st.P[(row0 + i) * TC + cB]);
     }
-#pragma unroll 2
+#pragma unroll (C > 8 ? 4 : 2)
     for (int c = 0; c < np; ++c) {
       const double2 a0 = st.K[c][cA + o0], a1 = st.K[c][cA + o1];
       const double2 b0 = st.K[c][cB + o0], b1 = st.K[c][cB + o1];
