@@ -6,3 +6,4 @@ reference's ``Robot`` class (robot.py).  There is no CPU fallback anywhere in th
 """
 from .ekf import EkfFilter, EkfBatch, EkfError, LineExtractor, load_library, library_path  # noqa: F401
 from .robot import Robot, Line  # noqa: F401
+from .node import SlamNode  # noqa: F401
