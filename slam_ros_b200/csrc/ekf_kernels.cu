@@ -1325,6 +1325,7 @@ void ekf_prefer_max_smem_carveout(void) {
 }
 int ekf_pick_cluster(void) {
   cudaFuncSetAttribute(k_scan_lines<512, false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  { const char* e = getenv("EKF_CLUSTER"); const int v = e ? atoi(e) : 0; if (v == 1 || v == 2 || v == 4 || v == 8) return v; }   /* A/B measurements */
   const int tries[2] = {16, 8};
   for (int t = 0; t < 2; ++t) {
     cudaLaunchConfig_t cfg;
