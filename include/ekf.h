@@ -163,7 +163,7 @@ int ekf_nccl_unique_id(unsigned char id[128]);
 int ekf_create_sharded(ekf_ctx** out, const ekf_config* cfg, int rank, int world,
                        const unsigned char nccl_unique_id[128]);
 
-/* Fused exchange: after ekf_shard_connect the H-column slices no longer go through NCCL.  The line-loop kernel
+/* Fused exchange: after ekf_shard_connect + ekf_shard_use_fused(1) the H-column slices no longer go through NCCL.  The line-loop kernel
  * itself stores the slice entries a rank owns straight into every peer's exchange buffer over NVLink (peer memory
  * mapped with CUDA IPC), publishes an arrival epoch with a system-scope release store and spins (bounded) on its
  * own flags -- one NVLink round trip per matched line, no kernel boundary, and the scan's sweep then overlaps
@@ -174,6 +174,10 @@ int ekf_create_sharded(ekf_ctx** out, const ekf_config* cfg, int rank, int world
  * EKF_ENCCL instead of hanging the GPU. */
 int ekf_shard_ipc_handle(ekf_ctx* ctx, unsigned char handle[64]);
 int ekf_shard_connect(ekf_ctx* ctx, const unsigned char* handles);
+/* Two-phase switch: ekf_shard_connect only MAPS the peers; the ranks then agree (host-side, e.g. an all-reduce
+ * MIN of the outcomes) and every rank calls ekf_shard_use_fused(ctx, all_mapped) -- ranks on different exchange
+ * paths would wait for each other forever.  on = 0 returns to the NCCL exchange. */
+int ekf_shard_use_fused(ekf_ctx* ctx, int on);
 
 /* --- independent filters (Monte-Carlo batch): no communication -------------------------------------
  * B filters of identical capacity on one device, one thread block per filter, covariance staged in

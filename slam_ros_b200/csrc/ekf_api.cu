@@ -96,7 +96,8 @@ struct ekf_ctx {
   double* xchg;               /* this rank's exchange buffer: [2 halves][colA | colB][ld] doubles + 8 arrival flags */
   void* peer_map[8];          /* the peers' buffers as mapped by cudaIpcOpenMemHandle (NULL for the local one) */
   EkfPeers peers;
-  int peers_ok;               /* ekf_shard_connect succeeded: the H-column slices travel inside the line-loop kernel */
+  int peers_mapped;           /* ekf_shard_connect succeeded: every peer's exchange buffer is mapped */
+  int peers_ok;               /* ekf_shard_use_fused(1): the H-column slices travel inside the line-loop kernel */
   /* staging for download / upload / stats */
   double* d_stage; size_t stage_elems;
   double* d_partials; double* d_out3;
@@ -483,7 +484,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8;
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
   ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);
-  ctx->xchg = 0; ctx->peers_ok = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
+  ctx->xchg = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
   *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -639,7 +640,7 @@ int ekf_shard_connect(ekf_ctx* ctx, const unsigned char* handles) {
   if (!ctx || !handles) return EKF_EINVAL;
   if (!ctx->xchg) { snprintf(ctx->err, sizeof ctx->err, "not a row-sharded filter (or world > 8)"); return EKF_ESTATE; }
   if (ctx->scan_open) return EKF_ESTATE;
-  if (ctx->peers_ok) return EKF_OK;
+  if (ctx->peers_mapped) return EKF_OK;
   CU(cudaSetDevice(ctx->cfg.device));
   const int world = ctx->g.world, rank = ctx->g.rank;
   memset(&ctx->peers, 0, sizeof ctx->peers);
@@ -659,8 +660,18 @@ int ekf_shard_connect(ekf_ctx* ctx, const unsigned char* handles) {
     ctx->peer_map[p] = ptr;
     ctx->peers.xchg[p] = (double*)ptr;
   }
-  ctx->peers_ok = 1;
-  return enable_overlap(ctx);
+  ctx->peers_mapped = 1;
+  return EKF_OK;
+}
+
+int ekf_shard_use_fused(ekf_ctx* ctx, int on) {
+  if (!ctx) return EKF_EINVAL;
+  if (ctx->scan_open) return EKF_ESTATE;
+  if (on && !ctx->peers_mapped) { snprintf(ctx->err, sizeof ctx->err, "ekf_shard_use_fused before a successful ekf_shard_connect"); return EKF_ESTATE; }
+  CU(cudaSetDevice(ctx->cfg.device));
+  { int rc = drain(ctx); if (rc) return rc; }
+  ctx->peers_ok = on ? 1 : 0;
+  return on ? enable_overlap(ctx) : EKF_OK;
 }
 
 int ekf_destroy(ekf_ctx* ctx) {

@@ -45,7 +45,7 @@ SYMBOLS = [
     "ekf_update", "ekf_add_line", "ekf_end_scan", "ekf_scan", "ekf_scan_device", "ekf_sync", "ekf_get_state",
     "ekf_get_robot_cov", "ekf_get_ellipse", "ekf_download", "ekf_upload", "ekf_download_live",
     "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_profile_read_lines", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
-    "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_shard_ipc_handle", "ekf_shard_connect", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
+    "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_shard_ipc_handle", "ekf_shard_connect", "ekf_shard_use_fused", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
     "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
     "ekf_lx_create", "ekf_lx_destroy", "ekf_lx_last_error", "ekf_lx_extract", "ekf_lx_extract_device", "ekf_lx_sync",
 ]
@@ -72,6 +72,7 @@ def load_library():
     lib.ekf_nccl_unique_id.argtypes = [C.c_char_p]
     lib.ekf_shard_ipc_handle.argtypes = [vp, C.c_char_p]
     lib.ekf_shard_connect.argtypes = [vp, C.c_char_p]
+    lib.ekf_shard_use_fused.argtypes = [vp, C.c_int]
     lib.ekf_destroy.argtypes = [vp]
     lib.ekf_predict.argtypes = [vp, _dp, _dp, _dp]
     lib.ekf_associate.argtypes = [vp, _dp, _dp, _ip, _dp]
@@ -188,13 +189,17 @@ class EkfFilter:
 
     def shard_connect(self, handles):
         """handles: the ranks' IPC handles in rank order (list of 64-byte strings).  Returns True when the peers
-        are mapped (fused exchange + overlapped sweep), False when the filter stays on the NCCL exchange."""
+        are mapped; the fused exchange is switched on by shard_use_fused once ALL ranks report True."""
         blob = b"".join(bytes(h) for h in handles)
         rc = self._lib.ekf_shard_connect(self._h, blob)
         if rc == EKF_ECUDA:
             return False
         self._check(rc, "ekf_shard_connect")
         return True
+
+    def shard_use_fused(self, on=True):
+        """Every rank must make the same choice (parallel.connect_shards does the agreement)."""
+        self._check(self._lib.ekf_shard_use_fused(self._h, 1 if on else 0), "ekf_shard_use_fused")
 
     # -- step-wise path (one call per reference block) -----------------------------------------------
     def predict(self, u, x_t0=None):

@@ -49,7 +49,8 @@ def gather_filter_results(local_ids, local_values, n_filters, group=None):
 
 def connect_shards(filt, device, group=None):
     """Row-sharded filter: all-gather the ranks' CUDA IPC handles with torch.distributed and map the peers'
-    exchange buffers (ekf_shard_connect).  Returns True on every rank iff every rank connected."""
+    exchange buffers (ekf_shard_connect); if and only if every rank succeeded, every rank switches to the fused
+    exchange (ekf_shard_use_fused).  Returns the common outcome."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -59,7 +60,10 @@ def connect_shards(filt, device, group=None):
     ok = filt.shard_connect([bytes(h.cpu().tolist()) for h in allh])
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    return bool(int(flag[0]))
+    all_ok = bool(int(flag[0]))
+    if all_ok:                                  # two-phase: only switch paths when EVERY rank mapped its peers
+        filt.shard_use_fused(True)
+    return all_ok
 
 
 def max_over_ranks(value, group=None):

@@ -73,3 +73,52 @@ def test_row_block_ownership_balances_the_triangle():
         rows = [r for r in range(0, 64 * 40) if par.owner_of_row(r, world) == rank]
         loc = sorted(par.local_row(r, world) for r in rows)
         assert loc == list(range(len(rows)))
+
+
+class _StubShard:
+    """Stands in for a row-sharded EkfFilter: records the handles it is asked to connect."""
+
+    def __init__(self, rank, fail=False):
+        self.rank = rank; self.fail = fail; self.seen = None; self.fused = False
+
+    def shard_ipc_handle(self):
+        return bytes([self.rank]) * 64
+
+    def shard_connect(self, handles):
+        self.seen = [bytes(h) for h in handles]
+        return not self.fail
+
+    def shard_use_fused(self, on=True):
+        self.fused = bool(on)
+
+
+def _connect_worker(rank, world, port, fail_rank, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        stub = _StubShard(rank, fail=(rank == fail_rank))
+        ok = par.connect_shards(stub, "cpu")
+        q.put((rank, ok, stub.seen, stub.fused))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_shard_handle_exchange_world2(fail_rank):
+    """connect_shards: every rank receives every rank's 64-byte IPC handle in rank order, and the ranks agree on
+    the outcome (one rank failing to map its peers keeps ALL ranks on the NCCL exchange)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_connect_worker, args=(r, world, port, fail_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, seen, fused in res:
+        assert seen == [bytes([r]) * 64 for r in range(world)]
+        assert ok == (fail_rank < 0) and fused == ok        # no rank switches paths unless all mapped their peers
