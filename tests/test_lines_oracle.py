@@ -56,3 +56,24 @@ def test_lines_are_canonical_and_feed_the_filter_convention():
         assert (rows[:, 1] >= 0).all() and (np.abs(rows[:, 0]) <= np.pi + 1e-12).all()
         assert (rows[:, 3] == 0).all() and (rows[:, 4] == 0).all()
         assert (rows[:, 2] >= 0).all() and (rows[:, 2] <= 0.01).all() and (rows[:, 5] >= 0).all()
+
+
+def test_closed_form_of_the_pair_sums_used_on_the_device():
+    """The identity k_lx_segments relies on (slam_ros_b200/csrc/ekf_lines.cu): with X = r cos a, Y = r sin a and unit
+    weights, (2/p) sum_1 + (1/p) sum_2 = -2 S_xy and (2/p) sum_3 + (1/p) sum_4 = -(S_xx - S_yy) (centred moments),
+    and sum_i r_i cos(a_i - alfa) = cos(alfa) SX + sin(alfa) SY -- so the O(p) evaluation returns the fit of
+    lineFitting.cpp:267-304 (checked here against the restatement's O(p^2) pair sums)."""
+    lo = LinesOracle()
+    rng = np.random.default_rng(4)
+    PI = 3.14159265
+    for _ in range(40):
+        p = int(rng.integers(2, 120))
+        al = rng.uniform(-np.pi, np.pi); R = rng.uniform(0.5, 8.0)
+        th = al + np.sort(rng.uniform(-0.6, 0.6, p))
+        r = R / np.cos(th - al) + rng.standard_normal(p) * 3e-3
+        ref = lo.fit(th, r)
+        X = r * np.cos(th); Y = r * np.sin(th)
+        dx = X - X.mean(); dy = Y - Y.mean()
+        ar = 0.5 * np.arctan2(-2.0 * (dx * dy).sum(), -((dx * dx).sum() - (dy * dy).sum()))
+        rr = (np.cos(ar) * X.sum() + np.sin(ar) * Y.sum()) / p
+        assert abs((ar * 180 / PI) * (PI / 180) - ref[0]) < 1e-11 and abs(rr - ref[1]) < 1e-11
