@@ -386,7 +386,8 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
   if (ctx->overlap) {
     /* small maps: the sweep is a few microseconds, nothing to hide -- the in-place path with the 16-CTA
      * cluster line loop is faster there (measured crossover: a few thousand state entries) */
-    if (m >= 1 && m <= ctx->group && ctx->L_ub > 0 && 3 + 2 * ctx->L_ub >= kOverlapMinN)
+    if (m >= 1 && m <= ctx->group && ctx->L_ub > 0 && 3 + 2 * ctx->L_ub >= kOverlapMinN &&
+        (ctx->g.world == 1 || ctx->peers_ok))     /* a row-sharded filter overlaps only on the fused exchange */
       return enqueue_scan_overlapped(ctx, d_u, d_x_t0, m, d_z, d_R);
     int rc = drain(ctx);
     if (rc) return rc;

@@ -31,7 +31,7 @@ def main():
     cap = N + 64
     f = EkfFilter(capacity_lines=cap, device=local, shard=(rank, world, bytes(uid.cpu().tolist())))
     mode = sys.argv[3] if len(sys.argv) > 3 else "fused"
-    if mode == "fused":                     # in-kernel NVLink exchange; "nccl" keeps the ncclAllReduce path
+    if mode in ("fused", "switch"):         # in-kernel NVLink exchange; "nccl" keeps the ncclAllReduce path
         from slam_ros_b200.parallel import connect_shards
         assert connect_shards(f, dev), "CUDA IPC peer mapping failed"
     so = StructuredOracle(cap)
@@ -40,6 +40,8 @@ def main():
     so.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
     assert rc == 0 and f.lines == so.lines == N
     for s in range(steps):
+        if mode == "switch" and s % 3 == 0:     # every rank leaves / re-enters the fused exchange at the same step
+            f.shard_use_fused((s // 3) % 2 == 1)
         rc, j, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
         st, jo = so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
         assert np.array_equal(j, jo), "rank %d step %d: %s vs %s" % (rank, s, j, jo)

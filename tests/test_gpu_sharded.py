@@ -24,6 +24,7 @@ def _run(world, n_landmarks, steps, mode, port):
     ("nccl", 300, 25, 29517),
     ("fused", 300, 25, 29518),      # synchronous path: cooperative line loop, sweep after it
     ("fused", 3300, 12, 29519),     # n = 6603 >= the overlap threshold: sweep of scan s under the line loop of scan s+1
+    ("switch", 3300, 12, 29520),    # alternates between the NCCL and the fused exchange every 3 scans (same bits either way)
 ])
 def test_row_sharded_filter_two_ranks(libekf, mode, n_landmarks, steps, port):
     import torch
