@@ -505,3 +505,54 @@ def test_sweep_ring_for_every_pending_count_and_pass_width(libekf, maxc):
     env = dict(os.environ, EKF_SWEEP_MAXC=str(maxc))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "all counts ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_overlapped_pipeline_through_augmentation_capacity_and_map_reset(libekf, oracle_cls):
+    """The overlapped two-stream path (n = 6203) while the map GROWS (unmatched lines appended while the previous
+    scan's sweep is in flight), hits the capacity policy (Q4: lines that do not fit are dropped, EKF_ECAPACITY) and
+    the map reset (Robot.cpp:893-904: savedLineCount > capacity - headroom wipes the map), then rebuilds -- all
+    without leaving the asynchronous path; every step's matches and pose against the oracle, state at the end."""
+    from slam_ros_b200.ekf import EKF_ECAPACITY
+    N, steps, m = 3100, 12, 8
+    scn = sc.map_scenario(N, steps, m=m, seed=61)
+    cap = N + 14                                              # reset when L > cap - 10 = 3104; room for 14 new lines
+    f, so = seed_pair(N, cap, oracle_cls, scn)
+    so._lib.ekfo_set_threads(so._h, 0)
+    rng = np.random.default_rng(5)
+    saw_capacity = saw_reset = False
+    for s in range(steps):
+        z = scn["z"][s].copy(); R = scn["R"][s].copy()
+        if s >= 2:                                            # half of the lines are walls the map has never seen
+            z[4:, 0] = rng.uniform(-3.0, 3.0, m - 4)
+            z[4:, 1] = rng.uniform(20.0, 30.0, m - 4)
+        L_before = so.lines
+        rc, j, pose = f.scan(scn["u"][s], z, R)
+        st, jo = so.scan(scn["u"][s], z, R)
+        assert np.array_equal(j, jo), "step %d: %s vs %s" % (s, j, jo)
+        assert rel(pose, so.pose) < TOL or np.abs(pose - so.pose).max() < 1e-12
+        assert rc == st
+        saw_capacity |= (rc == EKF_ECAPACITY)
+        saw_reset |= (so.lines < L_before)
+        if s in (3, 6, steps - 1):
+            compare_state(f, so, "step %d" % s)
+    assert saw_reset, "the scenario must drive the map through a reset"
+    assert f.state()[1] == so.lines
+
+
+def test_overlapped_pipeline_with_ragged_scans(libekf, oracle_cls):
+    """Scans of 8, 0, 3, 16, 40, 1, 32, 8, 33, 2 lines on a map large enough for the overlapped path: empty scans,
+    group sizes that select the 8- / 16- / 32-term sweep, and scans above 32 lines that drain the pipeline and run
+    synchronously, back to back."""
+    N = 3100
+    ms = [8, 0, 3, 16, 40, 1, 32, 8, 33, 2]
+    scn = sc.map_scenario(N, len(ms), m=40, seed=77, stride=43)
+    f, so = seed_pair(N, N + 64, oracle_cls, scn)
+    so._lib.ekfo_set_threads(so._h, 0)
+    for s, m in enumerate(ms):
+        z, R = scn["z"][s, :m], scn["R"][s, :m]
+        rc, j, pose = f.scan(scn["u"][s], z, R)
+        st, jo = so.scan(scn["u"][s], z, R)
+        assert rc == st and np.array_equal(j, jo), "step %d (m = %d)" % (s, m)
+        assert rel(pose, so.pose) < TOL or np.abs(pose - so.pose).max() < 1e-12
+        if s in (4, 7, len(ms) - 1):
+            compare_state(f, so, "step %d" % s)
