@@ -456,7 +456,14 @@ int enable_overlap(ekf_ctx* ctx) {
       (ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS | EKF_FLAG_SWEEP_DIRECT | EKF_FLAG_NO_OVERLAP)))
     return EKF_OK;
   const size_t bytes = (size_t)ekf_local_tile_rows(ctx->g) * EKF_TILE * (size_t)ctx->g.ld * sizeof(double);
-  CU(cudaMalloc(&ctx->Pbuf[1], bytes));
+  if (cudaMalloc(&ctx->Pbuf[1], bytes) != cudaSuccess) {
+    /* no room for the second covariance buffer (e.g. a 40k-landmark filter on too few GPUs): stay on the in-place,
+     * non-overlapped path -- slower, same results */
+    (void)cudaGetLastError();
+    ctx->Pbuf[1] = 0;
+    snprintf(ctx->err, sizeof ctx->err, "no memory for the second covariance buffer (%.1f GB): sweeps will not overlap", bytes / 1e9);
+    return EKF_OK;
+  }
   CU(cudaMemsetAsync(ctx->Pbuf[1], 0, bytes, ctx->stream));
   CU(cudaStreamCreateWithFlags(&ctx->wstream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&ctx->evE, cudaEventDisableTiming));
