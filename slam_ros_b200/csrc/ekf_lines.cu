@@ -61,6 +61,25 @@ __device__ __forceinline__ double block_sum(double v, double* sbuf) {
   for (int w = 0; w < THREADS / 32; ++w) t += sbuf[w];
   return t;
 }
+/* N sums in ONE pass (one pair of barriers instead of N): v[] in, totals out in v[]; sbuf holds N * THREADS/32 doubles */
+template <int THREADS, int N>
+__device__ __forceinline__ void block_sum_n(double (&v)[N], double* sbuf) {
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) sbuf[k * (THREADS / 32) + (threadIdx.x >> 5)] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double t = 0.0;
+    for (int w = 0; w < THREADS / 32; ++w) t += sbuf[k * (THREADS / 32) + w];
+    v[k] = t;
+  }
+}
 template <int THREADS>
 __device__ __forceinline__ int block_sum_int(int v, int* sbuf) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -215,7 +234,7 @@ __device__ void lx_end_point(const double* a, const double* r, int n, const LxFi
 __global__ void __launch_bounds__(LX_SEG_THREADS) k_lx_segments(LxBuffers b) {
   __shared__ double s_a[LX_MAX_POINTS], s_r[LX_MAX_POINTS], s_X[LX_MAX_POINTS], s_Y[LX_MAX_POINTS];
   __shared__ int s_stack[2 * LX_MAX_POINTS];
-  __shared__ double s_red[LX_SEG_THREADS / 32];
+  __shared__ double s_red[4 * (LX_SEG_THREADS / 32)];
   __shared__ double s_best[LX_SEG_THREADS / 32];
   __shared__ int s_besti[LX_SEG_THREADS / 32];
   __shared__ LxFit s_fit;
@@ -242,17 +261,18 @@ __global__ void __launch_bounds__(LX_SEG_THREADS) k_lx_segments(LxBuffers b) {
       /* ---- fit, lineFitting.cpp:267-304 in closed form (see the header) ---- */
       double sx = 0.0, sy = 0.0;
       for (int i = lo + t; i < hi; i += LX_SEG_THREADS) { sx += s_X[i]; sy += s_Y[i]; }
-      const double SX = block_sum<LX_SEG_THREADS>(sx, s_red);
-      const double SY = block_sum<LX_SEG_THREADS>(sy, s_red);
+      double r2[2] = {sx, sy};
+      block_sum_n<LX_SEG_THREADS, 2>(r2, s_red);
+      const double SX = r2[0], SY = r2[1];
       const double mx = SX / n, my = SY / n;
       double qxy = 0.0, qxx = 0.0, qyy = 0.0;
       for (int i = lo + t; i < hi; i += LX_SEG_THREADS) {
         const double dx = s_X[i] - mx, dy = s_Y[i] - my;
         qxy += dx * dy; qxx += dx * dx; qyy += dy * dy;
       }
-      const double Sxy = block_sum<LX_SEG_THREADS>(qxy, s_red);
-      const double Sxx = block_sum<LX_SEG_THREADS>(qxx, s_red);
-      const double Syy = block_sum<LX_SEG_THREADS>(qyy, s_red);
+      double r3[3] = {qxy, qxx, qyy};
+      block_sum_n<LX_SEG_THREADS, 3>(r3, s_red);
+      const double Sxy = r3[0], Sxx = r3[1], Syy = r3[2];
       if (t == 0) {
         const double alfa_raw = 0.5 * atan2(-2.0 * Sxy, -(Sxx - Syy));
         const double sum_r = cos(alfa_raw) * SX + sin(alfa_raw) * SY;
@@ -283,9 +303,9 @@ __global__ void __launch_bounds__(LX_SEG_THREADS) k_lx_segments(LxBuffers b) {
           if (dist > best) { best = dist; besti = i; }                 /* ascending i per thread: first maximum kept */
         }
       }
-      const double sum_di = block_sum<LX_SEG_THREADS>(q_di, s_red);
-      const double sum_var = sqrt(block_sum<LX_SEG_THREADS>(q_var, s_red));
-      const double tres = block_sum<LX_SEG_THREADS>(q_t, s_red);
+      double r4[3] = {q_di, q_var, q_t};
+      block_sum_n<LX_SEG_THREADS, 3>(r4, s_red);
+      const double sum_di = r4[0], sum_var = sqrt(r4[1]), tres = r4[2];
       /* arg max with the reference's tie rule (strict >, ascending index): larger distance, then smaller index */
       for (int o = 16; o > 0; o >>= 1) {
         const double ob = __shfl_down_sync(0xffffffffu, best, o);
@@ -341,8 +361,9 @@ __global__ void __launch_bounds__(LX_SEG_THREADS) k_lx_segments(LxBuffers b) {
         q0 += (F0 * cxv) * F0;                                         /* (F C_x) F^T, diagonal C_x (:443-444) */
         q3 += (F1 * cxv) * F1;
       }
-      const double C0 = block_sum<LX_SEG_THREADS>(q0, s_red);
-      const double C3 = block_sum<LX_SEG_THREADS>(q3, s_red);
+      double r5[2] = {q0, q3};
+      block_sum_n<LX_SEG_THREADS, 2>(r5, s_red);
+      const double C0 = r5[0], C3 = r5[1];
       if (t == 0) {
         LxLeaf lf;
         lf.alfa = L.alfa; lf.r = L.r; lf.c0 = C0; lf.c3 = C3;
