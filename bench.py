@@ -163,7 +163,13 @@ def cpu_run(workload, steps, warmup, budget_s, threads=None):
             break
     dt = time.perf_counter() - t0
     val = done / dt
+    n = 3 + 2 * N
+    # the literal Robot::localize spends 7.1 ms in its dense n^3 prediction dgemms and 0.45 ms per
+    # matched line in n^2 passes at n = 203 (LINESIZE = 100, this container's host); scaled, NOT measured
+    lit_ms = 7.1 * (n / 203.0) ** 3 + m * 0.45 * (n / 203.0) ** 2
     info = {"kind": "port", "cores": so.threads, "value": val, "unit": "steps/s",
+            "literal_reference_extrapolated": "EXTRAPOLATED, not measured: the reference's own dense GSL path would need about "
+                                              "%.3g s per step at n = %d (2 n^3 MACs per prediction dgemm)" % (lit_ms / 1e3, n),
             "sample": "%d full steps (of %d requested) of the same workload on the structured oracle (oracle/ekf_oracle.cpp, "
                       "the runtime-capacity restatement of Robot::localize; OpenMP over the %d host threads for the n^2 "
                       "row sweeps; the literal reference is fixed at LINESIZE=100 and cannot run this size)" % (done, steps, so.threads)}
