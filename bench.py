@@ -8,7 +8,8 @@ observed lines against every map landmark, the matched updates (folded into one 
 sweep), augmentation.  Workloads (BASELINE.json `configs`):
 
     10k      configs[2]  single filter, 10 000 line landmarks (P 20003^2 fp64 = 3.2 GB), m = 8   [default]
-    1k       configs[1]  single filter, 1 000 landmarks (P fits L2: launch-bound, not HBM-bound)
+    1k       configs[1]  single filter, 1 000 landmarks (P fits L2: launch-bound, not HBM-bound); its CPU baseline /
+                         reference arm is the LITERAL reference compiled with LINESIZE = 1000 (oracle/_ref/libslamref1k.so)
     40k      configs[4]  single filter, 40 000 landmarks (51 GB); with --gpus N > 1 row-sharded over N ranks
     mc       configs[3]  Monte-Carlo batch, 4096 independent filters x 50 landmarks, sharded over ranks
     room     configs[0]  the reference-sized filter (LINESIZE=100) on the synthetic room; its CPU baseline /
@@ -166,7 +167,9 @@ def cpu_run(workload, steps, warmup, budget_s, threads=None):
     n = 3 + 2 * N
     # the literal Robot::localize spends 7.1 ms in its dense n^3 prediction dgemms and 0.45 ms per
     # matched line in n^2 passes at n = 203 (LINESIZE = 100, this container's host); scaled, NOT measured
-    lit_ms = 7.1 * (n / 203.0) ** 3 + m * 0.45 * (n / 203.0) ** 2
+    # + ~0.05 ms per (line, landmark) gate pair; check: the LINESIZE = 1000 build of the reference itself measures 12.7 s
+    # per step at n = 2003, m = 8 (bench.py --workload 1k), this formula gives 11.1 s
+    lit_ms = 7.1 * (n / 203.0) ** 3 + m * 0.45 * (n / 203.0) ** 2 + m * N * 0.05 * (n / 203.0)
     info = {"kind": "port", "cores": so.threads, "value": val, "unit": "steps/s",
             "literal_reference_extrapolated": "EXTRAPOLATED, not measured: the reference's own dense GSL path would need about "
                                               "%.3g s per step at n = %d (2 n^3 MACs per prediction dgemm)" % (lit_ms / 1e3, n),
@@ -174,6 +177,37 @@ def cpu_run(workload, steps, warmup, budget_s, threads=None):
                       "the runtime-capacity restatement of Robot::localize; OpenMP over the %d host threads for the n^2 "
                       "row sweeps; the literal reference is fixed at LINESIZE=100 and cannot run this size)" % (done, steps, so.threads)}
     return val, info
+
+
+def _have_literal_1k():
+    from oracle.oracle import have_literal_1k
+    return have_literal_1k()
+
+
+def literal_1k_run(steps, budget_s):
+    """configs[1] on the reference ITSELF: oracle/_ref/libslamref1k.so = slam_ros/Robot.cpp compiled with
+    LINESIZE = 1000 (the two size macros of Robot.h rewritten into a generated header), single thread.  980 landmarks
+    (its map resets above LINESIZE - 10); one call is ~12 s (dense n^3 prediction), so the sample is 1-2 steps."""
+    from oracle.oracle import LiteralReference
+    from slam_ros_b200 import scenario as sc
+    N, m = 980, 8
+    scn = sc.map_scenario(N, steps + 1, m=m, seed=1)
+    lit = LiteralReference(big=True)
+    zero = np.zeros(3)
+    lit.localize(scn["seed_z"], scn["seed_R"], sc.encoder_for(zero, zero))
+    t0 = time.perf_counter(); done = 0
+    for s in range(steps):
+        y, P, L, pose = lit.state()
+        lit.localize(scn["z"][s], scn["R"][s], sc.encoder_for(pose, scn["u"][s]))
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    val = done / dt
+    return val, {"kind": "reference", "cores": 1, "value": val, "unit": "steps/s",
+                 "sample": "%d Robot::localize calls of the literal reference compiled with LINESIZE=1000 (n = 2003; g++ -O2, GSL shim, "
+                           "cout disabled) on a 980-landmark map, m = 8 -- the structured oracle is bitwise equal to it at this size "
+                           "(tests/test_oracle.py)" % done}
 
 
 def literal_run(steps, warmup, budget_s):
@@ -324,7 +358,9 @@ def run_reference_arm(args, rank, world):
                           "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}), flush=True)
         return
-    if args.workload == "room":
+    if args.workload == "1k" and args.lines == 0 and _have_literal_1k():
+        val, info = literal_1k_run(min(args.steps, 8), budget_s=150.0)
+    elif args.workload == "room":
         val, info = literal_run(args.steps, args.warmup, budget_s=150.0)
         if val is None:
             print(json.dumps({"impl": "reference", "unavailable": info["unavailable"]}), flush=True)
@@ -586,6 +622,8 @@ def main():
                 val, info = lines_cpu_run(steps=200, budget_s=args.cpu_budget)
             elif args.workload == "room":
                 val, info = literal_run(steps=1000, warmup=3, budget_s=args.cpu_budget)
+            elif args.workload == "1k" and args.lines == 0 and _have_literal_1k():
+                val, info = literal_1k_run(steps=2, budget_s=args.cpu_budget)
             else:
                 val, info = cpu_run(args.workload, steps=1000, warmup=1, budget_s=args.cpu_budget)
             line["cpu_baseline"] = info

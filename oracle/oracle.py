@@ -179,15 +179,26 @@ class StructuredOracle:
         return bool(ok), (float(ax[0]), float(ax[1])), float(ang.value)
 
 
-class LiteralReference:
-    """The reference's own Robot (LINESIZE = 100), driven through oracle/ref_harness.cpp."""
+_REF1K_SO = os.path.join(_HERE, "_ref", "libslamref1k.so")
 
-    def __init__(self):
-        if not os.path.exists(_REF_SO):
+
+def have_literal_1k():
+    return os.path.exists(_REF1K_SO)
+
+
+class LiteralReference:
+    """The reference's own Robot, driven through oracle/ref_harness.cpp.  big=False: LINESIZE = 100 as shipped
+    (Robot.h:13); big=True: the same sources with LINESIZE = 1000 / SLAMSIZE = 2003 (oracle/_ref/libslamref1k.so,
+    BASELINE configs[1]) -- its localize needs ~300 MB of stack and runs on a dedicated thread."""
+
+    def __init__(self, big=False):
+        so = _REF1K_SO if big else _REF_SO
+        self._big = bool(big)
+        if not os.path.exists(so):
             build()
-        if not os.path.exists(_REF_SO):
-            raise FileNotFoundError(_REF_SO + " (needs /root/reference to build)")
-        L = self._lib = C.CDLL(_REF_SO)
+        if not os.path.exists(so):
+            raise FileNotFoundError(so + " (needs /root/reference to build)")
+        L = self._lib = C.CDLL(so)
         L.ref_create.restype = C.c_void_p
         L.ref_gate.restype = C.c_double
         L.ref_encoder_noise.restype = C.c_double
@@ -210,7 +221,12 @@ class LiteralReference:
         ea, ep = _d(encoder)
         z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 4)
-        self._lib.ref_localize(self._h, C.c_int(z.shape[0]), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp), ep)
+        if self._big:
+            rc = self._lib.ref_localize_bigstack(self._h, C.c_int(z.shape[0]), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp), ep, C.c_int(1024))
+            if rc != 0:
+                raise RuntimeError("ref_localize_bigstack failed: %d" % rc)
+        else:
+            self._lib.ref_localize(self._h, C.c_int(z.shape[0]), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp), ep)
 
     def state(self):
         y = np.zeros(self.n); P = np.zeros((self.n, self.n)); L = C.c_int(0); pose = np.zeros(3)

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <random>
+#include <pthread.h>
 #define private public
 #include "Robot.h"
 #undef private
@@ -58,6 +59,22 @@ int ref_localize(void* h, int m, const double* z, const double* R, const double*
   for (int i = 0; i < m; ++i) gsl_matrix_free(lines[i].C_AR);
   rb->lineIntervals.data.clear();
   return 0;
+}
+/* The same call on a thread with a stack of `stack_mb` MB: Robot::localize keeps ~8 SLAMSIZE^2 arrays of doubles on
+ * the stack (Robot.cpp:153, 204, 210, 226, 344, 558), 330 KB each at LINESIZE = 100 but 32 MB each in the
+ * LINESIZE = 1000 build (oracle/_ref/libslamref1k.so). */
+struct BigCall { void* h; int m; const double* z; const double* R; const double* enc; int rc; };
+static void* big_call_main(void* p) { BigCall* c = (BigCall*)p; c->rc = ref_localize(c->h, c->m, c->z, c->R, c->enc); return 0; }
+int ref_localize_bigstack(void* h, int m, const double* z, const double* R, const double* encoder, int stack_mb) {
+  BigCall c = {h, m, z, R, encoder, -1};
+  pthread_attr_t attr;
+  if (pthread_attr_init(&attr) != 0) return -1;
+  if (pthread_attr_setstacksize(&attr, (size_t)stack_mb << 20) != 0) return -2;
+  pthread_t th;
+  if (pthread_create(&th, &attr, big_call_main, &c) != 0) return -3;
+  pthread_join(th, 0);
+  pthread_attr_destroy(&attr);
+  return c.rc;
 }
 void ref_get(void* h, double* y, double* P, int* L, double* pose) {
   Robot* rb = (Robot*)h;

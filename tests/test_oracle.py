@@ -189,3 +189,28 @@ def test_motion_model_quiz():
     # (Robot.cpp:148), so u[2] = pi/4 reproduces the quiz's x and y; theta advances by the full u[2]
     assert np.allclose(x[:2], [1.038268343236509, 2.0923879532511287], atol=1e-15)
     assert abs(x[2] - np.pi / 2) < 1e-15
+
+
+def test_structured_oracle_is_bitwise_the_reference_at_linesize_1000():
+    """BASELINE configs[1] size: the reference's own Robot.cpp compiled with LINESIZE = 1000 / SLAMSIZE = 2003
+    (oracle/_ref/libslamref1k.so: the two macros rewritten into a generated header, nothing else touched) against
+    the structured oracle at capacity 1000 -- state and the full 2003 x 2003 covariance bit for bit after a
+    300-line seeding scan and an update scan.  (~12 s per reference call: its prediction is a dense n^3 dgemm.)"""
+    from oracle.oracle import LiteralReference, StructuredOracle, have_literal_1k
+    if not have_literal_1k():
+        pytest.skip("literal reference at LINESIZE=1000 not built (no /root/reference)")
+    lit = LiteralReference(big=True)
+    assert lit.capacity == 1000 and lit.n == 2003
+    so = StructuredOracle(1000)
+    scn = sc.map_scenario(300, 1, m=8, seed=3)
+    zero = np.zeros(3)
+    lit.localize(scn["seed_z"], scn["seed_R"], sc.encoder_for(zero, zero))
+    so.localize(scn["seed_z"], scn["seed_R"], sc.encoder_for(zero, zero))
+    y, P, L, pose = lit.state()
+    assert L == so.lines == 300
+    lit.localize(scn["z"][0], scn["R"][0], sc.encoder_for(pose, scn["u"][0]))
+    st, j = so.localize(scn["z"][0], scn["R"][0], sc.encoder_for(so.pose, scn["u"][0]))
+    y, P, L, pose = lit.state()
+    assert (j >= 0).sum() >= 6
+    assert L == so.lines and np.array_equal(y, so.y_full()) and np.array_equal(P, so.P_full())
+    assert np.array_equal(pose, so.pose)
