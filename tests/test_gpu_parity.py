@@ -556,3 +556,35 @@ def test_overlapped_pipeline_with_ragged_scans(libekf, oracle_cls):
         assert rel(pose, so.pose) < TOL or np.abs(pose - so.pose).max() < 1e-12
         if s in (4, 7, len(ms) - 1):
             compare_state(f, so, "step %d" % s)
+
+
+def test_against_golden_vectors_of_the_reference_at_linesize_1000(libekf):
+    """tests/golden/literal_1k.npz was produced by the reference's OWN Robot.cpp compiled with LINESIZE = 1000
+    (BASELINE configs[1] size; make_golden_1k.py).  libekfcuda, fed the same inputs through the Robot mirror's
+    arithmetic (pose - encoder odometry), must land on its state and covariance within 1e-9 -- no oracle involved."""
+    from slam_ros_b200 import EkfFilter
+    g = np.load(os.path.join(ROOT, "tests", "golden", "literal_1k.npz"))
+    f = EkfFilter(capacity_lines=1000)
+    pose = np.zeros(3)
+
+    def step(z, R, enc):
+        nonlocal pose
+        dX, dY = pose[0] - enc[0], pose[1] - enc[1]
+        u = (np.sqrt(dX * dX + dY * dY), 0.0, pose[2] - enc[2])          # Robot.cpp:141-144 (Q5)
+        rc, j, pose = f.scan(u, z, R, x_t0=pose)
+        assert rc == 0
+        return j
+
+    step(g["seed_z"], g["seed_R"], sc.encoder_for(np.zeros(3), np.zeros(3)))
+    for s in range(g["u"].shape[0]):
+        j = step(g["z"][s], g["R"][s], g["encoder"][s])
+        assert (j >= 0).sum() >= 6
+        assert np.abs(pose - g["pose"][s]).max() < 1e-9
+    L = int(g["L"][0]); nl = 3 + 2 * L
+    y, P, Lg = f.download_live()
+    pmax = float(g["pmax"][0])
+    assert Lg == L and rel(y, g["y"]) < TOL
+    assert np.abs(np.diag(P) - g["diag"]).max() / pmax < TOL and np.abs(P[:3] - g["top"]).max() / pmax < TOL
+    assert np.abs(P.sum(axis=1) - g["rowsum"]).max() / (pmax * nl) < TOL
+    for (r, c), blk in zip(g["corners"], g["blocks"]):
+        assert np.abs(P[r:r + blk.shape[0], c:c + blk.shape[1]] - blk).max() / pmax < TOL

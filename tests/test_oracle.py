@@ -214,3 +214,24 @@ def test_structured_oracle_is_bitwise_the_reference_at_linesize_1000():
     assert (j >= 0).sum() >= 6
     assert L == so.lines and np.array_equal(y, so.y_full()) and np.array_equal(P, so.P_full())
     assert np.array_equal(pose, so.pose)
+
+
+def test_structured_oracle_against_golden_vectors_of_the_1k_reference():
+    """tests/golden/literal_1k.npz: produced by the reference's own Robot.cpp at LINESIZE = 1000 (make_golden_1k.py).
+    Travels to machines without /root/reference: the structured oracle must reproduce it bit for bit."""
+    import os
+    from oracle.oracle import StructuredOracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "literal_1k.npz"))
+    so = StructuredOracle(1000)
+    zero = np.zeros(3)
+    so.localize(g["seed_z"], g["seed_R"], sc.encoder_for(zero, zero))
+    for s in range(g["u"].shape[0]):
+        so.localize(g["z"][s], g["R"][s], g["encoder"][s])
+        assert np.array_equal(so.pose, g["pose"][s])
+    L = int(g["L"][0]); nl = 3 + 2 * L
+    assert so.lines == L
+    P = so.P_full()
+    assert np.array_equal(so.y_full()[:nl], g["y"])
+    assert np.array_equal(np.diag(P)[:nl], g["diag"]) and np.array_equal(P[:3, :nl], g["top"])
+    for (r, c), blk in zip(g["corners"], g["blocks"]):
+        assert np.array_equal(P[r:r + blk.shape[0], c:c + blk.shape[1]], blk)
