@@ -201,7 +201,7 @@ const char* ekf_batch_last_error(const ekf_batch* b);
  * difference covariance, end points, LineConversion), then alfa += pi (main.cpp:66-69).  Output per line, in the
  * reference's order: 10 doubles = alfa, r, C_AR[4] (row-major, off-diagonals 0), lineInterval[0] (alfa, r),
  * lineInterval[1] (alfa, r) -- i.e. the `line` fields Robot::localize reads (simplifyPath.h:62-79).
- * At most 1024 points per payload.  *n_lines may exceed max_lines (then only max_lines were written). */
+ * At most 4096 points per payload.  *n_lines may exceed max_lines (then only max_lines were written). */
 typedef struct ekf_lx ekf_lx;
 int ekf_lx_create(ekf_lx** out, int device, int max_lines);
 int ekf_lx_destroy(ekf_lx* lx);

@@ -27,7 +27,9 @@
 #include <stdio.h>
 #include <string.h>
 
-#define LX_MAX_POINTS 1024
+#define LX_MAX_POINTS 4096            /* returns per payload (a 0.09-degree scanner) */
+#define LX_PREP_THREADS 1024
+#define LX_ITEMS (LX_MAX_POINTS / LX_PREP_THREADS)
 #define LX_SEG_THREADS 128
 #define LX_PI 3.14159265
 #define LX_MPI 3.14159265358979323846
@@ -104,87 +106,131 @@ __device__ __forceinline__ int block_scan_flags(int flag, int* sbuf, int* total)
   return base + __popc(m & ((1u << lane) - 1u));
 }
 
+__host__ __device__ __forceinline__ int lx_npad(int n_pairs) {
+  int npad = LX_PREP_THREADS;
+  while (npad < n_pairs && npad < LX_MAX_POINTS) npad <<= 1;
+  return npad;
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* main.cpp:46-62 (polar points), lineFitting.cpp:642 (sort by alfa + PI), :541-584 (segmentation),
  * :645-649 (rotate so that the scan starts at a break, segment again). */
-__global__ void __launch_bounds__(LX_MAX_POINTS) k_lx_prepare(LxBuffers b, int n_pairs) {
-  __shared__ double s_key[LX_MAX_POINTS];
-  __shared__ double s_a[LX_MAX_POINTS], s_r[LX_MAX_POINTS];
-  __shared__ int s_idx[LX_MAX_POINTS];
-  __shared__ int s_flag[LX_MAX_POINTS];
+__global__ void __launch_bounds__(LX_PREP_THREADS) k_lx_prepare(LxBuffers b, int n_pairs) {
+  extern __shared__ unsigned char lx_raw[];
+  double* s_key = reinterpret_cast<double*>(lx_raw);                    /* [LX_MAX_POINTS] each */
+  double* s_a = s_key + LX_MAX_POINTS;
+  double* s_r = s_a + LX_MAX_POINTS;
+  int* s_idx = reinterpret_cast<int*>(s_r + LX_MAX_POINTS);
+  int* s_flag = s_idx + LX_MAX_POINTS;
   __shared__ int s_red[32];
   __shared__ int s_misc[4];
   const int t = threadIdx.x;
-  /* polar points with a return */
-  float rr = 0.f, ang = 0.f;
-  int keep = 0;
-  if (t < n_pairs) { rr = b.data[2 * t]; ang = b.data[2 * t + 1]; keep = ((double)rr > 0.05) ? 1 : 0; }
+  /* work on the smallest power-of-two window that holds the payload: a 361-beam scan costs what it did with a
+   * 1024-point limit */
+  const int npad = lx_npad(n_pairs), items = npad / LX_PREP_THREADS;
+  /* polar points with a return; order-preserving compaction, one 1024-point chunk at a time */
   int np = 0;
-  const int pos = block_scan_flags<LX_MAX_POINTS>(keep, s_red, &np);
-  s_key[t] = INFINITY; s_idx[t] = t;
+  for (int c = 0; c < items; ++c) {
+    const int i = c * LX_PREP_THREADS + t;
+    float rr = 0.f, ang = 0.f;
+    int keep = 0;
+    if (i < n_pairs) { rr = b.data[2 * i]; ang = b.data[2 * i + 1]; keep = ((double)rr > 0.05) ? 1 : 0; }
+    int cnt = 0;
+    const int pos = np + block_scan_flags<LX_PREP_THREADS>(keep, s_red, &cnt);
+    if (keep) { s_a[pos] = (double)ang - LX_MPI; s_r[pos] = (double)rr; }
+    np += cnt;
+  }
   __syncthreads();
-  if (keep) { s_a[pos] = (double)ang - LX_MPI; s_r[pos] = (double)rr; }
-  __syncthreads();
-  if (t < np) s_key[t] = s_a[t] + LX_PI;
+  for (int i = t; i < npad; i += LX_PREP_THREADS) { s_key[i] = (i < np) ? s_a[i] + LX_PI : INFINITY; s_idx[i] = i; }
   __syncthreads();
   /* already sorted (the usual case for a rotating scanner)? */
-  const int inv = (t + 1 < np && s_key[t + 1] < s_key[t]) ? 1 : 0;
-  const int ninv = block_sum_int<LX_MAX_POINTS>(inv, s_red);
+  int inv = 0;
+  for (int i = t; i + 1 < np; i += LX_PREP_THREADS) inv += (s_key[i + 1] < s_key[i]) ? 1 : 0;
+  const int ninv = block_sum_int<LX_PREP_THREADS>(inv, s_red);
   if (ninv > 0) {
     /* bitonic sort of (key, original index): the index breaks ties, i.e. the sort is stable */
-    for (int k = 2; k <= LX_MAX_POINTS; k <<= 1)
+    for (int k = 2; k <= npad; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
-        const int ixj = t ^ j;
-        if (ixj > t) {
-          const bool up = (t & k) == 0;
-          const double ka = s_key[t], kb = s_key[ixj];
-          const int ia = s_idx[t], ib = s_idx[ixj];
-          const bool a_after_b = (ka > kb) || (ka == kb && ia > ib);
-          if (a_after_b == up) { s_key[t] = kb; s_key[ixj] = ka; s_idx[t] = ib; s_idx[ixj] = ia; }
+        for (int i = t; i < npad; i += LX_PREP_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const bool up = (i & k) == 0;
+            const double ka = s_key[i], kb = s_key[ixj];
+            const int ia = s_idx[i], ib = s_idx[ixj];
+            const bool a_after_b = (ka > kb) || (ka == kb && ia > ib);
+            if (a_after_b == up) { s_key[i] = kb; s_key[ixj] = ka; s_idx[i] = ib; s_idx[ixj] = ia; }
+          }
         }
         __syncthreads();
       }
-    double na = 0.0, nr = 0.0;
-    if (t < np) { na = s_a[s_idx[t]]; nr = s_r[s_idx[t]]; }
+    double na[LX_ITEMS], nr[LX_ITEMS];
+#pragma unroll
+    for (int c = 0; c < LX_ITEMS; ++c) {
+      const int i = c * LX_PREP_THREADS + t;
+      na[c] = 0.0; nr[c] = 0.0;
+      if (c < items && i < np) { na[c] = s_a[s_idx[i]]; nr[c] = s_r[s_idx[i]]; }
+    }
     __syncthreads();
-    if (t < np) { s_a[t] = na; s_r[t] = nr; }
+#pragma unroll
+    for (int c = 0; c < LX_ITEMS; ++c) {
+      const int i = c * LX_PREP_THREADS + t;
+      if (i < np) { s_a[i] = na[c]; s_r[i] = nr[c]; }
+    }
     __syncthreads();
   }
   /* segmentation: split between neighbours more than 0.5 m apart */
   for (int pass = 0; pass < 2; ++pass) {
-    int f = 0;
-    if (t >= 1 && t < np) {
-      const double r0 = s_r[t - 1], r1 = s_r[t];
-      const double dist = sqrt(r0 * r0 + r1 * r1 - 2 * r0 * r1 * cos(s_a[t] - s_a[t - 1]));
-      f = (dist > 0.5) ? 1 : 0;
-    }
-    s_flag[t] = f;
     if (t == 0) s_misc[0] = 0;
     __syncthreads();
-    if (pass == 1) break;
-    if (f) atomicMax(&s_misc[0], t);                                   /* split.back() */
+    for (int i = t; i < npad; i += LX_PREP_THREADS) {
+      int f = 0;
+      if (i >= 1 && i < np) {
+        const double r0 = s_r[i - 1], r1 = s_r[i];
+        const double dist = sqrt(r0 * r0 + r1 * r1 - 2 * r0 * r1 * cos(s_a[i] - s_a[i - 1]));
+        f = (dist > 0.5) ? 1 : 0;
+      }
+      s_flag[i] = f;
+      if (f && pass == 0) atomicMax(&s_misc[0], i);                    /* split.back() */
+    }
     __syncthreads();
+    if (pass == 1) break;
     const int last = s_misc[0];
     if (last == 0) break;                                              /* no break in the scan: one segment, no rotation */
-    double na = 0.0, nr = 0.0;
-    if (t < np) { const int src = (t + last) % np; na = s_a[src]; nr = s_r[src]; }
+    double na[LX_ITEMS], nr[LX_ITEMS];
+#pragma unroll
+    for (int c = 0; c < LX_ITEMS; ++c) {
+      const int i = c * LX_PREP_THREADS + t;
+      na[c] = 0.0; nr[c] = 0.0;
+      if (c < items && i < np) { const int src = (i + last) % np; na[c] = s_a[src]; nr[c] = s_r[src]; }
+    }
     __syncthreads();
-    if (t < np) { s_a[t] = na; s_r[t] = nr; }
+#pragma unroll
+    for (int c = 0; c < LX_ITEMS; ++c) {
+      const int i = c * LX_PREP_THREADS + t;
+      if (i < np) { s_a[i] = na[c]; s_r[i] = nr[c]; }
+    }
     __syncthreads();
   }
   /* segment table and point arrays */
-  const int is_start = (t < np) && (t == 0 || s_flag[t]);
   int nseg = 0;
-  const int spos = block_scan_flags<LX_MAX_POINTS>(is_start, s_red, &nseg);
-  if (is_start) b.seg[1 + spos] = t;
-  if (t == 0) { b.seg[0] = (np >= 2) ? nseg : 0; b.seg[1 + nseg] = np; *b.count = 0; }
-  if (t < np) {
-    const double a = s_a[t], r = s_r[t];
-    const double c = cos(a), s = sin(a);
-    b.a[t] = a; b.r[t] = r; b.ca[t] = c; b.sa[t] = s;
-    b.X[t] = c * r; b.Y[t] = s * r;                                     /* polar2descart, lineFitting.cpp:157-168 */
+  for (int c = 0; c < items; ++c) {
+    const int i = c * LX_PREP_THREADS + t;
+    const int is_start = (i < np) && (i == 0 || s_flag[i]);
+    int cnt = 0;
+    const int spos = nseg + block_scan_flags<LX_PREP_THREADS>(is_start, s_red, &cnt);
+    if (is_start) b.seg[1 + spos] = i;
+    nseg += cnt;
   }
-  b.leaf[t].valid = 0;
+  if (t == 0) { b.seg[0] = (np >= 2) ? nseg : 0; b.seg[1 + nseg] = np; *b.count = 0; }
+  for (int i = t; i < npad; i += LX_PREP_THREADS) {
+    if (i < np) {
+      const double a = s_a[i], r = s_r[i];
+      const double c = cos(a), sn = sin(a);
+      b.a[i] = a; b.r[i] = r; b.ca[i] = c; b.sa[i] = sn;
+      b.X[i] = c * r; b.Y[i] = sn * r;                                  /* polar2descart, lineFitting.cpp:157-168 */
+    }
+    b.leaf[i].valid = 0;
+  }
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -232,8 +278,12 @@ __device__ void lx_end_point(const double* a, const double* r, int n, const LxFi
 
 /* One thread block per segment: simplifyPath::simplifyWithRDP (simplifyPath.cpp:108-177) with an explicit stack. */
 __global__ void __launch_bounds__(LX_SEG_THREADS) k_lx_segments(LxBuffers b) {
-  __shared__ double s_a[LX_MAX_POINTS], s_r[LX_MAX_POINTS], s_X[LX_MAX_POINTS], s_Y[LX_MAX_POINTS];
-  __shared__ int s_stack[2 * LX_MAX_POINTS];
+  extern __shared__ unsigned char lx_raw[];
+  double* s_a = reinterpret_cast<double*>(lx_raw);                      /* [LX_MAX_POINTS] each: a segment may hold every point */
+  double* s_r = s_a + LX_MAX_POINTS;
+  double* s_X = s_r + LX_MAX_POINTS;
+  double* s_Y = s_X + LX_MAX_POINTS;
+  int* s_stack = reinterpret_cast<int*>(s_Y + LX_MAX_POINTS);          /* [2 * LX_MAX_POINTS] */
   __shared__ double s_red[4 * (LX_SEG_THREADS / 32)];
   __shared__ double s_best[LX_SEG_THREADS / 32];
   __shared__ int s_besti[LX_SEG_THREADS / 32];
@@ -383,30 +433,35 @@ __global__ void __launch_bounds__(LX_SEG_THREADS) k_lx_segments(LxBuffers b) {
 }
 
 /* LineConversion (lineFitting.cpp:586-638) + main.cpp:66-69, compacted in leaf (= reference) order. */
-__global__ void __launch_bounds__(LX_MAX_POINTS) k_lx_finish(LxBuffers b, int max_lines) {
+__global__ void __launch_bounds__(LX_PREP_THREADS) k_lx_finish(LxBuffers b, int max_lines, int n_pairs) {
   __shared__ int s_red[32];
   const int t = threadIdx.x;
-  LxLeaf lf = b.leaf[t];
-  int keep = 0;
-  if (lf.valid) {
-    keep = 1;
-    if (lf.c0 < 0 || lf.c3 < 0) keep = 0;
-    else if (isnan(lf.c0) || isnan(lf.c3)) keep = 0;
-    else if (lf.alfa == 0 && lf.r == 0) keep = 0;
-    else if (lf.c0 > 0.01) keep = 0;
-  }
+  const int items = lx_npad(n_pairs) / LX_PREP_THREADS;
   int total = 0;
-  const int pos = block_scan_flags<LX_MAX_POINTS>(keep, s_red, &total);
-  if (keep && pos < max_lines) {
-    double alfa = lf.alfa, r = lf.r;
-    lx_canonical(alfa, r);
-    alfa += LX_MPI;                                                    /* main.cpp:67-68 */
-    alfa = alfa > LX_MPI ? alfa - 2.0 * LX_MPI : alfa;
-    double* o = b.out + 10 * pos;
-    o[0] = alfa; o[1] = r; o[2] = lf.c0; o[3] = 0.0; o[4] = 0.0; o[5] = lf.c3;
-    o[6] = lf.ia0; o[7] = lf.ir0; o[8] = lf.ia1; o[9] = lf.ir1;
-    b.z[2 * pos] = alfa; b.z[2 * pos + 1] = r;
-    b.R[4 * pos] = lf.c0; b.R[4 * pos + 1] = 0.0; b.R[4 * pos + 2] = 0.0; b.R[4 * pos + 3] = lf.c3;
+  for (int c = 0; c < items; ++c) {
+    const LxLeaf lf = b.leaf[c * LX_PREP_THREADS + t];
+    int keep = 0;
+    if (lf.valid) {
+      keep = 1;
+      if (lf.c0 < 0 || lf.c3 < 0) keep = 0;
+      else if (isnan(lf.c0) || isnan(lf.c3)) keep = 0;
+      else if (lf.alfa == 0 && lf.r == 0) keep = 0;
+      else if (lf.c0 > 0.01) keep = 0;
+    }
+    int cnt = 0;
+    const int pos = total + block_scan_flags<LX_PREP_THREADS>(keep, s_red, &cnt);
+    total += cnt;
+    if (keep && pos < max_lines) {
+      double alfa = lf.alfa, r = lf.r;
+      lx_canonical(alfa, r);
+      alfa += LX_MPI;                                                  /* main.cpp:67-68 */
+      alfa = alfa > LX_MPI ? alfa - 2.0 * LX_MPI : alfa;
+      double* o = b.out + 10 * pos;
+      o[0] = alfa; o[1] = r; o[2] = lf.c0; o[3] = 0.0; o[4] = 0.0; o[5] = lf.c3;
+      o[6] = lf.ia0; o[7] = lf.ir0; o[8] = lf.ia1; o[9] = lf.ir1;
+      b.z[2 * pos] = alfa; b.z[2 * pos + 1] = r;
+      b.R[4 * pos] = lf.c0; b.R[4 * pos + 1] = 0.0; b.R[4 * pos + 2] = 0.0; b.R[4 * pos + 3] = lf.c3;
+    }
   }
   if (t == 0) *b.count = total;
 }
@@ -414,6 +469,9 @@ __global__ void __launch_bounds__(LX_MAX_POINTS) k_lx_finish(LxBuffers b, int ma
 }  // namespace
 
 /* ------------------------------------------------------------------------------------------------ */
+static const size_t kPrepSmem = (size_t)LX_MAX_POINTS * (3 * sizeof(double) + 2 * sizeof(int));   /* 128 KB */
+static const size_t kSegSmem = (size_t)LX_MAX_POINTS * (4 * sizeof(double) + 2 * sizeof(int));    /* 160 KB */
+
 struct ekf_lx {
   int device, max_lines;
   cudaStream_t stream;
@@ -463,6 +521,8 @@ int ekf_lx_create(ekf_lx** out, int device, int max_lines) {
   LXCU(cudaMallocHost(&lx->h_out, 10 * (size_t)max_lines * sizeof(double)));
   LXCU(cudaMallocHost(&lx->h_count, sizeof(int)));
   lx->b.data = lx->d_data;
+  LXCU(cudaFuncSetAttribute(k_lx_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmem));
+  LXCU(cudaFuncSetAttribute(k_lx_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegSmem));
   LXCU(cudaStreamSynchronize(lx->stream));
   return EKF_OK;
 }
@@ -484,11 +544,11 @@ const char* ekf_lx_last_error(const ekf_lx* lx) { return lx ? lx->err : "null ek
 static int lx_enqueue(ekf_lx* lx, const float* d_data, int n_pairs) {
   LxBuffers b = lx->b;
   b.data = d_data;
-  k_lx_prepare<<<1, LX_MAX_POINTS, 0, lx->stream>>>(b, n_pairs);
+  k_lx_prepare<<<1, LX_PREP_THREADS, kPrepSmem, lx->stream>>>(b, n_pairs);
   LXCU(cudaGetLastError());
-  k_lx_segments<<<148, LX_SEG_THREADS, 0, lx->stream>>>(b);
+  k_lx_segments<<<148, LX_SEG_THREADS, kSegSmem, lx->stream>>>(b);
   LXCU(cudaGetLastError());
-  k_lx_finish<<<1, LX_MAX_POINTS, 0, lx->stream>>>(b, lx->max_lines);
+  k_lx_finish<<<1, LX_PREP_THREADS, 0, lx->stream>>>(b, lx->max_lines, n_pairs);
   LXCU(cudaGetLastError());
   lx->launches += 3;
   return EKF_OK;

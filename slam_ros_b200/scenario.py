@@ -183,11 +183,12 @@ def room_scenario(steps=1000, seed=7, beams=361, range_sigma=1e-3, max_range=10.
     return {"u": u, "z": z, "R": R, "count": cnt, "poses": poses, "seed": seed, "walls": walls}
 
 
-def room_scan(pose, beams=361, range_sigma=1e-3, max_range=10.0, rng=None):
+def room_scan(pose, beams=361, range_sigma=1e-3, max_range=10.0, rng=None, step_deg=1.0):
     """One `mappingPoints` payload as the node receives it (slam_ros/main.cpp:37-56): float32 pairs (r, angle),
-    angle in [0, 2 pi] at 1 degree steps (the reference subtracts pi), r = 0 for beams without a return."""
+    angle in [0, 2 pi] at `step_deg` steps (1 degree in the reference's simulator; the reference subtracts pi),
+    r = 0 for beams without a return."""
     walls = room_walls()
-    angles = np.deg2rad(np.arange(beams, dtype=np.float64))
+    angles = np.deg2rad(np.arange(beams, dtype=np.float64) * step_deg)
     rng_, wall, hit = _raycast(walls, pose, angles - math.pi, max_range)
     rr = np.where(hit, rng_, 0.0)
     if rng is not None and range_sigma > 0:

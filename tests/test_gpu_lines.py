@@ -112,3 +112,26 @@ def test_messy_payloads(libekf):
             p = p[::rng.integers(2, 6)]
         rows, n = lx.extract(p); ref, m = lo.extract(p)
         _compare(rows, n, ref, m, "payload %d (kind %d)" % (t, kind))
+
+
+@pytest.mark.parametrize("beams,step_deg", [(1440, 0.25), (2880, 0.125), (4096, 360.0 / 4096)])
+def test_dense_scanners(libekf, beams, step_deg):
+    """Up to 4096 returns per payload (the reference's simulator sends 361): segments of several hundred points,
+    leaves whose finite-difference covariance the reference computes with O(p^3) trigonometric calls."""
+    from slam_ros_b200 import LineExtractor
+    from oracle.oracle import LinesOracle
+    lo = LinesOracle(); lx = LineExtractor()
+    rng = np.random.default_rng(beams)
+    for pose in ((0.3, -0.2, 0.1), (-1.0, 0.8, 2.0)):
+        p = sc.room_scan(pose, beams=beams, range_sigma=2e-3, rng=rng, step_deg=step_deg)
+        rows, n = lx.extract(p); ref, m = lo.extract(p)
+        _compare(rows, n, ref, m, "%d beams at %s" % (beams, pose))
+        assert n >= 15
+
+
+def test_payload_larger_than_the_limit_is_rejected(libekf):
+    from slam_ros_b200 import LineExtractor
+    from slam_ros_b200.ekf import EkfError, EKF_EINVAL
+    with pytest.raises(EkfError) as e:
+        LineExtractor().extract(np.ones((4097, 2), dtype=np.float32))
+    assert e.value.code == EKF_EINVAL
