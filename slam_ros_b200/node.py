@@ -17,9 +17,10 @@ from .robot import Robot, Line, LINESIZE
 
 
 class SlamNode:
-    def __init__(self, device=0, max_new_lines=None):
-        self.rover = Robot(0.0, 0.0, 0.0, device=device)          # main.cpp:98
-        self.extractor = LineExtractor(device=device)
+    def __init__(self, device=0, max_new_lines=None, rover=None, extractor=None):
+        # rover / extractor: injected stand-ins for host-logic tests; by default the device objects
+        self.rover = rover if rover is not None else Robot(0.0, 0.0, 0.0, device=device)          # main.cpp:98
+        self.extractor = extractor if extractor is not None else LineExtractor(device=device)
         self.lines = []                                            # main.cpp:35
         self.encoderPose = [0.0, 0.0, 0.0]                         # main.cpp:32
         self.rot = [0.0, 0.0]
