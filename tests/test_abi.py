@@ -66,3 +66,22 @@ def test_default_config_matches_reference_constants(libekf):
     from slam_ros_b200.ekf import default_config
     cfg = default_config()
     assert (cfg.capacity_lines, cfg.gate, cfg.encoder_noise, cfg.reset_headroom) == (100, 0.4, 0.024, 10)   # Robot.h:13-17, Robot.cpp:893
+
+
+def test_header_is_plain_c99():
+    """include/ekf.h is the boundary a C, Go (cgo), Java (JNI) or Python (ctypes) host binds: it must compile as C99
+    with no extension and no C++."""
+    import shutil
+    import subprocess
+    import tempfile
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "abi.c")
+        with open(src, "w") as f:
+            f.write('#include "ekf.h"\nint main(void) { ekf_config c; ekf_lx* lx = 0; (void)lx; return ekf_default_config(&c) ? 1 : 0; }\n')
+        out = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                              "-I", os.path.join(root, "include"), src], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
