@@ -517,6 +517,9 @@ def run_monte_carlo(args, rank, world, local):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     from slam_ros_b200.parallel import filters_of_rank
+    weak = getattr(args, "mc_per_gpu", 0) > 0
+    if weak:                                    # weak scaling: a fixed batch per GPU (the 4096-filter batch is the 1-GPU case)
+        B_total = args.mc_per_gpu * world
     ids = filters_of_rank(B_total, rank, world)
     B = len(ids)
     cap = N + w["headroom"]
@@ -568,7 +571,7 @@ def run_monte_carlo(args, rank, world, local):
     return {
         "metric": "EKF predict+update steps/s at N landmarks", "value": K / (ms_max / 1e3), "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "filters_total": B_total, "filters_per_gpu": B, "landmarks": N,
                    "lines_per_scan": m, "filter_steps_per_s": B_total * K / (ms_max / 1e3),
                    "parallelism": "independent filters, %d per GPU, no collective" % B,
@@ -590,6 +593,8 @@ def main():
     ap.add_argument("--workload", default="10k", choices=sorted(WORKLOADS))
     ap.add_argument("--lines", type=int, default=0, help="observed lines per scan (default: the workload's m = 8; "
                     "configs[2] also names m = 32 and 64: one rank-2m sweep per scan)")
+    ap.add_argument("--mc-per-gpu", type=int, default=0, help="Monte-Carlo workload: filters PER GPU (weak scaling) instead "
+                    "of splitting the 4096-filter batch over the ranks (strong scaling, default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
