@@ -43,8 +43,11 @@ enum {
   EKF_FLAG_PER_LINE_KERNELS = 4, /* ekf_scan launches associate / gain / apply per line instead of the single
                                     cluster kernel that walks all lines (same bits; A/B measurement) */
   EKF_FLAG_NO_OVERLAP = 8,   /* do not double-buffer P / overlap a scan's sweep with the next scan's line loop */
-  EKF_FLAG_SWEEP_DIRECT = 2  /* use the plain load/compute/store sweep kernel instead of the TMA + mbarrier
+  EKF_FLAG_SWEEP_DIRECT = 2, /* use the plain load/compute/store sweep kernel instead of the TMA + mbarrier
                                 pipeline (same bits; kept for A/B measurement) */
+  EKF_FLAG_FULL_GATES = 16   /* evaluate the full Mahalanobis gate (Robot.cpp:367-489) for EVERY landmark instead of
+                                first discarding those whose angle innovation alone puts them beyond twice the gate
+                                (d^2 >= v0^2 / S00); same associations, kept for A/B measurement and as a test */
 };
 
 typedef struct {
@@ -65,7 +68,10 @@ int ekf_create(ekf_ctx** out, const ekf_config* cfg);
 int ekf_destroy(ekf_ctx* ctx);
 const char* ekf_last_error(const ekf_ctx* ctx);
 
-/* --- the step-wise path: one call per reference block ------------------------------------------- */
+/* --- the step-wise path: one call per reference block -------------------------------------------
+ * A step-wise scan (ekf_predict ... ekf_end_scan) holds at most 64 lines -- more once a fused ekf_scan with more
+ * lines has run on the ctx (its line tables only grow between scans); a 65th ekf_associate / ekf_update /
+ * ekf_add_line returns EKF_EINVAL and leaves the scan open.  The fused ekf_scan has no such limit. */
 
 /* Robot.cpp:130-258: x_pre = f(x_t0, u); P <- Fx P Fx' + Fu Q Fu'.  Starts a scan (clears the
  * per-scan match list, Robot.cpp:288-295).  x_t0 == NULL uses the resident pose (xPos,yPos,thetaPos).

@@ -472,6 +472,20 @@ void ekfo_stats(void* h, double* min_margin, long long* gates, long long* matche
   if (matches) *matches = o->total_matches;
   if (resets) *resets = o->resets;
 }
+/* trace, sum and sum of squares of the live covariance as libekfcuda reports it (ekf_cov_stats: upper triangle
+ * mirrored), for full-size checks where the matrix itself (51 GB at 40k landmarks) cannot be compared or copied */
+void ekfo_upper_stats(void* h, double* trace, double* sum, double* sumsq) {
+  Oracle* o = (Oracle*)h; const int nl = 3 + 2 * o->L; const size_t n = o->n;
+  double tr = 0.0, sm = 0.0, sq = 0.0;
+#pragma omp parallel for reduction(+ : tr, sm, sq) schedule(dynamic, 64) num_threads(o->threads)
+  for (int r = 0; r < nl; ++r) {
+    const double* Pr = o->P + (size_t)r * n;
+    double s = 0.0, q = 0.0;
+    for (int c = r + 1; c < nl; ++c) { s += Pr[c]; q += Pr[c] * Pr[c]; }
+    tr += Pr[r]; sm += 2.0 * s + Pr[r]; sq += 2.0 * q + Pr[r] * Pr[r];
+  }
+  if (trace) *trace = tr; if (sum) *sum = sm; if (sumsq) *sumsq = sq;
+}
 /* copy out the live (nl x nl) corner, row-major with leading dimension nl */
 void ekfo_get_live(void* h, double* y, double* P) {
   Oracle* o = (Oracle*)h; const int nl = 3 + 2 * o->L, n = o->n;

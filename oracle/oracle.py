@@ -51,7 +51,7 @@ class StructuredOracle:
         for f in ("ekfo_destroy", "ekfo_set_threads", "ekfo_set_pose", "ekfo_predict", "ekfo_associate",
                   "ekfo_gate_pair", "ekfo_update", "ekfo_last_gain", "ekfo_queue", "ekfo_end", "ekfo_scan", "ekfo_localize", "ekfo_n",
                   "ekfo_lines", "ekfo_y_ptr", "ekfo_P_ptr", "ekfo_get_pose", "ekfo_get_xpre", "ekfo_stats",
-                  "ekfo_get_live", "ekfo_get_ellipse", "ekfo_get_threads"):
+                  "ekfo_get_live", "ekfo_get_ellipse", "ekfo_get_threads", "ekfo_upper_stats"):
             getattr(L, f).argtypes = None
         self._h = C.c_void_p(L.ekfo_create(int(capacity_lines), float(gate), float(encoder_noise), int(reset_headroom)))
         if not self._h:
@@ -172,6 +172,12 @@ class StructuredOracle:
         mm = C.c_double(0); g = C.c_longlong(0); mt = C.c_longlong(0); rs = C.c_longlong(0)
         self._lib.ekfo_stats(self._h, C.byref(mm), C.byref(g), C.byref(mt), C.byref(rs))
         return {"min_margin": mm.value, "gates": g.value, "matches": mt.value, "resets": rs.value}
+
+    def upper_stats(self):
+        """(trace, sum, sumsq) of the live covariance read as libekfcuda reads it: upper triangle mirrored."""
+        t = C.c_double(0); s = C.c_double(0); q = C.c_double(0)
+        self._lib.ekfo_upper_stats(self._h, C.byref(t), C.byref(s), C.byref(q))
+        return t.value, s.value, q.value
 
     def get_ellipse(self):
         ax = (C.c_float * 2)(); ang = C.c_float(0)

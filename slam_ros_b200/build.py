@@ -36,19 +36,46 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
-        return OUT
-    extra = os.environ.get("EKF_NVCC_EXTRA", "").split()
+# A/B builds of the same sources, loaded through EKF_LIB by tests and measurement scripts (never by default):
+#   exact   -DEKF_EXACT_RANK2: the reference's four-rounding p - (ks.x k.x + ks.y k.y) instead of two FMAs
+#   timing  -DEKF_LINE_TIMING: %globaltimer stamps of the line loop's phases (scripts/line_timing*.py)
+VARIANTS = {"exact": ["-DEKF_EXACT_RANK2"], "timing": ["-DEKF_LINE_TIMING"]}
+
+
+def variant_path(name):
+    return os.path.join(HERE, "libekfcuda_%s.so" % name)
+
+
+def _stale(out):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(out, extra, verbose=False):
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT, "-ldl"]
-    env = dict(os.environ)
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out, "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ))
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return OUT
+    return _compile(OUT, os.environ.get("EKF_NVCC_EXTRA", "").split(), verbose)
+
+
+def build_variant(name, force=False):
+    out = variant_path(name)
+    if not force and not _stale(out):
+        return out
+    return _compile(out, VARIANTS[name])
 
 
 if __name__ == "__main__":

@@ -98,6 +98,8 @@ struct ekf_ctx {
   EkfPeers peers;
   int peers_mapped;           /* ekf_shard_connect succeeded: every peer's exchange buffer is mapped */
   int peers_ok;               /* ekf_shard_use_fused(1): the H-column slices travel inside the line-loop kernel */
+  int poisoned;               /* a cross-GPU exchange timed out (EKF_ENCCL): the replicas may have diverged; every call
+                                 fails with EKF_ESTATE until ekf_upload restores a complete state */
   /* staging for download / upload / stats */
   double* d_stage; size_t stage_elems;
   double* d_partials; double* d_out3;
@@ -113,6 +115,14 @@ namespace {
       snprintf(ctx->err, sizeof ctx->err, "%s:%d %.120s: %s", "ekf_api.cu", __LINE__, #call, cudaGetErrorString(e_)); \
       return EKF_ECUDA;                                                                       \
     }                                                                                         \
+  } while (0)
+
+#define NOT_POISONED(ctx)                                                                                          \
+  do {                                                                                                             \
+    if ((ctx)->poisoned) {                                                                                         \
+      snprintf((ctx)->err, sizeof (ctx)->err, "a cross-GPU exchange timed out earlier (EKF_ENCCL): re-upload the state with ekf_upload"); \
+      return EKF_ESTATE;                                                                                           \
+    }                                                                                                              \
   } while (0)
 
 const size_t kStageElems = (size_t)8 << 20;   /* 64 MiB staging for download/upload */
@@ -162,7 +172,7 @@ int ensure_lines(ekf_ctx* ctx, int m) {
   free_line_tables(ctx);
   int cap = ctx->max_lines > 0 ? ctx->max_lines : 64;
   while (cap < m) cap *= 2;
-  ctx->max_lines = cap;
+  ctx->max_lines = 0;             /* committed only once every table below exists: a failed allocation sends the next call back here */
   const size_t n1 = (size_t)cap + 1;
   for (int t = 0; t < 2; ++t) {
     CU(cudaMalloc(&ctx->tab[t].jbest, n1 * sizeof(int)));
@@ -178,6 +188,7 @@ int ensure_lines(ekf_ctx* ctx, int m) {
   CU(cudaMalloc(&ctx->d_in, (6 + 6 * (size_t)cap) * sizeof(double)));
   CU(cudaMallocHost(&ctx->h_in, (6 + 6 * (size_t)cap) * sizeof(double)));
   CU(cudaMallocHost(&ctx->h_jout, n1 * sizeof(int)));
+  ctx->max_lines = cap;
   return EKF_OK;
 }
 
@@ -492,7 +503,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8;
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
   ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);
-  ctx->xchg = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
+  ctx->xchg = 0; ctx->poisoned = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
   *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -716,6 +727,7 @@ int ekf_scan(ekf_ctx* ctx, const double x_t0[3], const double u[3], int m, const
              int* j_out, double pose[3]) {
   if (!ctx || !u || m < 0 || (m > 0 && (!z || !R))) return EKF_EINVAL;
   if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_scan inside an open step-wise scan"); return EKF_ESTATE; }
+  NOT_POISONED(ctx);
   CU(cudaSetDevice(ctx->cfg.device));
   int rc = ensure_lines(ctx, m);
   if (rc) return rc;
@@ -738,6 +750,7 @@ int ekf_scan(ekf_ctx* ctx, const double x_t0[3], const double u[3], int m, const
   if (sticky) {
     CU(cudaMemsetAsync(&ctx->b.st->sticky, 0, sizeof(int), ctx->stream));
     snprintf(ctx->err, sizeof ctx->err, "scan finished with sticky status 0x%x", sticky);
+    if (sticky & EKF_STICKY_XCHG) ctx->poisoned = 1;
   }
   return sticky_to_status(sticky);
 }
@@ -745,6 +758,7 @@ int ekf_scan(ekf_ctx* ctx, const double x_t0[3], const double u[3], int m, const
 int ekf_scan_device(ekf_ctx* ctx, const double* d_u, int m, const double* d_z, const double* d_R, int* d_j_out) {
   if (!ctx || !d_u || m < 0 || (m > 0 && (!d_z || !d_R))) return EKF_EINVAL;
   if (ctx->scan_open) return EKF_ESTATE;
+  NOT_POISONED(ctx);
   CU(cudaSetDevice(ctx->cfg.device));
   int rc = ensure_lines(ctx, m);
   if (rc) return rc;
@@ -767,8 +781,10 @@ int ekf_sync(ekf_ctx* ctx) {
 int ekf_predict(ekf_ctx* ctx, const double x_t0[3], const double u[3], double x_pre[3]) {
   if (!ctx || !u) return EKF_EINVAL;
   if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_predict: previous scan not ended"); return EKF_ESTATE; }
+  NOT_POISONED(ctx);
   CU(cudaSetDevice(ctx->cfg.device));
   { int rc = drain(ctx); if (rc) return rc; }
+  { int rc = ensure_lines(ctx, 1); if (rc) return rc; }     /* re-creates the line tables after a failed growth */
   use_tables(ctx, 0);
   double* h = ctx->h_in;
   memcpy(h, u, 3 * sizeof(double));
@@ -786,7 +802,7 @@ int ekf_predict(ekf_ctx* ctx, const double x_t0[3], const double u[3], double x_
 namespace {
 int stage_line(ekf_ctx* ctx, const double z[2], const double R[4]) {
   if (ctx->cursor >= ctx->max_lines) {
-    snprintf(ctx->err, sizeof ctx->err, "more than %d lines in a step-wise scan", ctx->max_lines);
+    snprintf(ctx->err, sizeof ctx->err, "more than %d lines in a step-wise scan (limit of the step-wise ABI, see ekf.h; ekf_scan has none)", ctx->max_lines);
     return EKF_EINVAL;
   }
   const int i = ctx->cursor;
@@ -803,6 +819,7 @@ int stage_line(ekf_ctx* ctx, const double z[2], const double R[4]) {
 int ekf_associate(ekf_ctx* ctx, const double z[2], const double R[4], int* j_out, double innov[2]) {
   if (!ctx || !z || !R || !j_out) return EKF_EINVAL;
   if (!ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_associate before ekf_predict"); return EKF_ESTATE; }
+  NOT_POISONED(ctx);
   CU(cudaSetDevice(ctx->cfg.device));
   int rc = stage_line(ctx, z, R);
   if (rc) return rc;
@@ -827,6 +844,7 @@ int ekf_associate(ekf_ctx* ctx, const double z[2], const double R[4], int* j_out
 int ekf_update(ekf_ctx* ctx, int j, const double z[2], const double R[4], double x_post[3]) {
   if (!ctx || !z || !R || j < 0) return EKF_EINVAL;
   if (!ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_update before ekf_predict"); return EKF_ESTATE; }
+  NOT_POISONED(ctx);
   CU(cudaSetDevice(ctx->cfg.device));
   int rc = read_state(ctx);
   if (rc) return rc;
@@ -871,6 +889,7 @@ int ekf_end_scan(ekf_ctx* ctx, int n_lines, double pose[3]) {
   if (pose) memcpy(pose, ctx->h_st->pose, 3 * sizeof(double));
   const int sticky = ctx->h_st->sticky;
   if (sticky) CU(cudaMemsetAsync(&ctx->b.st->sticky, 0, sizeof(int), ctx->stream));
+  if (sticky & EKF_STICKY_XCHG) ctx->poisoned = 1;
   return sticky_to_status(sticky);
 }
 
@@ -884,6 +903,7 @@ int ekf_get_state(ekf_ctx* ctx, double pose[3], int* n_lines, int* sticky_status
   if (n_lines) *n_lines = ctx->h_st->L;
   if (sticky_status) {
     *sticky_status = sticky_to_status(ctx->h_st->sticky);
+    if (ctx->h_st->sticky & EKF_STICKY_XCHG) ctx->poisoned = 1;
     if (ctx->h_st->sticky) CU(cudaMemsetAsync(&ctx->b.st->sticky, 0, sizeof(int), ctx->stream));
   }
   return EKF_OK;
@@ -936,6 +956,7 @@ int ekf_get_ellipse(ekf_ctx* ctx, float axii[2], float* angle, int* ok) {
 int ekf_download(ekf_ctx* ctx, double* y, double* P, int* n_lines) {
   if (!ctx) return EKF_EINVAL;
   if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_download inside an open scan"); return EKF_ESTATE; }
+  NOT_POISONED(ctx);
   CU(cudaSetDevice(ctx->cfg.device));
   { int rc = drain(ctx); if (rc) return rc; }
   int rc = read_state(ctx);
@@ -954,6 +975,7 @@ int ekf_download(ekf_ctx* ctx, double* y, double* P, int* n_lines) {
 int ekf_download_live(ekf_ctx* ctx, double* y, double* P, int ldp, int max_n, int* n_lines) {
   if (!ctx) return EKF_EINVAL;
   if (ctx->scan_open) { snprintf(ctx->err, sizeof ctx->err, "ekf_download_live inside an open scan"); return EKF_ESTATE; }
+  NOT_POISONED(ctx);
   CU(cudaSetDevice(ctx->cfg.device));
   { int rc = drain(ctx); if (rc) return rc; }
   int rc = read_state(ctx);
@@ -1008,6 +1030,7 @@ int ekf_upload(ekf_ctx* ctx, const double* y, const double* P, int n_lines) {
   CU(cudaMemcpyAsync(ctx->b.st, ctx->h_st, sizeof(EkfDevState), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->L_ub = n_lines;
+  if (y && P) ctx->poisoned = 0;      /* a complete state replaces whatever a failed exchange left behind */
   return EKF_OK;
 }
 

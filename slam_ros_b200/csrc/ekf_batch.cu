@@ -1,13 +1,22 @@
 /* ekf_batch.cu -- independent filter instances (Monte-Carlo batches, BASELINE.json configs[3]).
  *
- * One 128-thread block per filter; the whole Robot::localize (slam_ros/Robot.cpp:126-943) of that filter
- * runs inside one kernel launch.  Same design as the single big filter, scaled down to one CTA: the hot
- * state (rows 0..2 of P, the 2x2 diagonal blocks, y) and the scan's pending gains live in shared memory
- * (~23 KB, so four filters share an SM and hide each other's fp64 latency chains); the cold part of P stays
- * in HBM, is read where a gain needs a column (with the pending terms applied on the fly) and is brought up
- * to date by ONE read-modify-write pass over its upper triangle at the end of the scan: 8 n (n+1) bytes per
- * filter-scan however many lines match.  Filters never communicate; a multi-GPU batch is N independent
- * ekf_batch objects, one per device (slam_ros_b200/parallel.py deals filters round-robin).
+ * One thread block per filter; the whole Robot::localize (slam_ros/Robot.cpp:126-943) of that filter runs inside
+ * one kernel launch with the filter's ENTIRE covariance in shared memory:
+ *
+ *   - storage, in HBM and in shared memory alike, is the upper triangle packed by COLUMNS: P[r,q] (r <= q) lives at
+ *     q (q+1) / 2 + r.  The live part (columns < 3 + 2 L) is then a contiguous prefix whatever the capacity, and
+ *     appending a landmark appends two columns at its end: a scan is ONE bulk copy in (cp.async.bulk, 43 KB at 50
+ *     landmarks), the arithmetic, ONE bulk copy out -- 8 nl (nl+1) bytes of HBM traffic per filter and scan, and no
+ *     global-memory round trip anywhere inside the scan;
+ *   - with P on chip nothing has to be deferred: each matched line updates every element at once,
+ *     p <- p - (K S)[r] K[q] (Robot.cpp:564-568), which is the reference's own order of operations;
+ *   - association (Robot.cpp:313-501): every landmark first takes a test that needs no trigonometry and no matrix
+ *     inverse -- the angle innovation alone bounds the Mahalanobis distance from below, d^2 >= v0^2 / S00 -- and is
+ *     rejected when even that bound is twice the gate; the few survivors (typically one) are compacted and evaluated
+ *     by the reference's full expression, one per thread; first fit = lowest passing index.
+ *
+ * Filters never communicate; a multi-GPU batch is N independent ekf_batch objects, one per device
+ * (slam_ros_b200/parallel.py deals filters round-robin).
  */
 #include "../../include/ekf.h"
 #include "ekf_internal.h"
@@ -17,6 +26,7 @@
 #include <string.h>
 
 #define EKFB_THREADS 128
+#define EKFB_MAXCAND 64
 
 struct EkfBatchState {
   double pose[3];
@@ -29,132 +39,119 @@ struct EkfBatchState {
 struct EkfBatchGeom {
   int B, cap, n, headroom;
   double gate, enc_noise;
+  long long pstride;        /* doubles per filter in the packed covariance array (even: 16-byte aligned filters) */
+  int ystride;              /* doubles per filter in the state array (even) */
+  int full_gates;           /* A/B: evaluate the full gate for every landmark (no lower-bound pre-test) */
 };
 
 namespace {
 
-#define EKFB_SLOTS 8        /* pending rank-2 terms kept in shared memory before the cold part is swept */
+__host__ __device__ inline int tri(int q) { return (q * (q + 1)) >> 1; }        /* first element of packed column q */
 
-/* Shared-memory footprint: hot state + pending gains only (the cold part of P never leaves HBM/L2 except for
- * the one read-modify-write sweep per scan), so several filters share an SM. */
-struct BatchSmem {
-  double* top;              /* [3][n]  rows 0..2 of P, upper authoritative */
-  double* diag;             /* [cap][3] P[a,a], P[a,b], P[b,b] */
-  double* y;                /* [n] */
-  double2* K;               /* [EKFB_SLOTS][n] pending gains */
-  double* S;                /* [EKFB_SLOTS][4] their innovation covariances (K S is recomputed: Robot.cpp:560) */
-  int* ext;                 /* [m] */
-  unsigned char* matched;   /* [cap] */
-};
-__host__ __device__ inline size_t batch_smem_bytes(int n, int cap, int m) {
-  size_t d = (size_t)(3 * n + 3 * cap + n);
-  d += d & 1;                                      /* double2 alignment of the pending gains */
-  size_t b = d * sizeof(double);
-  b += (size_t)EKFB_SLOTS * n * sizeof(double2) + (size_t)EKFB_SLOTS * 4 * sizeof(double);
-  b += (size_t)m * sizeof(int) + (size_t)cap;
-  return (b + 15) & ~(size_t)15;
+/* shared-memory carve-up for a scan whose live dimension cannot exceed ns */
+struct BatchLayout { int P, y, K, KS, cand, ext, matched, bytes; };
+__host__ __device__ inline BatchLayout batch_layout(int ns, int cap, int m) {
+  BatchLayout l;
+  int o = 0;
+  l.P = o; o += ((tri(ns) + 1) & ~1) * 8;            /* packed upper triangle, columns < ns */
+  l.y = o; o += ((ns + 1) & ~1) * 8;
+  l.K = o; o += ns * 16;
+  l.KS = o; o += ns * 16;
+  l.cand = o; o += EKFB_MAXCAND * 4;
+  l.ext = o; o += ((m + 3) & ~3) * 4;
+  l.matched = o; o += (cap + 15) & ~15;
+  l.bytes = o;
+  return l;
 }
 
-__device__ __forceinline__ bool b_is_hot(int r, int q) { return r <= 2 || q == r || (q == r + 1 && (r & 1)); }
-__device__ __forceinline__ double b_hot(const BatchSmem& sm, int n, int r, int q) {
-  if (r <= 2) return sm.top[r * n + q];
-  const int j = (r - 3) >> 1;
-  return (r & 1) ? sm.diag[3 * j + (q - r)] : sm.diag[3 * j + 2];
+__device__ __forceinline__ unsigned b_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void b_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_smem_u32(bar)), "r"(count));
 }
-/* (K S)[r] of pending term i, Robot.cpp:560 (NN, zero skip) */
-__device__ __forceinline__ double2 b_ks(const BatchSmem& sm, int n, int i, int r) {
-  const double2 k = sm.K[i * n + r];
-  const double* S = sm.S + 4 * i;
-  double s0 = 0.0, s1 = 0.0;
-  axpy_skip(s0, k.x, S[0]); axpy_skip(s1, k.x, S[1]);
-  axpy_skip(s0, k.y, S[2]); axpy_skip(s1, k.y, S[3]);
-  return make_double2(s0, s1);
+__device__ __forceinline__ void b_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_smem_u32(bar)), "r"(bytes) : "memory");
 }
-/* current value of a cold upper element: HBM value minus the pending terms, in order */
-__device__ __forceinline__ double b_cold(const BatchSmem& sm, const double* __restrict__ Pf, int n, int r, int q, int np) {
-  double p = Pf[(size_t)r * n + q];
-  for (int i = 0; i < np; ++i) p = sub_rank2(p, b_ks(sm, n, i, r), sm.K[i * n + q]);
-  return p;
+__device__ __forceinline__ void b_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B_WAIT_DONE;\n"
+      "bra B_WAIT_LOOP;\n"
+      "B_WAIT_DONE:\n"
+      "}\n" ::"r"(b_smem_u32(bar)), "r"(parity) : "memory");
 }
-/* fold the pending terms into the cold upper triangle of the live part (one read-modify-write pass) */
-__device__ void b_sweep(const BatchSmem& sm, double* __restrict__ Pf, int n, int nl, int np) {
-  if (np <= 0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int r = 3 + warp; r < nl; r += nw) {
-    double2 ks[EKFB_SLOTS];
-#pragma unroll
-    for (int i = 0; i < EKFB_SLOTS; ++i) if (i < np) ks[i] = b_ks(sm, n, i, r);
-    double* Pr = Pf + (size_t)r * n;
-    const int q0 = (r & 1) ? r + 2 : r + 1;            /* skip the 2x2 diagonal block (hot) */
-    for (int q = q0 + lane; q < nl; q += 32) {
-      double p = Pr[q];
-#pragma unroll
-      for (int i = 0; i < EKFB_SLOTS; ++i) if (i < np) p = sub_rank2(p, ks[i], sm.K[i * n + q]);
-      Pr[q] = p;
-    }
-  }
+__device__ __forceinline__ void b_bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(b_smem_u32(dst)), "l"(src), "r"(bytes), "r"(b_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void b_bulk_store(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(b_smem_u32(src)), "r"(bytes) : "memory");
 }
 
-/* Robot::localize for filter blockIdx.x */
-__global__ void __launch_bounds__(EKFB_THREADS, 8) k_batch_scan(EkfBatchGeom g, double* __restrict__ Yg,
-                                                                double* __restrict__ Pg, EkfBatchState* __restrict__ Sg,
-                                                                const double* __restrict__ U, const double* __restrict__ Z,
-                                                                const double* __restrict__ Rm, int m, int* __restrict__ Jout) {
-  extern __shared__ double smem[];
-  const int n = g.n, tid = threadIdx.x, nt = blockDim.x;
-  const int f = blockIdx.x;
-  BatchSmem sm;
-  sm.top = smem;
-  sm.diag = sm.top + 3 * n;
-  sm.y = sm.diag + 3 * g.cap;
-  sm.K = reinterpret_cast<double2*>(sm.y + n + ((3 * n + 3 * g.cap + n) & 1));
-  sm.S = reinterpret_cast<double*>(sm.K + (size_t)EKFB_SLOTS * n);
-  sm.ext = reinterpret_cast<int*>(sm.S + EKFB_SLOTS * 4);
-  sm.matched = reinterpret_cast<unsigned char*>(sm.ext + m);
-  __shared__ int s_min[EKFB_THREADS / 32];
-  __shared__ int s_best, s_ne, s_nmatch, s_L, s_stop;
-  __shared__ double s_xpre[3], s_pose[3], s_cs[2];
+/* Robot::localize for filter blockIdx.x.  ns: upper bound of the live dimension at the END of this scan (host-side
+ * bound: largest map of the batch + m, capped by the capacity; the shared-memory carve-up is sized by it). */
+__global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, int ns, double* __restrict__ Yg,
+                                                             double* __restrict__ Pg, EkfBatchState* __restrict__ Sg,
+                                                             const double* __restrict__ U, const double* __restrict__ Z,
+                                                             const double* __restrict__ Rm, int m, int* __restrict__ Jout) {
+  extern __shared__ __align__(16) unsigned char braw[];
+  const BatchLayout lay = batch_layout(ns, g.cap, m);
+  double* const Ps = reinterpret_cast<double*>(braw + lay.P);
+  double* const ys = reinterpret_cast<double*>(braw + lay.y);
+  double2* const Ks = reinterpret_cast<double2*>(braw + lay.K);
+  double2* const KSs = reinterpret_cast<double2*>(braw + lay.KS);
+  int* const cand = reinterpret_cast<int*>(braw + lay.cand);
+  int* const ext = reinterpret_cast<int*>(braw + lay.ext);
+  unsigned char* const matched = braw + lay.matched;
+  __shared__ unsigned long long s_bar;
+  __shared__ int s_best, s_ncand, s_sticky;
+  __shared__ double s_xpre[3];
   __shared__ Gate sG;
 
-  double* Pf = Pg + (size_t)f * n * n;
-  double* yf = Yg + (size_t)f * n;
-  EkfBatchState* st = Sg + f;
-  const double* u = U + 3 * (size_t)f;
-  const double* z = Z + 2 * (size_t)m * f;
-  const double* R = Rm + 4 * (size_t)m * f;
-  int* jout = Jout ? Jout + (size_t)m * f : 0;
+  const int tid = threadIdx.x, nt = EKFB_THREADS, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.x;
+  double* const Pf = Pg + (size_t)f * g.pstride;
+  double* const yf = Yg + (size_t)f * g.ystride;
+  EkfBatchState* const st = Sg + f;
+  const double* const u = U + 3 * (size_t)f;
+  const double* const z = Z + 2 * (size_t)m * f;
+  const double* const R = Rm + 4 * (size_t)m * f;
+  int* const jout = Jout ? Jout + (size_t)m * f : 0;
 
+  int L = st->L;
+  const int nl = 3 + 2 * L;
+  const double pose0 = st->pose[0], pose1 = st->pose[1], pose2 = st->pose[2];
+  /* ---- the filter's live covariance and state: two bulk copies, one barrier ---- */
   if (tid == 0) {
-    st->sticky = 0;                           /* status reports this scan only */
-    s_L = st->L; s_ne = 0; s_nmatch = 0;
-    s_pose[0] = st->pose[0]; s_pose[1] = st->pose[1]; s_pose[2] = st->pose[2];
+    const unsigned pbytes = (unsigned)(((tri(nl) + 1) & ~1) * 8), ybytes = (unsigned)(((nl + 1) & ~1) * 8);
+    b_mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    b_mbar_expect_tx(&s_bar, pbytes + ybytes);
+    b_bulk_load(Ps, Pf, pbytes, &s_bar);
+    b_bulk_load(ys, yf, ybytes, &s_bar);
+    s_sticky = 0;
   }
+  for (int j = tid; j < g.cap; j += nt) matched[j] = 0;
   __syncthreads();
-  int L = s_L;
-  int nl = 3 + 2 * L;
-  for (int i = tid; i < 3 * n; i += nt) { const int r = i / n, q = i % n; sm.top[i] = (q < nl) ? Pf[(size_t)r * n + q] : 0.0; }
-  for (int j = tid; j < g.cap; j += nt) {
-    const int a = 3 + 2 * j;
-    if (j < L) { sm.diag[3 * j] = Pf[(size_t)a * n + a]; sm.diag[3 * j + 1] = Pf[(size_t)a * n + a + 1]; sm.diag[3 * j + 2] = Pf[(size_t)(a + 1) * n + a + 1]; }
-    sm.matched[j] = 0;
-  }
-  for (int i = tid; i < n; i += nt) sm.y[i] = yf[i];
-  __syncthreads();
+  b_mbar_wait(&s_bar, 0);
 
   /* ---- prediction, Robot.cpp:130-258 ---- */
   const double u0 = u[0], u2 = u[2];
-  const double ang = add_rn(s_pose[2], __ddiv_rn(u2, 2.0));
+  const double ang = add_rn(pose2, __ddiv_rn(u2, 2.0));
   const double ca = cos(ang), sa = sin(ang);
   const double F02 = mul_rn(-u0, sa), F12 = mul_rn(u0, ca);
   for (int q = 3 + tid; q < nl; q += nt) {                            /* :242 rows 0,1 */
-    const double p2 = sm.top[2 * n + q];
-    double a0 = add_rn(0.0, sm.top[q]); axpy_skip(a0, F02, p2);
-    double a1 = add_rn(0.0, sm.top[n + q]); axpy_skip(a1, F12, p2);
-    sm.top[q] = a0; sm.top[n + q] = a1;
+    double* c = Ps + tri(q);
+    const double p2 = c[2];
+    double a0 = add_rn(0.0, c[0]); axpy_skip(a0, F02, p2);
+    double a1 = add_rn(0.0, c[1]); axpy_skip(a1, F12, p2);
+    c[0] = a0; c[1] = a1;
   }
   if (tid == 0) {
     double A[3][3], T[3][3], Pn[3][3];
-    for (int i = 0; i < 3; ++i) for (int k = i; k < 3; ++k) { A[i][k] = sm.top[i * n + k]; A[k][i] = A[i][k]; }
+    for (int i = 0; i < 3; ++i) for (int k = i; k < 3; ++k) { A[i][k] = Ps[tri(k) + i]; A[k][i] = A[i][k]; }
     for (int j = 0; j < 3; ++j) {
       double r0 = 0.0, r1 = 0.0, r2 = 0.0;
       axpy_skip(r0, 1.0, A[0][j]); axpy_skip(r1, 1.0, A[1][j]);
@@ -182,215 +179,237 @@ __global__ void __launch_bounds__(EKFB_THREADS, 8) k_batch_scan(EkfBatchGeom g, 
       for (int j = i; j < 3; ++j) {
         double t = 0.0;
         for (int k = 0; k < 3; ++k) t = add_rn(t, mul_rn(FQ[i][k], Fu[j][k]));
-        sm.top[i * n + j] = add_rn(Pn[i][j], add_rn(0.0, mul_rn(1.0, t)));
+        Ps[tri(j) + i] = add_rn(Pn[i][j], add_rn(0.0, mul_rn(1.0, t)));
       }
-    s_xpre[0] = add_rn(s_pose[0], mul_rn(u0, ca));
-    s_xpre[1] = add_rn(s_pose[1], mul_rn(u0, sa));
-    s_xpre[2] = add_rn(s_pose[2], u2);
+    s_xpre[0] = add_rn(pose0, mul_rn(u0, ca));
+    s_xpre[1] = add_rn(pose1, mul_rn(u0, sa));
+    s_xpre[2] = add_rn(pose2, u2);
   }
   __syncthreads();
 
   /* ---- the observed lines in order, Robot.cpp:298-645 ---- */
-  int np = 0;                                  /* pending terms (uniform across the block) */
+  int ne = 0, nmatch = 0;                                    /* uniform across the block */
+  const double gate2x4 = 4.0 * g.gate * g.gate;
   for (int i = 0; i < m; ++i) {
     const double z0 = z[2 * i], z1 = z[2 * i + 1];
-    const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
-    const double xp[3] = {s_xpre[0], s_xpre[1], s_xpre[2]};
-    int cand = EKF_NO_MATCH;
-    Gate G;
-    for (int j = tid; j < L; j += nt) {
-      if (sm.matched[j] || cand != EKF_NO_MATCH) continue;
-      const int a = 3 + 2 * j, bb = a + 1;
-      double Cm[5][5];
-      for (int r = 0; r < 3; ++r) {
-        for (int q = r; q < 3; ++q) { Cm[r][q] = sm.top[r * n + q]; Cm[q][r] = Cm[r][q]; }
-        Cm[r][3] = Cm[3][r] = sm.top[r * n + a]; Cm[r][4] = Cm[4][r] = sm.top[r * n + bb];
-      }
-      Cm[3][3] = sm.diag[3 * j]; Cm[3][4] = Cm[4][3] = sm.diag[3 * j + 1]; Cm[4][4] = sm.diag[3 * j + 2];
-      Gate Gj;
-      gate_from_block(Cm, sm.y[a], sm.y[bb], xp, z0, z1, Rl, Gj);
-      if (Gj.singular) atomicOr(&st->sticky, EKF_STICKY_SINGULAR);
-      else if (!(sqrt(fabs(Gj.d2)) > g.gate)) { cand = j; G = Gj; }
-    }
-    const int mine = cand;
-    cand = __reduce_min_sync(0xffffffffu, cand);
-    if ((tid & 31) == 0) s_min[tid >> 5] = cand;
+    const double xp0 = s_xpre[0], xp1 = s_xpre[1], xp2 = s_xpre[2];
+    if (tid == 0) { s_ncand = 0; s_best = EKF_NO_MATCH; }
     __syncthreads();
-    if (tid < 32) {
-      int v = (tid < EKFB_THREADS / 32) ? s_min[tid] : EKF_NO_MATCH;
-      v = __reduce_min_sync(0xffffffffu, v);
-      if (tid == 0) {
-        s_best = v;
-        if (v == EKF_NO_MATCH) { sm.ext[s_ne++] = i; if (jout) jout[i] = -1; }
+    /* pre-test: v0 is the gate's own angle innovation (Robot.cpp:423-475, no trigonometry); S00 = H0 P H0' + R00 with
+     * H0 = (0, 0, -1, .. 1 at a ..): d^2 = v' S^-1 v >= v0^2 / S00, so a landmark whose bound exceeds (2 gate)^2 -- twice
+     * the gate in d, far outside any rounding difference between the bound and the reference's LU expression -- cannot
+     * pass the reference's test either */
+    {
+      const double P22 = Ps[tri(2) + 2], R00 = R[4 * i];
+      for (int j = tid; j < L; j += nt) {
+        if (matched[j]) continue;
+        bool keep = true;
+        if (!g.full_gates) {
+          const int a = 3 + 2 * j;
+          const double* ca_ = Ps + tri(a);
+          double h0 = sub_rn(ys[a], xp2);
+          normalize_radian(h0);
+          double v0 = sub_rn(z0, h0);
+          const double two_pi = 2.0 * EKF_PI;
+          if (fabs(sub_rn(v0, two_pi)) < fabs(v0)) v0 = sub_rn(v0, two_pi);
+          else if (fabs(add_rn(v0, two_pi)) < fabs(v0)) v0 = add_rn(v0, two_pi);
+          const double S00 = (P22 - 2.0 * ca_[2]) + ca_[a] + R00;
+          keep = !(S00 > 0.0) || !(v0 * v0 > gate2x4 * S00);
+        }
+        if (keep) { const int k = atomicAdd(&s_ncand, 1); if (k < EKFB_MAXCAND) cand[k] = j; }
+      }
+    }
+    __syncthreads();
+    /* full gate of the survivors, one per thread */
+    {
+      const int ncand = s_ncand;
+      const bool overflow = ncand > EKFB_MAXCAND;          /* more survivors than the list holds: gate every landmark */
+      const int total = overflow ? L : ncand;
+      const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
+      const double xp[3] = {xp0, xp1, xp2};
+      int mine = EKF_NO_MATCH;
+      Gate G;
+      for (int k = tid; k < total; k += nt) {
+        const int j = overflow ? k : cand[k];
+        if (overflow && matched[j]) continue;
+        if (j > mine) continue;
+        const int a = 3 + 2 * j, bb = a + 1;
+        const double* ca_ = Ps + tri(a);
+        const double* cb_ = Ps + tri(bb);
+        double Cm[5][5];
+        for (int r = 0; r < 3; ++r) {
+          for (int q = r; q < 3; ++q) { Cm[r][q] = Ps[tri(q) + r]; Cm[q][r] = Cm[r][q]; }
+          Cm[r][3] = Cm[3][r] = ca_[r]; Cm[r][4] = Cm[4][r] = cb_[r];
+        }
+        Cm[3][3] = ca_[a]; Cm[3][4] = Cm[4][3] = cb_[a]; Cm[4][4] = cb_[bb];
+        Gate Gj;
+        gate_from_block(Cm, ys[a], ys[bb], xp, z0, z1, Rl, Gj);
+        if (Gj.singular) atomicOr(&s_sticky, EKF_STICKY_SINGULAR);
+        else if (!(sqrt(fabs(Gj.d2)) > g.gate)) { mine = j; G = Gj; }                /* :489 */
+      }
+      if (total > 0) {                                     /* uniform */
+        if (mine != EKF_NO_MATCH) atomicMin(&s_best, mine);
+        __syncthreads();
+        if (mine != EKF_NO_MATCH && mine == s_best) sG = G;   /* the winner publishes its gate record (evaluated once) */
       }
     }
     __syncthreads();
     const int jb = s_best;
-    if (jb == EKF_NO_MATCH) continue;
-    if (mine == jb) sG = G;                     /* the winner publishes its gate record (evaluated once) */
-    if (np == EKFB_SLOTS) {                     /* pending list full: fold it into the cold part first */
-      __syncthreads();
-      b_sweep(sm, Pf, n, nl, np);
-      np = 0;
+    if (jb == EKF_NO_MATCH) {                                         /* :309 / :325 / :493 */
+      if (tid == 0) { ext[ne] = i; if (jout) jout[i] = -1; }
+      ne += 1;
+      continue;
     }
-    __syncthreads();
     const int a = 3 + 2 * jb, bb = a + 1;
+    const int ta = tri(a), tb = tri(bb);
     for (int r = tid; r < nl; r += nt) {                              /* :516-560 */
-      double p0, p1, p2;
-      if (r <= 2) { p0 = sm.top[min(r, 0) * n + max(r, 0)]; p1 = sm.top[min(r, 1) * n + max(r, 1)]; p2 = sm.top[min(r, 2) * n + max(r, 2)]; }
-      else { p0 = sm.top[r]; p1 = sm.top[n + r]; p2 = sm.top[2 * n + r]; }
-      const int lo_a = min(r, a), hi_a = max(r, a), lo_b = min(r, bb), hi_b = max(r, bb);
-      const double pa = b_is_hot(lo_a, hi_a) ? b_hot(sm, n, lo_a, hi_a) : b_cold(sm, Pf, n, lo_a, hi_a, np);
-      const double pb = b_is_hot(lo_b, hi_b) ? b_hot(sm, n, lo_b, hi_b) : b_cold(sm, Pf, n, lo_b, hi_b, np);
+      const int tr_ = tri(r);
+      const double p0 = (r <= 0) ? Ps[r] : Ps[tr_];                   /* P[r,0..2] through the upper storage */
+      const double p1 = (r <= 1) ? Ps[tri(1) + r] : Ps[tr_ + 1];
+      const double p2 = (r <= 2) ? Ps[tri(2) + r] : Ps[tr_ + 2];
+      const double pa = (r <= a) ? Ps[ta + r] : Ps[tr_ + a];
+      const double pb = (r <= bb) ? Ps[tb + r] : Ps[tr_ + bb];
       double2 Kr, KSr;
       gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
-      sm.K[np * n + r] = Kr;
+      Ks[r] = Kr; KSs[r] = KSr;
     }
-    if (tid < 4) sm.S[4 * np + tid] = sG.S[tid];
     __syncthreads();
-    {                                                                 /* :564-602 on the hot elements */
-      const double2 ks0 = b_ks(sm, n, np, 0), ks1 = b_ks(sm, n, np, 1), ks2 = b_ks(sm, n, np, 2);
+    /* ---- :564-602: every element of the upper triangle, y, the pose.  Columns are paired (q, nl-1-q) so that every
+     * warp task spans nl+1 rows; a lane walks consecutive rows of a column (conflict-free). ---- */
+    {
       const double v0 = sG.v[0], v1 = sG.v[1];
-      for (int q = 3 + tid; q < nl; q += nt) {
-        const double2 kq = sm.K[np * n + q];
-        sm.top[q] = sub_rank2(sm.top[q], ks0, kq);
-        sm.top[n + q] = sub_rank2(sm.top[n + q], ks1, kq);
-        sm.top[2 * n + q] = sub_rank2(sm.top[2 * n + q], ks2, kq);
-        const double2 ksq = b_ks(sm, n, np, q);
-        const int jj = (q - 3) >> 1;
-        if (q & 1) {
-          sm.diag[3 * jj] = sub_rank2(sm.diag[3 * jj], ksq, kq);
-          sm.diag[3 * jj + 1] = sub_rank2(sm.diag[3 * jj + 1], ksq, sm.K[np * n + q + 1]);
-        } else {
-          sm.diag[3 * jj + 2] = sub_rank2(sm.diag[3 * jj + 2], ksq, kq);
+      const int npair = (nl + 1) >> 1;
+      for (int c = warp; c < npair; c += nt / 32) {
+        const int qa = c, qb = nl - 1 - c;
+        const double2 ka = Ks[qa], kb = Ks[qb];
+        double* colA = Ps + tri(qa);
+        double* colB = Ps + tri(qb);
+        const int span = (qa == qb) ? qa + 1 : nl + 1;
+        for (int v = lane; v < span; v += 32) {
+          if (v <= qa) colA[v] = sub_rank2(colA[v], KSs[v], ka);
+          else { const int r = v - qa - 1; colB[r] = sub_rank2(colB[r], KSs[r], kb); }
         }
+      }
+      for (int q = 3 + tid; q < nl; q += nt) {                        /* :585-589  y += K * delta */
+        const double2 kq = Ks[q];
         double t = 0.0;
         axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
-        sm.y[q] = add_rn(sm.y[q], t);
+        ys[q] = add_rn(ys[q], t);
       }
       if (tid == 0) {
-        const double2 kk[3] = {sm.K[np * n], sm.K[np * n + 1], sm.K[np * n + 2]};
-        const double2 ks[3] = {ks0, ks1, ks2};
-        for (int r = 0; r < 3; ++r)
-          for (int q = r; q < 3; ++q) sm.top[r * n + q] = sub_rank2(sm.top[r * n + q], ks[r], kk[q]);
         double yn[3];
         for (int r = 0; r < 3; ++r) {
+          const double2 kk = Ks[r];
           double t = 0.0;
-          axpy_skip(t, kk[r].x, v0); axpy_skip(t, kk[r].y, v1);
+          axpy_skip(t, kk.x, v0); axpy_skip(t, kk.y, v1);
           yn[r] = add_rn(s_xpre[r], t);
         }
-        normalize_radian(yn[2]);
-        for (int r = 0; r < 3; ++r) { sm.y[r] = yn[r]; s_pose[r] = yn[r]; s_xpre[r] = yn[r]; }
-        sm.matched[jb] = 1; s_nmatch++;
+        normalize_radian(yn[2]);                                      /* :596-602 */
+        for (int r = 0; r < 3; ++r) { ys[r] = yn[r]; s_xpre[r] = yn[r]; }
+        matched[jb] = 1;                                              /* :501 */
         if (jout) jout[i] = jb;
       }
     }
-    np += 1;
+    nmatch += 1;
     __syncthreads();
   }
 
-  /* ---- the one deferred sweep of the scan: cold upper triangle -= pending terms ---- */
-  b_sweep(sm, Pf, n, nl, np);
-
   /* ---- Robot.cpp:702-716 ---- */
-  if (tid == 0) {
-    if (m == 0 || s_nmatch == 0) {
-      sm.y[0] = s_xpre[0]; sm.y[1] = s_xpre[1]; sm.y[2] = s_xpre[2];
-      double th = s_xpre[2];
-      normalize_radian(th);
-      s_pose[0] = s_xpre[0]; s_pose[1] = s_xpre[1]; s_pose[2] = th;
-    }
-    s_stop = 0;
+  const double ps0 = s_xpre[0], ps1 = s_xpre[1];
+  double ps2 = s_xpre[2];
+  if (m == 0 || nmatch == 0) {
+    if (tid == 0) { ys[0] = ps0; ys[1] = ps1; ys[2] = ps2; }
+    normalize_radian(ps2);
   }
   __syncthreads();
 
-  /* ---- augmentation in queue order, Robot.cpp:776-866 ---- */
-  const int ne = s_ne;
+  /* ---- augmentation in queue order, Robot.cpp:776-866: two new packed columns per line ---- */
   for (int e = 0; e < ne; ++e) {
+    if (L >= g.cap) { if (tid == 0) s_sticky |= EKF_STICKY_CAPACITY; break; }      /* the reference overruns y[] here (Q4) */
     const int l = 3 + 2 * L;
-    if (tid == 0) {
-      if (L >= g.cap) { atomicOr(&st->sticky, EKF_STICKY_CAPACITY); s_stop = 1; }
-      else {
-        const int i = sm.ext[e];
-        double alfa = z[2 * i], r = z[2 * i + 1];
-        const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
-        r = add_rn(r, add_rn(mul_rn(s_pose[0], cos(alfa)), mul_rn(s_pose[1], sin(alfa))));
-        alfa = add_rn(alfa, s_pose[2]);
-        const double cw = cos(alfa), sw = sin(alfa);
-        const double Gx[2][3] = {{0.0, 0.0, 1.0}, {cw, sw, 0.0}};
-        const double Gl[2][2] = {{1.0, 0.0}, {sub_rn(mul_rn(sm.y[1], cw), mul_rn(sm.y[0], sw)), 1.0}};
-        normalize_radian(alfa);
-        sm.y[l] = alfa; sm.y[l + 1] = r;
-        s_cs[0] = cw; s_cs[1] = sw;
-        double A[3][3];
-        for (int ii = 0; ii < 3; ++ii) for (int kk = ii; kk < 3; ++kk) { A[ii][kk] = sm.top[ii * n + kk]; A[kk][ii] = A[ii][kk]; }
-        double GP[2][3] = {{0, 0, 0}, {0, 0, 0}};
-        for (int k = 0; k < 3; ++k)
-          for (int ii = 0; ii < 2; ++ii) {
-            const double t = mul_rn(1.0, Gx[ii][k]);
-            if (t != 0.0) for (int jj = 0; jj < 3; ++jj) GP[ii][jj] = add_rn(GP[ii][jj], mul_rn(t, A[k][jj]));
-          }
-        double Pll[2][2];
-        for (int ii = 0; ii < 2; ++ii)
-          for (int jj = 0; jj < 2; ++jj) {
-            double t = 0.0;
-            for (int k = 0; k < 3; ++k) t = add_rn(t, mul_rn(GP[ii][k], Gx[jj][k]));
-            Pll[ii][jj] = add_rn(0.0, mul_rn(1.0, t));
-          }
-        double GR[2][2] = {{0, 0}, {0, 0}};
-        for (int k = 0; k < 2; ++k)
-          for (int ii = 0; ii < 2; ++ii) {
-            const double t = mul_rn(1.0, Gl[ii][k]);
-            if (t != 0.0) for (int jj = 0; jj < 2; ++jj) GR[ii][jj] = add_rn(GR[ii][jj], mul_rn(t, Rl[k * 2 + jj]));
-          }
-        for (int ii = 0; ii < 2; ++ii)
-          for (int jj = 0; jj < 2; ++jj) {
-            double t = 0.0;
-            for (int k = 0; k < 2; ++k) t = add_rn(t, mul_rn(GR[ii][k], Gl[jj][k]));
-            Pll[ii][jj] = add_rn(Pll[ii][jj], add_rn(0.0, mul_rn(1.0, t)));
-          }
-        sm.diag[3 * L] = Pll[0][0]; sm.diag[3 * L + 1] = Pll[0][1]; sm.diag[3 * L + 2] = Pll[1][1];
-      }
-    }
-    __syncthreads();
-    if (s_stop) break;
-    const double cw = s_cs[0], sw = s_cs[1];
-    for (int k = tid; k < l; k += nt) {                               /* :856-860: the new landmark's column block */
-      const double a0 = (k <= 0) ? sm.top[k * n + 0] : sm.top[0 * n + k];   /* P[0,k] through the upper storage */
-      const double a1 = (k <= 1) ? sm.top[k * n + 1] : sm.top[1 * n + k];
-      const double a2 = (k <= 2) ? sm.top[k * n + 2] : sm.top[2 * n + k];
+    const int i = ext[e];
+    double alfa = z[2 * i], rr = z[2 * i + 1];
+    rr = add_rn(rr, add_rn(mul_rn(ps0, cos(alfa)), mul_rn(ps1, sin(alfa))));          /* :792 (Q8) */
+    alfa = add_rn(alfa, ps2);                                                       /* :793 */
+    const double cw = cos(alfa), sw = sin(alfa);
+    double* c0 = Ps + tri(l);
+    double* c1 = Ps + tri(l + 1);
+    for (int k = tid; k < l; k += nt) {                               /* :856-860: P[k, l], P[k, l+1] */
+      const int tk = tri(k);
+      const double a0 = (k <= 0) ? Ps[k] : Ps[tk];                    /* P[0,k], P[1,k], P[2,k] through the upper storage */
+      const double a1 = (k <= 1) ? Ps[tri(1) + k] : Ps[tk + 1];
+      const double a2 = (k <= 2) ? Ps[tri(2) + k] : Ps[tk + 2];
       double r0 = 0.0, r1 = 0.0;
       axpy_skip(r1, cw, a0);
       axpy_skip(r1, sw, a1);
       axpy_skip(r0, 1.0, a2);
-      if (k <= 2) { sm.top[k * n + l] = r0; sm.top[k * n + l + 1] = r1; }
-      else { Pf[(size_t)k * n + l] = r0; Pf[(size_t)k * n + l + 1] = r1; }
+      c0[k] = r0; c1[k] = r1;
+    }
+    if (tid == 0) {
+      const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
+      const double Gx[2][3] = {{0.0, 0.0, 1.0}, {cw, sw, 0.0}};
+      const double Gl[2][2] = {{1.0, 0.0}, {sub_rn(mul_rn(ys[1], cw), mul_rn(ys[0], sw)), 1.0}};   /* :797-798 */
+      double an = alfa;
+      normalize_radian(an);                                                         /* :801 */
+      ys[l] = an; ys[l + 1] = rr;
+      double A[3][3];
+      for (int ii = 0; ii < 3; ++ii) for (int kk = ii; kk < 3; ++kk) { A[ii][kk] = Ps[tri(kk) + ii]; A[kk][ii] = A[ii][kk]; }
+      double GP[2][3] = {{0, 0, 0}, {0, 0, 0}};                                     /* :823 (NN) */
+      for (int k = 0; k < 3; ++k)
+        for (int ii = 0; ii < 2; ++ii) {
+          const double t = mul_rn(1.0, Gx[ii][k]);
+          if (t != 0.0) for (int jj = 0; jj < 3; ++jj) GP[ii][jj] = add_rn(GP[ii][jj], mul_rn(t, A[k][jj]));
+        }
+      double Pll[2][2];
+      for (int ii = 0; ii < 2; ++ii)                                                /* :827 (NT) */
+        for (int jj = 0; jj < 2; ++jj) {
+          double t = 0.0;
+          for (int k = 0; k < 3; ++k) t = add_rn(t, mul_rn(GP[ii][k], Gx[jj][k]));
+          Pll[ii][jj] = add_rn(0.0, mul_rn(1.0, t));
+        }
+      double GR[2][2] = {{0, 0}, {0, 0}};                                           /* :831 (NN) */
+      for (int k = 0; k < 2; ++k)
+        for (int ii = 0; ii < 2; ++ii) {
+          const double t = mul_rn(1.0, Gl[ii][k]);
+          if (t != 0.0) for (int jj = 0; jj < 2; ++jj) GR[ii][jj] = add_rn(GR[ii][jj], mul_rn(t, Rl[k * 2 + jj]));
+        }
+      for (int ii = 0; ii < 2; ++ii)                                                /* :835, :839 */
+        for (int jj = 0; jj < 2; ++jj) {
+          double t = 0.0;
+          for (int k = 0; k < 2; ++k) t = add_rn(t, mul_rn(GR[ii][k], Gl[jj][k]));
+          Pll[ii][jj] = add_rn(Pll[ii][jj], add_rn(0.0, mul_rn(1.0, t)));
+        }
+      c0[l] = Pll[0][0]; c1[l] = Pll[0][1]; c1[l + 1] = Pll[1][1];
     }
     L += 1;
     __syncthreads();
   }
 
   /* ---- reset, Robot.cpp:893-904 (dead entries are never read; downloads zero them) ---- */
-  if (L > g.cap - g.headroom) {
-    L = 0;
-    if (tid == 0) st->resets += 1;
-  }
-  __syncthreads();
+  int resets = 0;
+  if (L > g.cap - g.headroom) { L = 0; resets = 1; }
   const int nl_new = 3 + 2 * L;
-  for (int i = tid; i < 3 * n; i += nt) { const int r = i / n, q = i % n; if (q < nl_new) Pf[(size_t)r * n + q] = sm.top[i]; }
-  for (int j = tid; j < L; j += nt) {
-    const int a = 3 + 2 * j;
-    Pf[(size_t)a * n + a] = sm.diag[3 * j]; Pf[(size_t)a * n + a + 1] = sm.diag[3 * j + 1]; Pf[(size_t)(a + 1) * n + a + 1] = sm.diag[3 * j + 2];
+  const int ns_even = (ns + 1) & ~1;
+  for (int q = nl_new + tid; q < ns_even; q += nt) ys[q] = 0.0;      /* Robot::y is zero beyond the live part */
+  /* ---- state and covariance back to HBM: one bulk store each ---- */
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    b_bulk_store(Pf, Ps, (unsigned)(((tri(nl_new) + 1) & ~1) * 8));
+    b_bulk_store(yf, ys, (unsigned)(ns_even * 8));
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    st->L = L; st->pose[0] = ps0; st->pose[1] = ps1; st->pose[2] = ps2;
+    st->sticky = s_sticky;                        /* status reports this scan only */
+    st->resets += resets;
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
-  for (int i = tid; i < n; i += nt) yf[i] = (i < nl_new) ? sm.y[i] : 0.0;
-  if (tid == 0) { st->L = L; st->pose[0] = s_pose[0]; st->pose[1] = s_pose[1]; st->pose[2] = s_pose[2]; }
 }
 
 __global__ void k_batch_init(EkfBatchGeom g, double* Pg) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f < g.B) {
-    double* Pf = Pg + (size_t)f * g.n * g.n;
-    Pf[0] = 0.05; Pf[(size_t)g.n + 1] = 0.05; Pf[(size_t)2 * g.n + 2] = 0.0;      /* Robot.cpp:27-30 */
+    double* Pf = Pg + (size_t)f * g.pstride;
+    Pf[tri(0)] = 0.05; Pf[tri(1) + 1] = 0.05; Pf[tri(2) + 2] = 0.0;               /* Robot.cpp:27-30 */
   }
 }
 
@@ -405,7 +424,10 @@ struct ekf_batch {
   double* d_in; double* h_in;       /* [u (3B) | z (2 m B) | R (4 m B)] */
   int* d_jout; int* h_jout;
   EkfBatchState* h_st;
-  size_t smem_bytes;
+  double* h_P;                      /* pinned staging of one filter's packed covariance (ekf_batch_download) */
+  int L_ub;                         /* host-side upper bound of max_f L */
+  int L_exact;                      /* L_ub is exact: no device-resident scan was enqueued since the states were read back */
+  size_t smem_set;
   char err[256];
 };
 
@@ -414,39 +436,68 @@ namespace {
   do {                                                                                        \
     cudaError_t e_ = (call);                                                                  \
     if (e_ != cudaSuccess) {                                                                  \
-      snprintf(b->err, sizeof b->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      snprintf(b->err, sizeof b->err, "%s:%d %s: %s", "ekf_batch.cu", __LINE__, #call, cudaGetErrorString(e_)); \
       return EKF_ECUDA;                                                                       \
     }                                                                                         \
   } while (0)
 
-size_t batch_smem(int n, int cap, int m) { return batch_smem_bytes(n, cap, m); }
+const size_t kBatchSmemMax = 227 * 1024 - 256;      /* dynamic shared memory one CTA may ask for (static part: ~200 B) */
+
+/* live dimension a scan of m lines cannot exceed */
+int batch_ns(const ekf_batch* b, int m) {
+  long long lub = (long long)b->L_ub + m;
+  if (lub > b->g.cap) lub = b->g.cap;
+  return 3 + 2 * (int)lub;
+}
 
 int batch_ensure_m(ekf_batch* b, int m) {
   if (m <= b->max_m) return EKF_OK;
+  /* nothing is released before the larger scan is known to fit: a rejected call leaves the batch usable */
+  int cap = b->max_m > 0 ? b->max_m : 8;
+  while (cap < m) cap *= 2;
+  if ((size_t)batch_layout(b->g.n, b->g.cap, cap).bytes > kBatchSmemMax) cap = m;    /* do not reject m over the rounding */
+  if ((size_t)batch_layout(b->g.n, b->g.cap, cap).bytes > kBatchSmemMax) {
+    snprintf(b->err, sizeof b->err, "scan of %d lines does not fit shared memory", m);
+    return EKF_EINVAL;
+  }
   CUB(cudaStreamSynchronize(b->stream));
   cudaFree(b->d_in); cudaFree(b->d_jout); cudaFreeHost(b->h_in); cudaFreeHost(b->h_jout);
   b->d_in = 0; b->d_jout = 0; b->h_in = 0; b->h_jout = 0;
-  int cap = b->max_m > 0 ? b->max_m : 8;
-  while (cap < m) cap *= 2;
-  const size_t smem = batch_smem(b->g.n, b->g.cap, cap);
-  if (smem > 227 * 1024) { snprintf(b->err, sizeof b->err, "scan of %d lines does not fit shared memory", m); return EKF_EINVAL; }
-  b->max_m = cap;
+  b->max_m = 0;                       /* until every buffer below exists, the next call must come back here */
   const size_t B = b->g.B;
   CUB(cudaMalloc(&b->d_in, (3 + 6 * (size_t)cap) * B * sizeof(double)));
   CUB(cudaMallocHost(&b->h_in, (3 + 6 * (size_t)cap) * B * sizeof(double)));
   CUB(cudaMalloc(&b->d_jout, (size_t)cap * B * sizeof(int)));
   CUB(cudaMallocHost(&b->h_jout, (size_t)cap * B * sizeof(int)));
+  b->max_m = cap;
   return EKF_OK;
 }
 
 int batch_launch(ekf_batch* b, const double* d_u, int m, const double* d_z, const double* d_R, int* d_jout) {
-  const size_t smem = batch_smem(b->g.n, b->g.cap, m);
-  if (smem > b->smem_bytes) {
+  const int ns = batch_ns(b, m);
+  const size_t smem = (size_t)batch_layout(ns, b->g.cap, m).bytes;
+  if (smem > kBatchSmemMax) { snprintf(b->err, sizeof b->err, "scan of %d lines does not fit shared memory", m); return EKF_EINVAL; }
+  if (smem > b->smem_set) {
     CUB(cudaFuncSetAttribute(k_batch_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    b->smem_bytes = smem;
+    CUB(cudaFuncSetAttribute(k_batch_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    b->smem_set = smem;
   }
-  k_batch_scan<<<b->g.B, EKFB_THREADS, smem, b->stream>>>(b->g, b->d_y, b->d_P, b->d_st, d_u, d_z, d_R, m, d_jout);
+  k_batch_scan<<<b->g.B, EKFB_THREADS, smem, b->stream>>>(b->g, ns, b->d_y, b->d_P, b->d_st, d_u, d_z, d_R, m, d_jout);
   CUB(cudaGetLastError());
+  { long long lub = (long long)b->L_ub + m; b->L_ub = (int)(lub > b->g.cap ? b->g.cap : lub); }
+  b->L_exact = 0;
+  return EKF_OK;
+}
+
+/* after a synchronisation: the exact largest map of the batch (B small records) */
+int batch_refresh_bound(ekf_batch* b) {
+  if (b->L_exact) return EKF_OK;
+  const size_t B = b->g.B;
+  CUB(cudaMemcpyAsync(b->h_st, b->d_st, B * sizeof(EkfBatchState), cudaMemcpyDeviceToHost, b->stream));
+  CUB(cudaStreamSynchronize(b->stream));
+  int mx = 0;
+  for (size_t f = 0; f < B; ++f) if (b->h_st[f].L > mx) mx = b->h_st[f].L;
+  b->L_ub = mx; b->L_exact = 1;
   return EKF_OK;
 }
 }  // namespace
@@ -468,21 +519,27 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   EkfBatchGeom& g = b->g;
   g.B = n_filters; g.cap = cfg->capacity_lines; g.n = 3 + 2 * g.cap; g.headroom = cfg->reset_headroom;
   g.gate = cfg->gate; g.enc_noise = cfg->encoder_noise;
-  if (batch_smem(g.n, g.cap, 8) > 227 * 1024) {
-    snprintf(b->err, sizeof b->err, "capacity %d does not fit shared memory; use ekf_create", g.cap);
+  g.pstride = (tri(g.n) + 2) & ~1;
+  g.ystride = (g.n + 1) & ~1;
+  g.full_gates = (cfg->flags & EKF_FLAG_FULL_GATES) ? 1 : 0;
+  if (g.cap > 4096 || (size_t)batch_layout(g.n, g.cap, 8).bytes > kBatchSmemMax) {
+    snprintf(b->err, sizeof b->err, "capacity %d does not fit shared memory (a batch filter keeps its whole covariance on chip: "
+             "about 110 lines at most); use ekf_create", g.cap);
     return EKF_EINVAL;
   }
   CUB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-  const size_t B = g.B, n = g.n;
-  CUB(cudaMalloc(&b->d_y, B * n * sizeof(double)));
-  CUB(cudaMalloc(&b->d_P, B * n * n * sizeof(double)));
+  const size_t B = g.B;
+  CUB(cudaMalloc(&b->d_y, B * (size_t)g.ystride * sizeof(double)));
+  CUB(cudaMalloc(&b->d_P, B * (size_t)g.pstride * sizeof(double)));
   CUB(cudaMalloc(&b->d_st, B * sizeof(EkfBatchState)));
   CUB(cudaMallocHost(&b->h_st, B * sizeof(EkfBatchState)));
-  CUB(cudaMemsetAsync(b->d_y, 0, B * n * sizeof(double), b->stream));
-  CUB(cudaMemsetAsync(b->d_P, 0, B * n * n * sizeof(double), b->stream));
+  CUB(cudaMallocHost(&b->h_P, (size_t)g.pstride * sizeof(double)));
+  CUB(cudaMemsetAsync(b->d_y, 0, B * (size_t)g.ystride * sizeof(double), b->stream));
+  CUB(cudaMemsetAsync(b->d_P, 0, B * (size_t)g.pstride * sizeof(double), b->stream));
   CUB(cudaMemsetAsync(b->d_st, 0, B * sizeof(EkfBatchState), b->stream));
   k_batch_init<<<(g.B + 255) / 256, 256, 0, b->stream>>>(g, b->d_P);
   CUB(cudaGetLastError());
+  b->L_ub = 0; b->L_exact = 1;
   int rc = batch_ensure_m(b, 8);
   if (rc) return rc;
   CUB(cudaStreamSynchronize(b->stream));
@@ -494,7 +551,7 @@ int ekf_batch_destroy(ekf_batch* b) {
   cudaSetDevice(b->cfg.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_in); cudaFree(b->d_jout);
-  cudaFreeHost(b->h_in); cudaFreeHost(b->h_jout); cudaFreeHost(b->h_st);
+  cudaFreeHost(b->h_in); cudaFreeHost(b->h_jout); cudaFreeHost(b->h_st); cudaFreeHost(b->h_P);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
   return EKF_OK;
@@ -505,7 +562,6 @@ const char* ekf_batch_last_error(const ekf_batch* b) { return b ? b->err : "null
 int ekf_batch_scan_device(ekf_batch* b, const double* d_u, int m, const double* d_z, const double* d_R, int* d_j_out) {
   if (!b || !d_u || m < 0 || (m > 0 && (!d_z || !d_R))) return EKF_EINVAL;
   CUB(cudaSetDevice(b->cfg.device));
-  if (batch_smem(b->g.n, b->g.cap, m) > 227 * 1024) return EKF_EINVAL;
   return batch_launch(b, d_u, m, d_z, d_R, d_j_out);
 }
 
@@ -529,12 +585,14 @@ int ekf_batch_scan(ekf_batch* b, const double* u, int m, const double* z, const 
   CUB(cudaMemcpyAsync(b->h_st, b->d_st, B * sizeof(EkfBatchState), cudaMemcpyDeviceToHost, b->stream));
   CUB(cudaStreamSynchronize(b->stream));
   if (j_out && m > 0) memcpy(j_out, b->h_jout, (size_t)m * B * sizeof(int));
-  int status = EKF_OK;
+  int status = EKF_OK, mx = 0;
   for (size_t f = 0; f < B; ++f) {
     if (pose) memcpy(pose + 3 * f, b->h_st[f].pose, 3 * sizeof(double));
+    if (b->h_st[f].L > mx) mx = b->h_st[f].L;
     if (b->h_st[f].sticky & EKF_STICKY_CAPACITY) status = EKF_ECAPACITY;
     else if ((b->h_st[f].sticky & EKF_STICKY_SINGULAR) && status == EKF_OK) status = EKF_ESINGULAR;
   }
+  b->L_ub = mx; b->L_exact = 1;       /* the states just came back: the bound is exact again */
   return status;
 }
 
@@ -542,26 +600,28 @@ int ekf_batch_sync(ekf_batch* b) {
   if (!b) return EKF_EINVAL;
   CUB(cudaSetDevice(b->cfg.device));
   CUB(cudaStreamSynchronize(b->stream));
-  return EKF_OK;
+  return batch_refresh_bound(b);
 }
 
 int ekf_batch_download(ekf_batch* b, int filter, double* y, double* P, int* n_lines, double pose[3]) {
   if (!b || filter < 0 || filter >= b->g.B) return EKF_EINVAL;
   CUB(cudaSetDevice(b->cfg.device));
   const size_t n = b->g.n;
-  if (y) CUB(cudaMemcpyAsync(y, b->d_y + (size_t)filter * n, n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-  if (P) CUB(cudaMemcpyAsync(P, b->d_P + (size_t)filter * n * n, n * n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (y) CUB(cudaMemcpyAsync(y, b->d_y + (size_t)filter * b->g.ystride, n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (P) CUB(cudaMemcpyAsync(b->h_P, b->d_P + (size_t)filter * b->g.pstride, (size_t)tri((int)n) * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
   CUB(cudaMemcpyAsync(b->h_st, b->d_st + filter, sizeof(EkfBatchState), cudaMemcpyDeviceToHost, b->stream));
   CUB(cudaStreamSynchronize(b->stream));
+  b->L_exact = 0;                     /* h_st[0] now holds one filter's record, not the batch's */
   if (n_lines) *n_lines = b->h_st[0].L;
   if (pose) memcpy(pose, b->h_st[0].pose, 3 * sizeof(double));
-  /* the device keeps the upper triangle of the live part: mirror it and zero the rest (Robot::P_t0 layout) */
+  /* the device keeps the upper triangle of the live part, packed by columns: unpack, mirror, zero the rest
+   * (Robot::P_t0 layout) */
   const size_t nl = 3 + 2 * (size_t)b->h_st[0].L;
   if (P)
     for (size_t r = 0; r < n; ++r)
       for (size_t q = 0; q < n; ++q) {
         if (r >= nl || q >= nl) P[r * n + q] = 0.0;
-        else if (q < r) P[r * n + q] = P[q * n + r];
+        else { const size_t lo = r < q ? r : q, hi = r < q ? q : r; P[r * n + q] = b->h_P[hi * (hi + 1) / 2 + lo]; }
       }
   if (y) for (size_t r = nl; r < n; ++r) y[r] = 0.0;
   return EKF_OK;

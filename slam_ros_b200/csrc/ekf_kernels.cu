@@ -627,6 +627,13 @@ __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_
       TS(10);
       group_sync();
       TS(11);
+      if (*(volatile int*)&st->sticky & EKF_STICKY_XCHG) {
+        /* a peer never arrived: the gathered slices are stale.  No gain, no update: the remaining lines of the scan are
+         * dropped (sane counters for the end-of-scan kernels) and the host marks the filter poisoned (EKF_ENCCL) */
+        if (gtid == 0) for (int i = line; i < line1; ++i) { b.jout[i] = -1; b.pidx[i + 1] = nm; b.eidx[i + 1] = ne; }
+        have_prev = false;
+        break;
+      }
       /* part 2: every rank forms the full K, K S (replicated) from the gathered slices */
       const double* cA = xchg_col(pe, g, g.rank, xpar, 0);
       const double* cB = xchg_col(pe, g, g.rank, xpar, 1);

@@ -17,6 +17,7 @@ EKF_FLAG_EAGER_SWEEP = 1
 EKF_FLAG_SWEEP_DIRECT = 2
 EKF_FLAG_PER_LINE_KERNELS = 4
 EKF_FLAG_NO_OVERLAP = 8
+EKF_FLAG_FULL_GATES = 16
 _STATUS = {0: "OK", 1: "EINVAL", 2: "ECAPACITY", 3: "ESINGULAR", 4: "ECUDA", 5: "ENCCL", 6: "ENOMEM", 7: "ESTATE"}
 
 _dp = C.POINTER(C.c_double)
@@ -346,10 +347,10 @@ def nccl_unique_id():
 class EkfBatch:
     """B independent filters on one device (Monte-Carlo batch); one thread block per filter."""
 
-    def __init__(self, n_filters, capacity_lines=50, gate=0.4, encoder_noise=0.024, reset_headroom=10, device=0):
+    def __init__(self, n_filters, capacity_lines=50, gate=0.4, encoder_noise=0.024, reset_headroom=10, device=0, flags=0):
         self._lib = load_library()
         self.cfg = default_config(capacity_lines=capacity_lines, gate=gate, encoder_noise=encoder_noise,
-                                  reset_headroom=reset_headroom, device=device)
+                                  reset_headroom=reset_headroom, device=device, flags=flags)
         self._h = C.c_void_p()
         rc = self._lib.ekf_batch_create(C.byref(self._h), C.byref(self.cfg), int(n_filters))
         if rc != EKF_OK:
