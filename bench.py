@@ -52,6 +52,28 @@ WORKLOADS = {
 }
 
 
+def static_config(wl_name, world, sharded=False, mc_per_gpu=0):
+    """The `config` object both arms print (own arm and --impl reference): what is measured, not how it went.
+    Run-specific facts (matches per step, exchange path, ...) go to the own arm's `run` object."""
+    w = WORKLOADS[wl_name]
+    N, m = w["N"], w["m"]
+    if wl_name == "mc":
+        Bt = mc_per_gpu * world if mc_per_gpu > 0 else w["filters"]
+        return {"workload": w["desc"], "landmarks": N, "lines_per_scan": m, "capacity_lines": N + w["headroom"],
+                "filters_total": Bt, "parallelism": "independent filters dealt round-robin over %d GPU(s), no collective" % world,
+                "l2": "every filter's state is touched once per step; batch state %.0f MB (packed upper triangles) against 126 MB L2; "
+                      "no flush between steps" % (Bt * (3 + 2 * N) * (4 + 2 * N) / 2 * 8 / 1e6)}
+    if wl_name in ("room", "extract"):
+        return {"workload": w["desc"]}
+    n = 3 + 2 * N
+    par = ("one filter, P row-sharded over %d GPUs" % world) if sharded else ("%d independent filter(s), one per GPU, no collective" % world)
+    ws = 8.0 * n * (n + 1) / 2 / 1e9
+    l2 = ("per-step working set %.2f GB read + %.2f GB written >> 126 MB L2: no flush needed" % (ws, ws)) if ws > 0.5 else \
+         ("P (%.0f MB) fits the 126 MB L2: a latency-bound configuration, no flush between steps (stated, not an HBM-roofline line)" % (ws * 1e3))
+    return {"workload": w["desc"], "landmarks": N, "state_dim": n, "lines_per_scan": m, "capacity_lines": N + w["headroom"],
+            "parallelism": par, "l2": l2, "seed": "1 (replicas: 1 + rank)"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -121,8 +143,14 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the structured oracle (port of Robot::localize), all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_run(workload, steps, warmup, budget_s, threads=None):
-    """Times the CPU restatement of the reference on the same workload.  Returns (steps_per_s, info)."""
+def cpu_run(workload, steps, warmup, budget_s, threads=None, n_filters=1, extra_legs=False):
+    """Times the CPU restatement of the reference (oracle/ekf_oracle.cpp) on the same workload.  Returns (steps/s, info).
+
+    threads: OpenMP threads of the n^2 row sweeps (None = all host threads; the reference itself has no threads).
+    n_filters > 1: the replicas workload at N GPUs -- the host runs the same N independent filters one after the other
+    (each with all threads), value = aggregate steps/s over all of them.
+    extra_legs: also time ONE step single-threaded (north_star: "reference single-threaded GSL path") and ONE step of
+    the -O0 build single-threaded (the reference's CMakeLists sets no optimisation flag), continuing from the same map."""
     from oracle.oracle import StructuredOracle, build
     from slam_ros_b200 import scenario as sc
     build()
@@ -130,8 +158,8 @@ def cpu_run(workload, steps, warmup, budget_s, threads=None):
     N, m = w["N"], w["m"]
     threads = threads or (os.cpu_count() or 1)
     if workload == "mc":
-        # independent filters: time a bounded number of filters for `steps` scans each, one thread each is
-        # the natural CPU mapping; we time filters sequentially on one thread and report filter-steps/s x 1
+        # independent filters: one 50-landmark filter is timed on one thread (the natural CPU mapping is a filter per
+        # core); batch steps/s = filter-steps/s / filters
         so = StructuredOracle(N + w["headroom"], threads=1)
         scn = sc.map_scenario(N, warmup + steps, m=m, seed=1000)
         so.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
@@ -146,36 +174,62 @@ def cpu_run(workload, steps, warmup, budget_s, threads=None):
                 break
         dt = time.perf_counter() - t0
         fps = done / dt                         # filter-steps per second on one core
-        return fps / w["filters"], {"kind": "port", "cores": 1, "value": fps / w["filters"],
+        cores = os.cpu_count() or 1
+        return fps / w["filters"], {"kind": "port", "cores": 1, "value": fps / w["filters"], "unit": "steps/s",
+                                    "all_cores_estimate": {"value": fps * cores / w["filters"], "cores": cores,
+                                                           "note": "ESTIMATE: one filter per core, perfect scaling (not measured)"},
                                     "sample": "%d scans of ONE 50-landmark filter on one thread; batch steps/s = filter-steps/s / %d filters (the reference has no threads)" % (done, w["filters"])}
-    so = StructuredOracle(N + w["headroom"], threads=threads)
-    scn = sc.map_scenario(N, warmup + steps, m=m, seed=1)
-    so.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
-    t_w = time.perf_counter()
-    for s in range(min(warmup, 1)):
-        so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
-    t_w = time.perf_counter() - t_w
-    t0 = time.perf_counter()
-    done = 0
-    for s in range(min(warmup, 1), min(warmup, 1) + steps):
-        so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    val = done / dt
+    total_done, total_dt = 0, 0.0
+    per_filter_budget = budget_s / max(n_filters, 1)
+    legs = {}
+    for fi in range(n_filters):
+        so = StructuredOracle(N + w["headroom"], threads=threads)
+        scn = sc.map_scenario(N, warmup + steps + 2, m=m, seed=1 + fi)
+        so.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
+        for s in range(min(warmup, 1)):
+            so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        t0 = time.perf_counter()
+        done = 0
+        for s in range(min(warmup, 1), min(warmup, 1) + steps):
+            so.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+            done += 1
+            if time.perf_counter() - t0 > per_filter_budget:
+                break
+        total_dt += time.perf_counter() - t0
+        total_done += done
+        if extra_legs and fi == 0:
+            s1 = min(warmup, 1) + done
+            so._lib.ekfo_set_threads(so._h, 1)
+            t1 = time.perf_counter()
+            so.scan(scn["u"][s1], scn["z"][s1], scn["R"][s1])
+            legs["single_thread_O2"] = {"value": 1.0 / (time.perf_counter() - t1), "unit": "steps/s", "cores": 1,
+                                        "sample": "1 step, g++ -O2, one thread: the reference's own threading (none)"}
+            try:
+                o0 = StructuredOracle(N + w["headroom"], threads=1, opt0=True)
+                o0.adopt(so)
+                t1 = time.perf_counter()
+                o0.scan(scn["u"][s1 + 1], scn["z"][s1 + 1], scn["R"][s1 + 1])
+                legs["single_thread_O0"] = {"value": 1.0 / (time.perf_counter() - t1), "unit": "steps/s", "cores": 1,
+                                            "sample": "1 step, g++ -O0 (the reference's CMakeLists.txt:18 sets no optimisation flag), one thread"}
+                o0.close()
+            except Exception as e:   # noqa: BLE001
+                legs["single_thread_O0"] = {"unavailable": str(e)[:120]}
+        so.close()
+    val = total_done / total_dt
     n = 3 + 2 * N
     # the literal Robot::localize spends 7.1 ms in its dense n^3 prediction dgemms and 0.45 ms per
     # matched line in n^2 passes at n = 203 (LINESIZE = 100, this container's host); scaled, NOT measured
     # + ~0.05 ms per (line, landmark) gate pair; check: the LINESIZE = 1000 build of the reference itself measures 12.7 s
     # per step at n = 2003, m = 8 (bench.py --workload 1k), this formula gives 11.1 s
     lit_ms = 7.1 * (n / 203.0) ** 3 + m * 0.45 * (n / 203.0) ** 2 + m * N * 0.05 * (n / 203.0)
-    info = {"kind": "port", "cores": so.threads, "value": val, "unit": "steps/s",
+    info = {"kind": "port", "cores": threads, "value": val, "unit": "steps/s",
             "literal_reference_extrapolated": "EXTRAPOLATED, not measured: the reference's own dense GSL path would need about "
                                               "%.3g s per step at n = %d (2 n^3 MACs per prediction dgemm)" % (lit_ms / 1e3, n),
-            "sample": "%d full steps (of %d requested) of the same workload on the structured oracle (oracle/ekf_oracle.cpp, "
-                      "the runtime-capacity restatement of Robot::localize; OpenMP over the %d host threads for the n^2 "
-                      "row sweeps; the literal reference is fixed at LINESIZE=100 and cannot run this size)" % (done, steps, so.threads)}
+            "sample": "%d full steps of the same workload%s on the structured oracle (oracle/ekf_oracle.cpp, the runtime-capacity "
+                      "restatement of Robot::localize, bitwise equal to the literal reference where that can run; g++ -O2, OpenMP over "
+                      "%d host threads for the n^2 row sweeps; the literal reference is fixed at LINESIZE=100 and cannot run this size)"
+                      % (total_done, (" (%d independent filters one after the other, aggregate rate)" % n_filters) if n_filters > 1 else "", threads)}
+    info.update(legs)
     return val, info
 
 
@@ -354,10 +408,11 @@ def run_reference_arm(args, rank, world):
         print(json.dumps({"impl": "reference", "metric": "line-extraction scans/s (361 beams -> (alfa, r, C_AR, end points) per line)",
                           "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic", "config": {"workload": w["desc"], "beams": 361}, "cpu_baseline": info,
+                          "data": "synthetic", "config": static_config("extract", args.gpus), "cpu_baseline": info,
                           "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}), flush=True)
         return
+    sharded = args.workload == "40k" and args.gpus > 1
     if args.workload == "1k" and args.lines == 0 and _have_literal_1k():
         val, info = literal_1k_run(min(args.steps, 8), budget_s=150.0)
     elif args.workload == "room":
@@ -366,12 +421,16 @@ def run_reference_arm(args, rank, world):
             print(json.dumps({"impl": "reference", "unavailable": info["unavailable"]}), flush=True)
             return
     else:
-        val, info = cpu_run(args.workload, args.steps, args.warmup, budget_s=150.0)
+        # replicas at N GPUs = N independent filters: the host runs the same N filters (aggregate rate), so that the
+        # driver's ratio compares N GPUs with this one host on the same job
+        nf = args.gpus if (args.workload in ("10k", "1k", "40k") and not sharded) else 1
+        val, info = cpu_run(args.workload, args.steps, args.warmup, budget_s=150.0, n_filters=nf)
     line = {
         "impl": "reference", "metric": "EKF predict+update steps/s at N landmarks", "value": val, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "landmarks": w["N"], "lines_per_scan": w["m"]},
+        "higher_is_better": True, "scaling": "strong" if (sharded or (args.workload == "mc" and args.mc_per_gpu == 0)) else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": static_config(args.workload, args.gpus, sharded, args.mc_per_gpu),
         "cpu_baseline": info,
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -382,20 +441,33 @@ def run_reference_arm(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------
-def run_single_or_replicas(args, rank, world, local, sharded):
+def _dist_reduce_sum(dev):
+    """Sum of per-rank partial read-outs (a row-sharded filter's ranks each emit what they own)."""
+    import torch
+    import torch.distributed as dist
+
+    def red(a):
+        t = torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+    return red
+
+
+def run_filter(wl_name, K, W, rank, world, local, sharded, parity_name=None, exchange_pref="fused", e2e_leg=True):
+    """One single-filter workload end to end on this rank's GPU (replica, or this rank's shard of a row-sharded filter).
+    parity_name: replay the committed oracle fixture tests/golden/oracle_<name>.npz first (same seeded sequence: the
+    timing legs then continue from where the fixture ends).  Returns a dict of raw measurements (rank 0: complete)."""
     import torch
     import torch.distributed as dist
     from slam_ros_b200 import EkfFilter, scenario as sc
     from slam_ros_b200.ekf import nccl_unique_id
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import replay as rp
 
-    w = WORKLOADS[args.workload]
+    w = WORKLOADS[wl_name]
     N, m = w["N"], w["m"]
-    K, W = args.steps, args.warmup
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
-
     shard = None
     if sharded and world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -404,23 +476,44 @@ def run_single_or_replicas(args, rank, world, local, sharded):
         dist.broadcast(uid, 0)
         shard = (rank, world, bytes(uid.cpu().tolist()))
     seed = 1 if (sharded or world == 1) else 1 + rank
-    total_steps = W + K + K            # device-resident leg, then the host-buffer (e2e) leg
+    gold = rp.load_golden(parity_name) if parity_name else None
+    if gold is not None and (int(gold["N"]) != N or int(gold["m"]) != m or int(gold["cap"]) != N + w["headroom"] or seed != int(gold["seed"])):
+        gold = None
+    S0 = int(gold["steps"]) if gold is not None else 0
+    total_steps = S0 + W + K + (K if e2e_leg else 0)
     scn = sc.map_scenario(N, total_steps, m=m, seed=seed)
     f = EkfFilter(capacity_lines=N + w["headroom"], device=local, shard=shard)
     exchange = None
     if shard is not None:
         # fused exchange over NVLink peer memory inside the line-loop kernel (EKF_SHARD_NCCL=1 keeps the NCCL path)
         from slam_ros_b200.parallel import connect_shards
-        fused = os.environ.get("EKF_SHARD_NCCL", "0") != "1" and connect_shards(f, dev)
+        fused = exchange_pref == "fused" and os.environ.get("EKF_SHARD_NCCL", "0") != "1" and connect_shards(f, dev)
         exchange = "in-kernel NVLink stores (CUDA IPC peer memory)" if fused else "ncclAllReduce per matched line"
+    t_seed = time.perf_counter()
     rc, j, pose = f.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
     assert rc == 0 and f.lines == N, (rc, f.lines)
+    t_seed = time.perf_counter() - t_seed
+
+    parity = None
+    if gold is not None:
+        sub = {k: (v[:S0] if k in ("u", "z", "R") else v) for k, v in scn.items()}
+        r = rp.replay(f, gold, sub, reduce_sum=_dist_reduce_sum(dev) if shard is not None else None)
+        parity = {"fixture": "tests/golden/oracle_%s.npz (CPU oracle, made by tests/golden/make_golden_fullsize.py)" % parity_name,
+                  "steps": r["steps"], "checkpoints": r["checkpoints"], "assoc_exact": r["assoc_exact"],
+                  "first_assoc_mismatch": r["first_assoc_mismatch"], "pose_max_abs_err": r["pose_max_abs_err"],
+                  "P_rel_err": r["P_rel_err"], "trace_rel_err": r["trace_rel_err"], "sumsq_rel_err": r["sumsq_rel_err"],
+                  "y_rel_err": r["y_rel_err"], "oracle_min_gate_margin": r["oracle_min_gate_margin"],
+                  "passed_1e-9": rp.passed(r), "exchange": exchange}
+    if K <= 0:
+        f.close()
+        return {"parity": parity, "exchange": exchange, "seed_s": t_seed}
 
     # ---- leg 1: inputs resident in HBM --------------------------------------------------------
-    d_u = torch.tensor(scn["u"], dtype=torch.float64, device=dev)
-    d_z = torch.tensor(scn["z"], dtype=torch.float64, device=dev)
-    d_R = torch.tensor(scn["R"], dtype=torch.float64, device=dev)
-    d_j = torch.full((total_steps, m), -7, dtype=torch.int32, device=dev)
+    lo = S0
+    d_u = torch.tensor(scn["u"][lo:], dtype=torch.float64, device=dev)
+    d_z = torch.tensor(scn["z"][lo:], dtype=torch.float64, device=dev)
+    d_R = torch.tensor(scn["R"][lo:], dtype=torch.float64, device=dev)
+    d_j = torch.full((total_steps - lo, m), -7, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
     def dev_step(s):
@@ -450,58 +543,161 @@ def run_single_or_replicas(args, rank, world, local, sharded):
     pose_dev, L_dev, st_dev = f.state()
 
     # ---- leg 2: end to end through the host-buffer call -------------------------------------------
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e2e_matched = 0
-    for s in range(W + K, W + 2 * K):
-        rc, jj, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
-        e2e_matched += int((jj >= 0).sum())
-    f.sync()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms, e2e_matched = float("nan"), 0
+    if e2e_leg:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(lo + W + K, lo + W + 2 * K):
+            rc, jj, pose = f.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+            e2e_matched += int((jj >= 0).sum())
+        f.sync()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+    f.close()
+    del d_u, d_z, d_R, d_j
+    torch.cuda.empty_cache()
 
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms if e2e_leg else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    filters = 1 if sharded else world
-    value = filters * K / (ms_max / 1e3)
-    e2e_value = filters * K / (e2e_ms_max / 1e3)
+    return {"ms_max": float(t[0]), "e2e_ms_max": float(t[1]) if e2e_leg else None, "ms": ms, "prof": prof, "lprof": lprof, "matched": matched,
+            "e2e_matched": e2e_matched, "L": L_dev, "clk": clk, "exchange": exchange, "parity": parity, "seed": seed, "seed_s": t_seed,
+            "N": N, "m": m}
 
-    if rank != 0:
-        return None
-    n = 3 + 2 * L_dev
+
+def sweep_roofline(r, K, world, sharded):
+    """The covariance sweep's roofline entry from the CUDA-event taps of the timed region (rank 0's launches)."""
+    n = 3 + 2 * r["L"]
     peak, peak_src = measured_peaks()
+    prof, lprof = r["prof"], r["lprof"]
     sweep_ms = prof["sweep_ms"] / max(prof["sweeps"], 1)
     # algorithmic bytes of one sweep: upper triangle read + written once, plus K and KS of the folded
     # terms (SURVEY 8d).  Row-sharded: each rank sweeps 1/world of the triangle (rank 0's share is timed).
-    mean_terms = matched / max(K, 1)
+    mean_terms = r["matched"] / max(K, 1)
     bytes_per_sweep = (8.0 * n * (n + 1) + 32.0 * n * mean_terms) / (world if sharded else 1)
     achieved = bytes_per_sweep / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    static_traffic = (r["N"] == 10000 and not sharded and r["m"] == 8)
+    return {"bound": "hbm", "kernel": "k_sweep_quad (P -= (K S) K' over the upper triangle; TMA + mbarrier ring, 8x4 register tiles, runs under the next scan's line loop)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+            "launch_ms": sweep_ms, "launches_timed": prof["sweeps"], "algorithmic_bytes_per_launch": bytes_per_sweep,
+            "sweep_share_of_step": (prof["sweep_ms"] / r["ms"]) if r["ms"] > 0 else None,
+            "line_stream_ms_per_step": (lprof["line_ms"] / lprof["scans"]) if lprof["scans"] else None,
+            "traffic": 3.167e9 if static_traffic else None,
+            "traffic_source": ("STATIC, not re-measured by this run (ncu cannot run inside the bench): dram__bytes_read.sum + "
+                               "dram__bytes_write.sum per launch from one ncu --set full capture of the same kernel and workload, "
+                               "profiles/r1_ncu_sweep_quad.csv (1.615 GB read + 1.552 GB written)") if static_traffic else None}
+
+
+def run_single_or_replicas(args, rank, world, local, sharded, wl_name=None, parity_name=None):
+    import torch
+    import torch.distributed as dist
+    wl_name = wl_name or args.workload
+    w = WORKLOADS[wl_name]
+    K, W = args.steps, args.warmup
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    r = run_filter(wl_name, K, W, rank, world, local, sharded, parity_name=parity_name)
+    if rank != 0:
+        return None
+    filters = 1 if sharded else world
+    value = filters * K / (r["ms_max"] / 1e3)
+    e2e_value = filters * K / (r["e2e_ms_max"] / 1e3)
+    m = w["m"]
     line = {
         "metric": "EKF predict+update steps/s at N landmarks", "value": value, "unit": "steps/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": r["ms_max"] / K, "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "landmarks": N, "state_dim": n, "lines_per_scan": m,
-                   "matched_per_step": mean_terms, "parallelism": ("row-sharded P x%d" % world) if sharded else ("independent filters x%d" % world),
-                   "exchange": exchange,
-                   "l2": "per-step working set %.2f GB read + %.2f GB written >> 126 MB L2: no flush needed" % (8.0 * n * (n + 1) / 2 / 1e9, 8.0 * n * (n + 1) / 2 / 1e9),
-                   "seed": seed},
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_quad (P -= (K S) K' over the upper triangle; TMA + mbarrier ring, 8x4 register tiles, runs under the next scan's line loop)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "launch_ms": sweep_ms, "launches_timed": prof["sweeps"], "algorithmic_bytes_per_launch": bytes_per_sweep,
-                     "sweep_share_of_step": (prof["sweep_ms"] / ms) if ms > 0 else None,
-                     "line_stream_ms_per_step": (lprof["line_ms"] / lprof["scans"]) if lprof["scans"] else None,
-                     "traffic": 3.167e9 if (N == 10000 and not sharded and m == 8) else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r1_ncu_sweep_quad.csv (10k workload, 8 terms: 1.615 GB read + 1.552 GB written)"},
+        "config": static_config(wl_name, world, sharded),
+        "run": {"matched_per_step": r["matched"] / max(K, 1), "landmarks_at_end": r["L"], "exchange": r["exchange"], "filters": filters,
+                "seed_scan_s": r["seed_s"]},
+        "roofline": sweep_roofline(r, K, world, sharded),
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": (6 + 2 * m) * 8 + 4 * m * 8,
-                "d2h_bytes_per_step": 4 * m + 128, "ms_per_step": e2e_ms_max / K, "matched_per_step": e2e_matched / max(K, 1)},
-        "gpu_launches": prof["launches"],
-        "clocks": clk,
+                "d2h_bytes_per_step": 4 * m + 128, "ms_per_step": r["e2e_ms_max"] / K, "matched_per_step": r["e2e_matched"] / max(K, 1)},
+        "gpu_launches": r["prof"]["launches"],
+        "clocks": r["clk"],
     }
+    if r["parity"] is not None:
+        line["parity"] = r["parity"]
     return line
+
+
+def run_extras(args, rank, world, local):
+    """Driver-visible evidence for the two multi-GPU modes north_star names, attached to the default line as `extra`:
+    (i) configs[4], 40k landmarks: ONE filter (row-sharded over the ranks when N > 1, un-sharded at N = 1 so that the
+    strong-scaling efficiency can be computed), with the 100-step parity prefix against the committed oracle fixture;
+    (ii) configs[3], Monte-Carlo 4096 x 50: the batch split over the ranks (strong) and 4096 filters per GPU (weak);
+    (iii) row-sharded parity at 3300 landmarks for BOTH exchange paths (NCCL, fused NVLink) against the oracle fixture."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    extra = {}
+    K, W = args.steps, args.warmup
+    # (i)
+    try:
+        free_gb = torch.cuda.mem_get_info(local)[0] / 1e9
+        need_gb = 2 * 8.0 * 82176.0 ** 2 / 1e9 / world + 4
+        if free_gb < need_gb:
+            extra["row_sharded_40k"] = {"skipped": "needs %.0f GB of HBM per GPU, %.0f free" % (need_gb, free_gb)}
+        else:
+            r = run_filter("40k", K, W, rank, world, local, sharded=(world > 1), parity_name="40k")
+            if rank == 0:
+                rf = sweep_roofline(r, K, world, world > 1)
+                extra["row_sharded_40k"] = {
+                    "value": K / (r["ms_max"] / 1e3), "unit": "steps/s", "ms_per_step": r["ms_max"] / K, "scaling": "strong",
+                    "config": static_config("40k", world, world > 1), "exchange": r["exchange"],
+                    "e2e": {"value": K / (r["e2e_ms_max"] / 1e3), "unit": "steps/s", "ms_per_step": r["e2e_ms_max"] / K},
+                    "sweep_roofline_per_gpu": {k: rf[k] for k in ("achieved", "peak", "unit", "frac", "launch_ms", "launches_timed",
+                                                                   "algorithmic_bytes_per_launch", "sweep_share_of_step")},
+                    "line_stream_ms_per_step": rf["line_stream_ms_per_step"],
+                    "bound_by": ("sweep" if rf["launch_ms"] >= (rf["line_stream_ms_per_step"] or 0.0) else "line loop"),
+                    "matched_per_step": r["matched"] / max(K, 1), "seed_scan_s": r["seed_s"], "parity": r["parity"]}
+    except Exception as e:   # noqa: BLE001
+        extra["row_sharded_40k"] = {"error": repr(e)[:300]}
+    if world > 1:
+        dist.barrier()
+    # (ii)
+    try:
+        a = copy.copy(args)
+        a.steps = max(K, 50)
+        mc = {}
+        a.mc_per_gpu = 0
+        ln = run_monte_carlo(a, rank, world, local)
+        if rank == 0:
+            mc["strong_4096_total"] = {k: ln[k] for k in ("value", "unit", "ms_per_step", "scaling", "e2e")}
+            mc["strong_4096_total"].update(filters_per_gpu=ln["run"]["filters_per_gpu"], filter_steps_per_s=ln["run"]["filter_steps_per_s"],
+                                           roofline_frac=ln["roofline"]["frac"])
+        if world > 1:
+            a.mc_per_gpu = 4096
+            ln = run_monte_carlo(a, rank, world, local)
+            if rank == 0:
+                mc["weak_4096_per_gpu"] = {k: ln[k] for k in ("value", "unit", "ms_per_step", "scaling", "e2e")}
+                mc["weak_4096_per_gpu"].update(filters_per_gpu=ln["run"]["filters_per_gpu"], filter_steps_per_s=ln["run"]["filter_steps_per_s"],
+                                               roofline_frac=ln["roofline"]["frac"])
+        extra["mc_4096x50"] = mc
+    except Exception as e:   # noqa: BLE001
+        extra["mc_4096x50"] = {"error": repr(e)[:300]}
+    if world > 1:
+        dist.barrier()
+    # (iii)
+    if world < 2:
+        extra["sharded_parity"] = {"skipped": "one process per GPU: needs >= 2 GPUs (the un-sharded replay of the same fixtures is "
+                                              "tests/test_gpu_fullsize.py and, for 40k, row_sharded_40k.parity above)"}
+    else:
+        sp = {}
+        WORKLOADS["3300"] = dict(N=3300, m=8, headroom=64, desc="row-sharded parity case, 3300 landmarks (n = 6603: overlapped path)")
+        for mode in ("nccl", "fused"):
+            try:
+                r = run_filter("3300", 0, 0, rank, world, local, sharded=True, parity_name="3300", exchange_pref=mode, e2e_leg=False)
+                sp[mode] = r["parity"]
+            except Exception as e:   # noqa: BLE001
+                sp[mode] = {"error": repr(e)[:300]}
+            dist.barrier()
+        extra["sharded_parity"] = sp
+    return extra if rank == 0 else None
 
 
 def run_monte_carlo(args, rank, world, local):
@@ -528,14 +724,15 @@ def run_monte_carlo(args, rank, world, local):
     reps = (B + len(rng_scn) - 1) // len(rng_scn)
     seed_z = np.concatenate([np.stack([s["seed_z"] for s in rng_scn])] * reps)[:B]
     seed_R = np.concatenate([np.stack([s["seed_R"] for s in rng_scn])] * reps)[:B]
-    U = np.concatenate([np.stack([s["u"] for s in rng_scn])] * reps)[:B]            # (B, total, 3)
-    Z = np.concatenate([np.stack([s["z"] for s in rng_scn])] * reps)[:B]            # (B, total, m, 2)
-    Rr = np.concatenate([np.stack([s["R"] for s in rng_scn])] * reps)[:B]
+    # step-major host arrays: one step's inputs of the whole batch are contiguous (what a caller hands to ekf_batch_scan)
+    U = np.ascontiguousarray(np.concatenate([np.stack([s["u"] for s in rng_scn])] * reps)[:B].transpose(1, 0, 2))          # (total, B, 3)
+    Z = np.ascontiguousarray(np.concatenate([np.stack([s["z"] for s in rng_scn])] * reps)[:B].transpose(1, 0, 2, 3))       # (total, B, m, 2)
+    Rr = np.ascontiguousarray(np.concatenate([np.stack([s["R"] for s in rng_scn])] * reps)[:B].transpose(1, 0, 2, 3))
     bt = EkfBatch(B, capacity_lines=cap, device=local)
     rc, j, pose = bt.scan(np.zeros((B, 3)), seed_z, seed_R)
-    d_u = torch.tensor(np.ascontiguousarray(U.transpose(1, 0, 2)), dtype=torch.float64, device=dev)        # (total, B, 3)
-    d_z = torch.tensor(np.ascontiguousarray(Z.transpose(1, 0, 2, 3)), dtype=torch.float64, device=dev)     # (total, B, m, 2)
-    d_R = torch.tensor(np.ascontiguousarray(Rr.transpose(1, 0, 2, 3)), dtype=torch.float64, device=dev)
+    d_u = torch.tensor(U, dtype=torch.float64, device=dev)
+    d_z = torch.tensor(Z, dtype=torch.float64, device=dev)
+    d_R = torch.tensor(Rr, dtype=torch.float64, device=dev)
     d_j = torch.zeros((B, m), dtype=torch.int32, device=dev)
     for s in range(W):
         bt.scan_device(d_u[s].data_ptr(), m, d_z[s].data_ptr(), d_R[s].data_ptr(), d_j.data_ptr())
@@ -546,18 +743,22 @@ def run_monte_carlo(args, rank, world, local):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     for s in range(W, W + K):
         bt.scan_device(d_u[s].data_ptr(), m, d_z[s].data_ptr(), d_R[s].data_ptr(), d_j.data_ptr())
     bt.sync()
-    ms = (time.perf_counter() - t0) * 1e3
+    ms = (time.perf_counter() - t0) * 1e3      # the library's stream is its own: host clock around enqueue + sync of K launches
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for s in range(W + K, W + 2 * K):
-        rc, jj, pose = bt.scan(np.ascontiguousarray(U[:, s]), np.ascontiguousarray(Z[:, s]), np.ascontiguousarray(Rr[:, s]))
+        rc, jj, pose = bt.scan(U[s], Z[s], Rr[s])
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    bt.close()
+    del d_u, d_z, d_R, d_j
+    torch.cuda.empty_cache()
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -572,15 +773,15 @@ def run_monte_carlo(args, rank, world, local):
         "metric": "EKF predict+update steps/s at N landmarks", "value": K / (ms_max / 1e3), "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
         "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "filters_total": B_total, "filters_per_gpu": B, "landmarks": N,
-                   "lines_per_scan": m, "filter_steps_per_s": B_total * K / (ms_max / 1e3),
-                   "parallelism": "independent filters, %d per GPU, no collective" % B,
-                   "l2": "batch state %.0f MB > 126 MB L2" % (B * (3 + 2 * cap) ** 2 * 8 / 1e6)},
-        "roofline": {"bound": "hbm", "kernel": "k_batch_scan (whole localize per CTA; hot state + pending gains in shared memory, one deferred sweep of the cold upper triangle)",
+        "config": static_config("mc", world, False, getattr(args, "mc_per_gpu", 0)),
+        "run": {"filters_total": B_total, "filters_per_gpu": B, "filter_steps_per_s": B_total * K / (ms_max / 1e3)},
+        "roofline": {"bound": "hbm", "kernel": "k_batch_scan (whole localize per CTA; the filter's packed covariance resident in shared memory for the scan: one bulk copy in, one out)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "launch_ms": ms_max / K, "algorithmic_bytes_per_launch": bytes_per_launch, "traffic": None},
+                     "launch_ms": ms_max / K, "algorithmic_bytes_per_launch": bytes_per_launch, "traffic": None,
+                     "note": "not HBM-bound: 8 sequential association gates per filter and scan (fp64 dependency chains) set the time; "
+                             "the fraction says how far the batch is from streaming its covariances at HBM speed"},
         "e2e": {"value": K / (e2e_max / 1e3), "unit": "steps/s", "h2d_bytes_per_step": (3 + 6 * m) * 8 * B,
-                "d2h_bytes_per_step": (4 * m + 32) * B, "ms_per_step": e2e_max / K},
+                "d2h_bytes_per_step": (4 * m + 40) * B, "ms_per_step": e2e_max / K},
         "gpu_launches": K, "clocks": clk,
     }
 
@@ -597,6 +798,9 @@ def main():
                     "of splitting the 4096-filter batch over the ranks (strong scaling, default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="default workload only: skip the `extra` object (40k row-sharded / "
+                    "un-sharded filter with its parity prefix, Monte-Carlo strong + weak, row-sharded parity on both exchange paths)")
+    ap.add_argument("--parity", action="store_true", help="10k / 1k / 40k: replay the committed oracle fixture first and report `parity`")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
     if args.lines > 0 and args.workload in ("10k", "1k", "40k"):
@@ -620,7 +824,12 @@ def main():
         line = run_extract(args, rank, world, local) if rank == 0 else None
     else:
         sharded = args.workload == "40k" and world > 1
-        line = run_single_or_replicas(args, rank, world, local, sharded)
+        line = run_single_or_replicas(args, rank, world, local, sharded,
+                                      parity_name=args.workload if (args.parity and args.lines == 0) else None)
+        if args.workload == "10k" and args.lines == 0 and not args.no_extras:
+            extra = run_extras(args, rank, world, local)
+            if rank == 0 and line is not None:
+                line["extra"] = extra
     if rank == 0 and line is not None:
         if world == 1 and not args.no_cpu_baseline:
             if args.workload == "extract":
@@ -630,7 +839,7 @@ def main():
             elif args.workload == "1k" and args.lines == 0 and _have_literal_1k():
                 val, info = literal_1k_run(steps=2, budget_s=args.cpu_budget)
             else:
-                val, info = cpu_run(args.workload, steps=1000, warmup=1, budget_s=args.cpu_budget)
+                val, info = cpu_run(args.workload, steps=1000, warmup=1, budget_s=min(args.cpu_budget, 6.0), extra_legs=True)
             line["cpu_baseline"] = info
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -403,6 +403,9 @@ void ekfo_set_threads(void* h, int t) {
 #endif
 }
 int ekfo_get_threads(void* h) { return ((Oracle*)h)->threads; }
+/* adopt a state prepared elsewhere (bench.py: the -O0 build continues from the -O2 build's seeded map); y and P are
+ * written through ekfo_y_ptr / ekfo_P_ptr */
+void ekfo_set_lines(void* h, int L) { Oracle* o = (Oracle*)h; if (L >= 0 && L <= o->cap) o->L = L; }
 void ekfo_set_pose(void* h, const double pose[3]) { Oracle* o = (Oracle*)h; std::memcpy(o->pose, pose, sizeof o->pose); }
 
 /* primitives mirroring include/ekf.h */

@@ -15,7 +15,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(_HERE, "libekforacle.so")
+_ORACLE_O0_SO = os.path.join(_HERE, "libekforacle_O0.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libslamref.so")
+_REF_O0_SO = os.path.join(_HERE, "_ref", "libslamref_O0.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -40,10 +42,12 @@ def _d(a):
 
 
 class StructuredOracle:
-    def __init__(self, capacity_lines, gate=0.4, encoder_noise=0.024, reset_headroom=10, threads=1):
-        if not os.path.exists(_ORACLE_SO):
+    def __init__(self, capacity_lines, gate=0.4, encoder_noise=0.024, reset_headroom=10, threads=1, opt0=False):
+        """opt0: the -O0 build of the same source (the reference's CMakeLists sets no optimisation flag)."""
+        so = _ORACLE_O0_SO if opt0 else _ORACLE_SO
+        if not os.path.exists(so):
             build()
-        L = self._lib = C.CDLL(_ORACLE_SO)
+        L = self._lib = C.CDLL(so)
         L.ekfo_create.restype = C.c_void_p
         L.ekfo_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int]
         L.ekfo_y_ptr.restype = _dp
@@ -51,7 +55,7 @@ class StructuredOracle:
         for f in ("ekfo_destroy", "ekfo_set_threads", "ekfo_set_pose", "ekfo_predict", "ekfo_associate",
                   "ekfo_gate_pair", "ekfo_update", "ekfo_last_gain", "ekfo_queue", "ekfo_end", "ekfo_scan", "ekfo_localize", "ekfo_n",
                   "ekfo_lines", "ekfo_y_ptr", "ekfo_P_ptr", "ekfo_get_pose", "ekfo_get_xpre", "ekfo_stats",
-                  "ekfo_get_live", "ekfo_get_ellipse", "ekfo_get_threads", "ekfo_upper_stats"):
+                  "ekfo_get_live", "ekfo_get_ellipse", "ekfo_get_threads", "ekfo_upper_stats", "ekfo_set_lines"):
             getattr(L, f).argtypes = None
         self._h = C.c_void_p(L.ekfo_create(int(capacity_lines), float(gate), float(encoder_noise), int(reset_headroom)))
         if not self._h:
@@ -86,6 +90,15 @@ class StructuredOracle:
         p = np.zeros(3)
         self._lib.ekfo_get_xpre(self._h, p.ctypes.data_as(_dp))
         return p
+
+    def adopt(self, other):
+        """Copy the whole state (y, P, savedLineCount, pose) of another oracle of the same capacity."""
+        assert other.n == self.n
+        np.ctypeslib.as_array(self._lib.ekfo_y_ptr(self._h), shape=(self.n,))[:] = other.y_full()
+        nl = 3 + 2 * other.lines
+        self.P_view()[:nl] = other.P_view()[:nl]
+        self._lib.ekfo_set_lines(self._h, C.c_int(other.lines))
+        self.set_pose(other.pose)
 
     def set_pose(self, pose):
         a, p = _d(pose)
@@ -197,8 +210,8 @@ class LiteralReference:
     (Robot.h:13); big=True: the same sources with LINESIZE = 1000 / SLAMSIZE = 2003 (oracle/_ref/libslamref1k.so,
     BASELINE configs[1]) -- its localize needs ~300 MB of stack and runs on a dedicated thread."""
 
-    def __init__(self, big=False):
-        so = _REF1K_SO if big else _REF_SO
+    def __init__(self, big=False, opt0=False):
+        so = _REF1K_SO if big else (_REF_O0_SO if opt0 else _REF_SO)
         self._big = bool(big)
         if not os.path.exists(so):
             build()

@@ -12,8 +12,9 @@
  *     p <- p - (K S)[r] K[q] (Robot.cpp:564-568), which is the reference's own order of operations;
  *   - association (Robot.cpp:313-501): every landmark first takes a test that needs no trigonometry and no matrix
  *     inverse -- the angle innovation alone bounds the Mahalanobis distance from below, d^2 >= v0^2 / S00 -- and is
- *     rejected when even that bound is twice the gate; the few survivors (typically one) are compacted and evaluated
- *     by the reference's full expression, one per thread; first fit = lowest passing index.
+ *     rejected when even that bound is twice the gate; the few survivors (typically one) are compacted onto the first
+ *     lanes of one warp and evaluated by the reference's full expression; first fit = lowest passing index.  That warp
+ *     works on the NEXT line's association while the other warps apply the previous match to the bulk of P.
  *
  * Filters never communicate; a multi-GPU batch is N independent ekf_batch objects, one per device
  * (slam_ros_b200/parallel.py deals filters round-robin).
@@ -23,10 +24,10 @@
 #include "ekf_device.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define EKFB_THREADS 128
-#define EKFB_MAXCAND 64
 
 struct EkfBatchState {
   double pose[3];
@@ -48,16 +49,17 @@ namespace {
 
 __host__ __device__ inline int tri(int q) { return (q * (q + 1)) >> 1; }        /* first element of packed column q */
 
-/* shared-memory carve-up for a scan whose live dimension cannot exceed ns */
-struct BatchLayout { int P, y, K, KS, cand, ext, matched, bytes; };
-__host__ __device__ inline BatchLayout batch_layout(int ns, int cap, int m) {
+/* shared-memory carve-up: the packed triangle holds columns < ns (a HINT: the largest map the host last saw, plus a
+ * little; a filter that has outgrown it works on its HBM copy instead -- slower, same bits); y and the gain vectors
+ * are sized by the capacity */
+struct BatchLayout { int P, y, K, KS, ext, matched, bytes; };
+__host__ __device__ inline BatchLayout batch_layout(int ns, int n, int cap, int m) {
   BatchLayout l;
   int o = 0;
   l.P = o; o += ((tri(ns) + 1) & ~1) * 8;            /* packed upper triangle, columns < ns */
-  l.y = o; o += ((ns + 1) & ~1) * 8;
-  l.K = o; o += ns * 16;
-  l.KS = o; o += ns * 16;
-  l.cand = o; o += EKFB_MAXCAND * 4;
+  l.y = o; o += ((n + 1) & ~1) * 8;
+  l.K = o; o += n * 16;
+  l.KS = o; o += n * 16;
   l.ext = o; o += ((m + 3) & ~3) * 4;
   l.matched = o; o += (cap + 15) & ~15;
   l.bytes = o;
@@ -90,23 +92,56 @@ __device__ __forceinline__ void b_bulk_store(void* dst, const void* src, unsigne
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(b_smem_u32(src)), "r"(bytes) : "memory");
 }
 
-/* Robot::localize for filter blockIdx.x.  ns: upper bound of the live dimension at the END of this scan (host-side
- * bound: largest map of the batch + m, capped by the capacity; the shared-memory carve-up is sized by it). */
-__global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, int ns, double* __restrict__ Yg,
-                                                             double* __restrict__ Pg, EkfBatchState* __restrict__ Sg,
-                                                             const double* __restrict__ U, const double* __restrict__ Z,
-                                                             const double* __restrict__ Rm, int m, int* __restrict__ Jout) {
+/* Robot.cpp:564-568 on the COLD elements of the packed upper triangle, p <- p - (K S)[r] K[q]: column q >= 3, rows 3 up
+ * to (excluding) its landmark's 2x2 diagonal block; rows 0..2 and the diagonal blocks are the hot part (phase A of the
+ * line loop).  Columns are taken two at a time, a long one with a short one, so that one load of (K S)[r] serves both;
+ * a lane walks consecutive rows (conflict-free).  Warp w0 of nw. */
+__device__ __forceinline__ void batch_update_cold(double* __restrict__ P, const double2* __restrict__ Ks,
+                                                  const double2* __restrict__ KSs, int nl, int w0, int nw, int lane) {
+  const int ncol = nl - 3;                                  /* columns 3 .. nl-1 */
+  const int npair = (ncol + 1) >> 1;
+  for (int c = w0; c < npair; c += nw) {
+    const int qs = 3 + c, ql = nl - 1 - c;                  /* short and long column of the pair (qs <= ql) */
+    const int es = (qs & 1) ? qs : qs - 1, el = (ql & 1) ? ql : ql - 1;      /* first hot row of each */
+    const double2 ks_ = Ks[qs], kl = Ks[ql];
+    double* cs = P + tri(qs);
+    double* cl = P + tri(ql);
+    if (qs == ql) {
+      for (int r = 3 + lane; r < es; r += 32) cs[r] = sub_rank2(cs[r], KSs[r], ks_);
+      continue;
+    }
+    for (int r = 3 + lane; r < el; r += 64) {               /* two row groups in flight */
+      const int r2 = r + 32;
+      const double2 k1 = KSs[r];
+      const double pl1 = cl[r];
+      double2 k2 = k1; double pl2 = 0.0, ps1 = 0.0, ps2 = 0.0;
+      if (r2 < el) { k2 = KSs[r2]; pl2 = cl[r2]; }
+      if (r < es) ps1 = cs[r];
+      if (r2 < es) ps2 = cs[r2];
+      cl[r] = sub_rank2(pl1, k1, kl);
+      if (r2 < el) cl[r2] = sub_rank2(pl2, k2, kl);
+      if (r < es) cs[r] = sub_rank2(ps1, k1, ks_);
+      if (r2 < es) cs[r2] = sub_rank2(ps2, k2, ks_);
+    }
+  }
+}
+
+/* The whole scan of one filter.  ns: columns of the packed triangle that fit the shared-memory carve-up. */
+template <bool ON_CHIP>
+__device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int ns, double* __restrict__ Yg,
+                                                double* __restrict__ Pg, EkfBatchState* __restrict__ Sg,
+                                                const double* __restrict__ U, const double* __restrict__ Z,
+                                                const double* __restrict__ Rm, const int m, int* __restrict__ Jout, const int L0) {
   extern __shared__ __align__(16) unsigned char braw[];
-  const BatchLayout lay = batch_layout(ns, g.cap, m);
-  double* const Ps = reinterpret_cast<double*>(braw + lay.P);
+  const BatchLayout lay = batch_layout(ns, g.n, g.cap, m);
+  double* const Psm = reinterpret_cast<double*>(braw + lay.P);
   double* const ys = reinterpret_cast<double*>(braw + lay.y);
   double2* const Ks = reinterpret_cast<double2*>(braw + lay.K);
   double2* const KSs = reinterpret_cast<double2*>(braw + lay.KS);
-  int* const cand = reinterpret_cast<int*>(braw + lay.cand);
   int* const ext = reinterpret_cast<int*>(braw + lay.ext);
   unsigned char* const matched = braw + lay.matched;
   __shared__ unsigned long long s_bar;
-  __shared__ int s_best, s_ncand, s_sticky;
+  __shared__ int s_best, s_sticky;
   __shared__ double s_xpre[3];
   __shared__ Gate sG;
 
@@ -120,16 +155,19 @@ __global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, int
   const double* const R = Rm + 4 * (size_t)m * f;
   int* const jout = Jout ? Jout + (size_t)m * f : 0;
 
-  int L = st->L;
+  int L = L0;
   const int nl = 3 + 2 * L;
   const double pose0 = st->pose[0], pose1 = st->pose[1], pose2 = st->pose[2];
+  /* the whole live triangle on chip -- or, for a filter that has outgrown the carve-up, its HBM copy in place */
+  constexpr bool on_chip = ON_CHIP;
+  double* const Ps = ON_CHIP ? Psm : Pf;
   /* ---- the filter's live covariance and state: two bulk copies, one barrier ---- */
   if (tid == 0) {
-    const unsigned pbytes = (unsigned)(((tri(nl) + 1) & ~1) * 8), ybytes = (unsigned)(((nl + 1) & ~1) * 8);
+    const unsigned pbytes = on_chip ? (unsigned)(((tri(nl) + 1) & ~1) * 8) : 0u, ybytes = (unsigned)(((nl + 1) & ~1) * 8);
     b_mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     b_mbar_expect_tx(&s_bar, pbytes + ybytes);
-    b_bulk_load(Ps, Pf, pbytes, &s_bar);
+    if (on_chip) b_bulk_load(Psm, Pf, pbytes, &s_bar);
     b_bulk_load(ys, yf, ybytes, &s_bar);
     s_sticky = 0;
   }
@@ -187,114 +225,35 @@ __global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, int
   }
   __syncthreads();
 
-  /* ---- the observed lines in order, Robot.cpp:298-645 ---- */
+  /* ---- the observed lines in order, Robot.cpp:298-645 ----
+   * Per line, three phases separated by block barriers:
+   *   A  (all warps)  the HOT part of the previous match's update: rows 0..2 of every column, the 2x2 diagonal blocks,
+   *                   y, the pose -- everything the next gate reads;
+   *   B  warp 0       associates this line (pre-test of every landmark, full gate of the survivors, first fit), WHILE
+   *      warps 1..3   apply the previous match to the cold rest of the triangle;
+   *   C  (all warps)  the gain rows of this line's match (needs the complete P).
+   * The long dependent chain of a gate (trigonometry, 2x2 LU inverse) thus runs beside the bulk of the update. */
   int ne = 0, nmatch = 0;                                    /* uniform across the block */
   const double gate2x4 = 4.0 * g.gate * g.gate;
-  for (int i = 0; i < m; ++i) {
-    const double z0 = z[2 * i], z1 = z[2 * i + 1];
-    const double xp0 = s_xpre[0], xp1 = s_xpre[1], xp2 = s_xpre[2];
-    if (tid == 0) { s_ncand = 0; s_best = EKF_NO_MATCH; }
-    __syncthreads();
-    /* pre-test: v0 is the gate's own angle innovation (Robot.cpp:423-475, no trigonometry); S00 = H0 P H0' + R00 with
-     * H0 = (0, 0, -1, .. 1 at a ..): d^2 = v' S^-1 v >= v0^2 / S00, so a landmark whose bound exceeds (2 gate)^2 -- twice
-     * the gate in d, far outside any rounding difference between the bound and the reference's LU expression -- cannot
-     * pass the reference's test either */
-    {
-      const double P22 = Ps[tri(2) + 2], R00 = R[4 * i];
-      for (int j = tid; j < L; j += nt) {
-        if (matched[j]) continue;
-        bool keep = true;
-        if (!g.full_gates) {
-          const int a = 3 + 2 * j;
-          const double* ca_ = Ps + tri(a);
-          double h0 = sub_rn(ys[a], xp2);
-          normalize_radian(h0);
-          double v0 = sub_rn(z0, h0);
-          const double two_pi = 2.0 * EKF_PI;
-          if (fabs(sub_rn(v0, two_pi)) < fabs(v0)) v0 = sub_rn(v0, two_pi);
-          else if (fabs(add_rn(v0, two_pi)) < fabs(v0)) v0 = add_rn(v0, two_pi);
-          const double S00 = (P22 - 2.0 * ca_[2]) + ca_[a] + R00;
-          keep = !(S00 > 0.0) || !(v0 * v0 > gate2x4 * S00);
-        }
-        if (keep) { const int k = atomicAdd(&s_ncand, 1); if (k < EKFB_MAXCAND) cand[k] = j; }
-      }
-    }
-    __syncthreads();
-    /* full gate of the survivors, one per thread */
-    {
-      const int ncand = s_ncand;
-      const bool overflow = ncand > EKFB_MAXCAND;          /* more survivors than the list holds: gate every landmark */
-      const int total = overflow ? L : ncand;
-      const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
-      const double xp[3] = {xp0, xp1, xp2};
-      int mine = EKF_NO_MATCH;
-      Gate G;
-      for (int k = tid; k < total; k += nt) {
-        const int j = overflow ? k : cand[k];
-        if (overflow && matched[j]) continue;
-        if (j > mine) continue;
-        const int a = 3 + 2 * j, bb = a + 1;
-        const double* ca_ = Ps + tri(a);
-        const double* cb_ = Ps + tri(bb);
-        double Cm[5][5];
-        for (int r = 0; r < 3; ++r) {
-          for (int q = r; q < 3; ++q) { Cm[r][q] = Ps[tri(q) + r]; Cm[q][r] = Cm[r][q]; }
-          Cm[r][3] = Cm[3][r] = ca_[r]; Cm[r][4] = Cm[4][r] = cb_[r];
-        }
-        Cm[3][3] = ca_[a]; Cm[3][4] = Cm[4][3] = cb_[a]; Cm[4][4] = cb_[bb];
-        Gate Gj;
-        gate_from_block(Cm, ys[a], ys[bb], xp, z0, z1, Rl, Gj);
-        if (Gj.singular) atomicOr(&s_sticky, EKF_STICKY_SINGULAR);
-        else if (!(sqrt(fabs(Gj.d2)) > g.gate)) { mine = j; G = Gj; }                /* :489 */
-      }
-      if (total > 0) {                                     /* uniform */
-        if (mine != EKF_NO_MATCH) atomicMin(&s_best, mine);
-        __syncthreads();
-        if (mine != EKF_NO_MATCH && mine == s_best) sG = G;   /* the winner publishes its gate record (evaluated once) */
-      }
-    }
-    __syncthreads();
-    const int jb = s_best;
-    if (jb == EKF_NO_MATCH) {                                         /* :309 / :325 / :493 */
-      if (tid == 0) { ext[ne] = i; if (jout) jout[i] = -1; }
-      ne += 1;
-      continue;
-    }
-    const int a = 3 + 2 * jb, bb = a + 1;
-    const int ta = tri(a), tb = tri(bb);
-    for (int r = tid; r < nl; r += nt) {                              /* :516-560 */
-      const int tr_ = tri(r);
-      const double p0 = (r <= 0) ? Ps[r] : Ps[tr_];                   /* P[r,0..2] through the upper storage */
-      const double p1 = (r <= 1) ? Ps[tri(1) + r] : Ps[tr_ + 1];
-      const double p2 = (r <= 2) ? Ps[tri(2) + r] : Ps[tr_ + 2];
-      const double pa = (r <= a) ? Ps[ta + r] : Ps[tr_ + a];
-      const double pb = (r <= bb) ? Ps[tb + r] : Ps[tr_ + bb];
-      double2 Kr, KSr;
-      gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
-      Ks[r] = Kr; KSs[r] = KSr;
-    }
-    __syncthreads();
-    /* ---- :564-602: every element of the upper triangle, y, the pose.  Columns are paired (q, nl-1-q) so that every
-     * warp task spans nl+1 rows; a lane walks consecutive rows of a column (conflict-free). ---- */
-    {
+  bool have_prev = false;                                    /* a match whose update of P is still to be applied */
+  for (int i = 0; i <= m; ++i) {
+    const bool gating = i < m;
+    if (!gating && !have_prev) break;
+    /* ---- phase A ---- */
+    if (have_prev) {
       const double v0 = sG.v[0], v1 = sG.v[1];
-      const int npair = (nl + 1) >> 1;
-      for (int c = warp; c < npair; c += nt / 32) {
-        const int qa = c, qb = nl - 1 - c;
-        const double2 ka = Ks[qa], kb = Ks[qb];
-        double* colA = Ps + tri(qa);
-        double* colB = Ps + tri(qb);
-        const int span = (qa == qb) ? qa + 1 : nl + 1;
-        for (int v = lane; v < span; v += 32) {
-          if (v <= qa) colA[v] = sub_rank2(colA[v], KSs[v], ka);
-          else { const int r = v - qa - 1; colB[r] = sub_rank2(colB[r], KSs[r], kb); }
-        }
-      }
-      for (int q = 3 + tid; q < nl; q += nt) {                        /* :585-589  y += K * delta */
+      for (int q = tid; q < nl; q += nt) {
+        double* c = Ps + tri(q);
         const double2 kq = Ks[q];
-        double t = 0.0;
-        axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
-        ys[q] = add_rn(ys[q], t);
+        const int top = q < 3 ? q + 1 : 3;
+        for (int r = 0; r < top; ++r) c[r] = sub_rank2(c[r], KSs[r], kq);           /* :564-568, rows 0..2 */
+        if (q >= 3) {
+          if (q & 1) c[q] = sub_rank2(c[q], KSs[q], kq);                             /* (a,a) */
+          else { c[q - 1] = sub_rank2(c[q - 1], KSs[q - 1], kq); c[q] = sub_rank2(c[q], KSs[q], kq); }   /* (a,b), (b,b) */
+          double t = 0.0;                                                            /* :585-589  y += K * delta */
+          axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
+          ys[q] = add_rn(ys[q], t);
+        }
       }
       if (tid == 0) {
         double yn[3];
@@ -306,10 +265,86 @@ __global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, int
         }
         normalize_radian(yn[2]);                                      /* :596-602 */
         for (int r = 0; r < 3; ++r) { ys[r] = yn[r]; s_xpre[r] = yn[r]; }
-        matched[jb] = 1;                                              /* :501 */
-        if (jout) jout[i] = jb;
       }
+      __syncthreads();
     }
+    /* ---- phase B ---- */
+    if (warp == 0 && gating) {
+      const double z0 = z[2 * i], z1 = z[2 * i + 1];
+      const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
+      const double xp[3] = {s_xpre[0], s_xpre[1], s_xpre[2]};
+      const double P22 = Ps[tri(2) + 2];
+      int best = EKF_NO_MATCH;
+      for (int j0 = 0; j0 < L && best == EKF_NO_MATCH; j0 += 32) {    /* first fit: a match in this round ends the search */
+        const int j = j0 + lane;
+        bool keep = j < L && !matched[j];
+        if (keep && !g.full_gates) {
+          /* pre-test: v0 is the gate's own angle innovation (Robot.cpp:423-475, no trigonometry); S00 = H0 P H0' + R00
+           * with H0 = (0, 0, -1, .. 1 at a ..): d^2 = v' S^-1 v >= v0^2 / S00, so a landmark whose bound exceeds
+           * (2 gate)^2 -- twice the gate in d, far outside any rounding difference between the bound and the reference's
+           * LU expression -- cannot pass the reference's test either */
+          const int a = 3 + 2 * j;
+          const double* ca_ = Ps + tri(a);
+          double h0 = sub_rn(ys[a], xp[2]);
+          normalize_radian(h0);
+          double v0 = sub_rn(z0, h0);
+          const double two_pi = 2.0 * EKF_PI;
+          if (fabs(sub_rn(v0, two_pi)) < fabs(v0)) v0 = sub_rn(v0, two_pi);
+          else if (fabs(add_rn(v0, two_pi)) < fabs(v0)) v0 = add_rn(v0, two_pi);
+          const double S00 = (P22 - 2.0 * ca_[2]) + ca_[a] + Rl[0];
+          keep = !(S00 > 0.0) || !(v0 * v0 > gate2x4 * S00);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int ncand = __popc(mask);
+        int mine = EKF_NO_MATCH;
+        Gate Gj;
+        if (lane < ncand) {                                           /* the survivors, compacted onto the first lanes */
+          const int jj = j0 + (int)__fns(mask, 0, lane + 1);
+          const int a = 3 + 2 * jj, bb = a + 1;
+          const double* ca_ = Ps + tri(a);
+          const double* cb_ = Ps + tri(bb);
+          double Cm[5][5];
+          for (int r = 0; r < 3; ++r) {
+            for (int q = r; q < 3; ++q) { Cm[r][q] = Ps[tri(q) + r]; Cm[q][r] = Cm[r][q]; }
+            Cm[r][3] = Cm[3][r] = ca_[r]; Cm[r][4] = Cm[4][r] = cb_[r];
+          }
+          Cm[3][3] = ca_[a]; Cm[3][4] = Cm[4][3] = cb_[a]; Cm[4][4] = cb_[bb];
+          gate_from_block(Cm, ys[a], ys[bb], xp, z0, z1, Rl, Gj);
+          if (Gj.singular) atomicOr(&s_sticky, EKF_STICKY_SINGULAR);
+          else if (!(sqrt(fabs(Gj.d2)) > g.gate)) mine = jj;                           /* :489 */
+        }
+        best = __reduce_min_sync(0xffffffffu, mine);
+        if (mine != EKF_NO_MATCH && mine == best) sG = Gj;            /* the winner publishes its gate record */
+      }
+      if (lane == 0) {
+        s_best = best;
+        if (best == EKF_NO_MATCH) { ext[ne] = i; if (jout) jout[i] = -1; }           /* :309 / :325 / :493 */
+        else { matched[best] = 1; if (jout) jout[i] = best; }                       /* :501 */
+      }
+    } else if (have_prev && (warp != 0 || !gating)) {
+      /* the cold rest of the previous match's update (Robot.cpp:564-568): column q, rows 3 .. its diagonal block */
+      const int w0 = gating ? warp - 1 : warp, nw = gating ? nt / 32 - 1 : nt / 32;
+      batch_update_cold(Ps, Ks, KSs, nl, w0, nw, lane);
+    }
+    __syncthreads();
+    if (!gating) break;
+    const int jb = s_best;
+    if (jb == EKF_NO_MATCH) { ne += 1; have_prev = false; continue; }
+    /* ---- phase C: Robot.cpp:516-560 ---- */
+    const int a = 3 + 2 * jb, bb = a + 1;
+    const int ta = tri(a), tb = tri(bb);
+    for (int r = tid; r < nl; r += nt) {
+      const int tr_ = tri(r);
+      const double p0 = (r <= 0) ? Ps[r] : Ps[tr_];                   /* P[r,0..2] through the upper storage */
+      const double p1 = (r <= 1) ? Ps[tri(1) + r] : Ps[tr_ + 1];
+      const double p2 = (r <= 2) ? Ps[tri(2) + r] : Ps[tr_ + 2];
+      const double pa = (r <= a) ? Ps[ta + r] : Ps[tr_ + a];
+      const double pb = (r <= bb) ? Ps[tb + r] : Ps[tr_ + bb];
+      double2 Kr, KSr;
+      gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
+      Ks[r] = Kr; KSs[r] = KSr;
+    }
+    have_prev = true;
     nmatch += 1;
     __syncthreads();
   }
@@ -332,13 +367,15 @@ __global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, int
     rr = add_rn(rr, add_rn(mul_rn(ps0, cos(alfa)), mul_rn(ps1, sin(alfa))));          /* :792 (Q8) */
     alfa = add_rn(alfa, ps2);                                                       /* :793 */
     const double cw = cos(alfa), sw = sin(alfa);
-    double* c0 = Ps + tri(l);
-    double* c1 = Ps + tri(l + 1);
+    /* a new column lives on chip while it fits the carve-up, else straight in the filter's HBM copy (write-mostly:
+     * only its rows 0..2 are read again, by the columns appended after it in this scan) */
+    double* c0 = ((on_chip && l < ns) ? Psm : Pf) + tri(l);
+    double* c1 = ((on_chip && l + 1 < ns) ? Psm : Pf) + tri(l + 1);
     for (int k = tid; k < l; k += nt) {                               /* :856-860: P[k, l], P[k, l+1] */
-      const int tk = tri(k);
-      const double a0 = (k <= 0) ? Ps[k] : Ps[tk];                    /* P[0,k], P[1,k], P[2,k] through the upper storage */
-      const double a1 = (k <= 1) ? Ps[tri(1) + k] : Ps[tk + 1];
-      const double a2 = (k <= 2) ? Ps[tri(2) + k] : Ps[tk + 2];
+      const double* ck = ((on_chip && k < ns) ? Psm : Pf) + tri(k);
+      const double a0 = (k <= 0) ? Ps[k] : ck[0];                     /* P[0,k], P[1,k], P[2,k] through the upper storage */
+      const double a1 = (k <= 1) ? Ps[tri(1) + k] : ck[1];
+      const double a2 = (k <= 2) ? Ps[tri(2) + k] : ck[2];
       double r0 = 0.0, r1 = 0.0;
       axpy_skip(r1, cw, a0);
       axpy_skip(r1, sw, a1);
@@ -389,20 +426,29 @@ __global__ void __launch_bounds__(EKFB_THREADS) k_batch_scan(EkfBatchGeom g, int
   int resets = 0;
   if (L > g.cap - g.headroom) { L = 0; resets = 1; }
   const int nl_new = 3 + 2 * L;
-  const int ns_even = (ns + 1) & ~1;
-  for (int q = nl_new + tid; q < ns_even; q += nt) ys[q] = 0.0;      /* Robot::y is zero beyond the live part */
+  for (int q = nl_new + tid; q < g.ystride; q += nt) ys[q] = 0.0;    /* Robot::y is zero beyond the live part */
   /* ---- state and covariance back to HBM: one bulk store each ---- */
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
-    b_bulk_store(Pf, Ps, (unsigned)(((tri(nl_new) + 1) & ~1) * 8));
-    b_bulk_store(yf, ys, (unsigned)(ns_even * 8));
+    if (on_chip) b_bulk_store(Pf, Psm, (unsigned)(((tri(min(nl_new, ns)) + 1) & ~1) * 8));
+    b_bulk_store(yf, ys, (unsigned)(g.ystride * 8));
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     st->L = L; st->pose[0] = ps0; st->pose[1] = ps1; st->pose[2] = ps2;
     st->sticky = s_sticky;                        /* status reports this scan only */
     st->resets += resets;
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
+}
+
+/* Robot::localize for filter blockIdx.x */
+__global__ void __launch_bounds__(EKFB_THREADS, 4) k_batch_scan(EkfBatchGeom g, int ns, double* __restrict__ Yg,
+                                                                double* __restrict__ Pg, EkfBatchState* __restrict__ Sg,
+                                                                const double* __restrict__ U, const double* __restrict__ Z,
+                                                                const double* __restrict__ Rm, int m, int* __restrict__ Jout) {
+  const int L0 = Sg[blockIdx.x].L;
+  if (3 + 2 * L0 <= ns) batch_scan_body<true>(g, ns, Yg, Pg, Sg, U, Z, Rm, m, Jout, L0);
+  else batch_scan_body<false>(g, ns, Yg, Pg, Sg, U, Z, Rm, m, Jout, L0);
 }
 
 __global__ void k_batch_init(EkfBatchGeom g, double* Pg) {
@@ -425,8 +471,9 @@ struct ekf_batch {
   int* d_jout; int* h_jout;
   EkfBatchState* h_st;
   double* h_P;                      /* pinned staging of one filter's packed covariance (ekf_batch_download) */
-  int L_ub;                         /* host-side upper bound of max_f L */
-  int L_exact;                      /* L_ub is exact: no device-resident scan was enqueued since the states were read back */
+  int L_hint;                       /* largest map of the batch when the states were last read back (sizes the on-chip triangle) */
+  int L_exact;                      /* no device-resident scan was enqueued since then */
+  int ns_forced;                    /* EKF_BATCH_NS: test knob, columns of the on-chip triangle (0 = from L_hint) */
   size_t smem_set;
   char err[256];
 };
@@ -443,11 +490,17 @@ namespace {
 
 const size_t kBatchSmemMax = 227 * 1024 - 256;      /* dynamic shared memory one CTA may ask for (static part: ~200 B) */
 
-/* live dimension a scan of m lines cannot exceed */
-int batch_ns(const ekf_batch* b, int m) {
-  long long lub = (long long)b->L_ub + m;
-  if (lub > b->g.cap) lub = b->g.cap;
-  return 3 + 2 * (int)lub;
+/* Columns of the on-chip triangle: the largest map last seen plus two lines of slack.  Not a bound -- a filter whose
+ * live dimension exceeds it runs the same kernel on its HBM copy -- so device-resident scans enqueued back to back
+ * keep the small carve-up (4 filters per SM at 50 landmarks) instead of drifting to the capacity. */
+int batch_ns(const ekf_batch* b) {
+  long long l = (long long)b->L_hint + 2;
+  if (b->ns_forced > 0) l = (b->ns_forced - 3) / 2;
+  /* an even number of lines: the packed prefix then has an even number of doubles, so the 16-byte granularity of the
+   * bulk copies never reaches into the first column kept off chip */
+  l += l & 1;
+  if (l > b->g.cap + 1) l = (b->g.cap + 1) & ~1;
+  return 3 + 2 * (int)l;
 }
 
 int batch_ensure_m(ekf_batch* b, int m) {
@@ -455,8 +508,8 @@ int batch_ensure_m(ekf_batch* b, int m) {
   /* nothing is released before the larger scan is known to fit: a rejected call leaves the batch usable */
   int cap = b->max_m > 0 ? b->max_m : 8;
   while (cap < m) cap *= 2;
-  if ((size_t)batch_layout(b->g.n, b->g.cap, cap).bytes > kBatchSmemMax) cap = m;    /* do not reject m over the rounding */
-  if ((size_t)batch_layout(b->g.n, b->g.cap, cap).bytes > kBatchSmemMax) {
+  if ((size_t)batch_layout(3, b->g.n, b->g.cap, cap).bytes > kBatchSmemMax) cap = m;    /* do not reject m over the rounding */
+  if ((size_t)batch_layout(3, b->g.n, b->g.cap, cap).bytes > kBatchSmemMax) {
     snprintf(b->err, sizeof b->err, "scan of %d lines does not fit shared memory", m);
     return EKF_EINVAL;
   }
@@ -474,8 +527,9 @@ int batch_ensure_m(ekf_batch* b, int m) {
 }
 
 int batch_launch(ekf_batch* b, const double* d_u, int m, const double* d_z, const double* d_R, int* d_jout) {
-  const int ns = batch_ns(b, m);
-  const size_t smem = (size_t)batch_layout(ns, b->g.cap, m).bytes;
+  int ns = batch_ns(b);
+  while (ns > 3 && (size_t)batch_layout(ns, b->g.n, b->g.cap, m).bytes > kBatchSmemMax) ns -= 4;   /* very large maps: partly off chip */
+  const size_t smem = (size_t)batch_layout(ns, b->g.n, b->g.cap, m).bytes;
   if (smem > kBatchSmemMax) { snprintf(b->err, sizeof b->err, "scan of %d lines does not fit shared memory", m); return EKF_EINVAL; }
   if (smem > b->smem_set) {
     CUB(cudaFuncSetAttribute(k_batch_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -484,7 +538,6 @@ int batch_launch(ekf_batch* b, const double* d_u, int m, const double* d_z, cons
   }
   k_batch_scan<<<b->g.B, EKFB_THREADS, smem, b->stream>>>(b->g, ns, b->d_y, b->d_P, b->d_st, d_u, d_z, d_R, m, d_jout);
   CUB(cudaGetLastError());
-  { long long lub = (long long)b->L_ub + m; b->L_ub = (int)(lub > b->g.cap ? b->g.cap : lub); }
   b->L_exact = 0;
   return EKF_OK;
 }
@@ -497,7 +550,7 @@ int batch_refresh_bound(ekf_batch* b) {
   CUB(cudaStreamSynchronize(b->stream));
   int mx = 0;
   for (size_t f = 0; f < B; ++f) if (b->h_st[f].L > mx) mx = b->h_st[f].L;
-  b->L_ub = mx; b->L_exact = 1;
+  b->L_hint = mx; b->L_exact = 1;
   return EKF_OK;
 }
 }  // namespace
@@ -522,11 +575,11 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   g.pstride = (tri(g.n) + 2) & ~1;
   g.ystride = (g.n + 1) & ~1;
   g.full_gates = (cfg->flags & EKF_FLAG_FULL_GATES) ? 1 : 0;
-  if (g.cap > 4096 || (size_t)batch_layout(g.n, g.cap, 8).bytes > kBatchSmemMax) {
-    snprintf(b->err, sizeof b->err, "capacity %d does not fit shared memory (a batch filter keeps its whole covariance on chip: "
-             "about 110 lines at most); use ekf_create", g.cap);
+  if (g.cap > 2048 || (size_t)batch_layout(3, g.n, g.cap, 8).bytes > kBatchSmemMax) {
+    snprintf(b->err, sizeof b->err, "capacity %d is too large for a batch filter (state and gain vectors are kept on chip); use ekf_create", g.cap);
     return EKF_EINVAL;
   }
+  { const char* e = getenv("EKF_BATCH_NS"); b->ns_forced = e ? atoi(e) : 0; if (b->ns_forced < 0) b->ns_forced = 0; if (b->ns_forced > 0 && b->ns_forced < 3) b->ns_forced = 3; }
   CUB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   const size_t B = g.B;
   CUB(cudaMalloc(&b->d_y, B * (size_t)g.ystride * sizeof(double)));
@@ -539,7 +592,7 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   CUB(cudaMemsetAsync(b->d_st, 0, B * sizeof(EkfBatchState), b->stream));
   k_batch_init<<<(g.B + 255) / 256, 256, 0, b->stream>>>(g, b->d_P);
   CUB(cudaGetLastError());
-  b->L_ub = 0; b->L_exact = 1;
+  b->L_hint = 0; b->L_exact = 1;
   int rc = batch_ensure_m(b, 8);
   if (rc) return rc;
   CUB(cudaStreamSynchronize(b->stream));
@@ -592,7 +645,7 @@ int ekf_batch_scan(ekf_batch* b, const double* u, int m, const double* z, const 
     if (b->h_st[f].sticky & EKF_STICKY_CAPACITY) status = EKF_ECAPACITY;
     else if ((b->h_st[f].sticky & EKF_STICKY_SINGULAR) && status == EKF_OK) status = EKF_ESINGULAR;
   }
-  b->L_ub = mx; b->L_exact = 1;       /* the states just came back: the bound is exact again */
+  b->L_hint = mx; b->L_exact = 1;     /* the states just came back */
   return status;
 }
 
