@@ -39,7 +39,8 @@ def stale():
 # A/B builds of the same sources, loaded through EKF_LIB by tests and measurement scripts (never by default):
 #   exact   -DEKF_EXACT_RANK2: the reference's four-rounding p - (ks.x k.x + ks.y k.y) instead of two FMAs
 #   timing  -DEKF_LINE_TIMING: %globaltimer stamps of the line loop's phases (scripts/line_timing*.py)
-VARIANTS = {"exact": ["-DEKF_EXACT_RANK2"], "timing": ["-DEKF_LINE_TIMING"]}
+#   mctiming -DEKFB_TIMING: clock64 phase totals of one Monte-Carlo filter's scan, printed by the kernel
+VARIANTS = {"exact": ["-DEKF_EXACT_RANK2"], "timing": ["-DEKF_LINE_TIMING"], "mctiming": ["-DEKFB_TIMING"]}
 
 
 def variant_path(name):

@@ -204,7 +204,7 @@ int make_tensor_map(ekf_ctx* ctx, size_t p_rows, double* base, CUtensorMap* out)
   const cuuint64_t gdim[2] = {(cuuint64_t)ctx->g.ld, (cuuint64_t)p_rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ctx->g.ld * sizeof(double)};
   int tr = 64, tc = 64;
-  ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
+  ekf_sweep_pbox(ctx->sweep_shape, &tr, &tc);
   const cuuint32_t box[2] = {(cuuint32_t)tc, (cuuint32_t)tr};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
@@ -541,7 +541,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
+  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9 && ctx->sweep_shape != 10) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
   { const int cap = ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
   { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
   { int tr = 64, tc = 64; ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);

@@ -38,6 +38,7 @@ struct EkfBatchState {
 };
 
 struct EkfBatchGeom {
+  double2* scratch;         /* [B][4][n]: the pending gains of filters that run off chip */
   int B, cap, n, headroom;
   double gate, enc_noise;
   long long pstride;        /* doubles per filter in the packed covariance array (even: 16-byte aligned filters) */
@@ -58,8 +59,8 @@ __host__ __device__ inline BatchLayout batch_layout(int ns, int n, int cap, int 
   int o = 0;
   l.P = o; o += ((tri(ns) + 1) & ~1) * 8;            /* packed upper triangle, columns < ns */
   l.y = o; o += ((n + 1) & ~1) * 8;
-  l.K = o; o += n * 16;
-  l.KS = o; o += n * 16;
+  l.K = o; o += 2 * ns * 16;                         /* two pending gains: K, then K S (off-chip filters: HBM scratch) */
+  l.KS = o; o += 2 * ns * 16;
   l.ext = o; o += ((m + 3) & ~3) * 4;
   l.matched = o; o += (cap + 15) & ~15;
   l.bytes = o;
@@ -92,41 +93,71 @@ __device__ __forceinline__ void b_bulk_store(void* dst, const void* src, unsigne
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(b_smem_u32(src)), "r"(bytes) : "memory");
 }
 
-/* Robot.cpp:564-568 on the COLD elements of the packed upper triangle, p <- p - (K S)[r] K[q]: column q >= 3, rows 3 up
- * to (excluding) its landmark's 2x2 diagonal block; rows 0..2 and the diagonal blocks are the hot part (phase A of the
- * line loop).  Columns are taken two at a time, a long one with a short one, so that one load of (K S)[r] serves both;
- * a lane walks consecutive rows (conflict-free).  Warp w0 of nw. */
-__device__ __forceinline__ void batch_update_cold(double* __restrict__ P, const double2* __restrict__ Ks,
-                                                  const double2* __restrict__ KSs, int nl, int w0, int nw, int lane) {
-  const int ncol = nl - 3;                                  /* columns 3 .. nl-1 */
-  const int npair = (ncol + 1) >> 1;
-  for (int c = w0; c < npair; c += nw) {
-    const int qs = 3 + c, ql = nl - 1 - c;                  /* short and long column of the pair (qs <= ql) */
-    const int es = (qs & 1) ? qs : qs - 1, el = (ql & 1) ? ql : ql - 1;      /* first hot row of each */
-    const double2 ks_ = Ks[qs], kl = Ks[ql];
-    double* cs = P + tri(qs);
-    double* cl = P + tri(ql);
-    if (qs == ql) {
-      for (int r = 3 + lane; r < es; r += 32) cs[r] = sub_rank2(cs[r], KSs[r], ks_);
-      continue;
+/* Robot.cpp:564-568 on the COLD elements of the packed upper triangle, p <- (p - (K S)_0[r] K_0[q]) - (K S)_1[r] K_1[q] for
+ * one or two pending matches in their order: column q >= 3, rows 3 up to (excluding) its landmark's 2x2 diagonal block;
+ * rows 0..2 and the diagonal blocks are the hot part (phase A of the line loop).  A lane owns the rows lane, lane + 32,
+ * lane + 64, lane + 96 and keeps their (K S) entries in registers for the whole pass; it walks consecutive rows of a column
+ * (conflict-free) and takes the columns two at a time, a long one with a short one: per element and pass the shared
+ * memory sees one 8-byte load and one 8-byte store.  Warp w0 of nw. */
+__device__ __forceinline__ void batch_update_cold(double* __restrict__ P, const double2* __restrict__ K0, const double2* __restrict__ KS0,
+                                                  const double2* __restrict__ K1, const double2* __restrict__ KS1, bool two,
+                                                  int nl, int w0, int nw, int lane) {
+  const int npair = (nl - 2) >> 1;                          /* columns 3 .. nl-1 in pairs (3 + c, nl - 1 - c) */
+  for (int rb = 0; rb < nl; rb += 128) {                    /* maps beyond 128 rows: one more sweep per 128 rows */
+    double2 a0[4], a1[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int r = rb + lane + 32 * t;
+      a0[t] = make_double2(0.0, 0.0); a1[t] = a0[t];
+      if (r < nl) { a0[t] = KS0[r]; if (two) a1[t] = KS1[r]; }
     }
-    for (int r = 3 + lane; r < el; r += 64) {               /* two row groups in flight */
-      const int r2 = r + 32;
-      const double2 k1 = KSs[r];
-      const double pl1 = cl[r];
-      double2 k2 = k1; double pl2 = 0.0, ps1 = 0.0, ps2 = 0.0;
-      if (r2 < el) { k2 = KSs[r2]; pl2 = cl[r2]; }
-      if (r < es) ps1 = cs[r];
-      if (r2 < es) ps2 = cs[r2];
-      cl[r] = sub_rank2(pl1, k1, kl);
-      if (r2 < el) cl[r2] = sub_rank2(pl2, k2, kl);
-      if (r < es) cs[r] = sub_rank2(ps1, k1, ks_);
-      if (r2 < es) cs[r2] = sub_rank2(ps2, k2, ks_);
+    for (int c = w0; c < npair; c += nw) {
+      const int qs = 3 + c, ql = nl - 1 - c;                /* short and long column of the pair (qs <= ql) */
+      const int es = (qs & 1) ? qs : qs - 1, el = (ql & 1) ? ql : ql - 1;      /* first hot row of each */
+      if (el <= rb) continue;
+      const double2 ks0 = K0[qs], kl0 = K0[ql];
+      double2 ks1 = ks0, kl1 = kl0;
+      if (two) { ks1 = K1[qs]; kl1 = K1[ql]; }
+      double* cs = P + tri(qs);
+      double* cl = P + tri(ql);
+      double pl[4], ps[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int r = rb + lane + 32 * t;
+        if (r >= 3 && r < el) pl[t] = cl[r];
+        if (r >= 3 && r < es && qs != ql) ps[t] = cs[r];
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int r = rb + lane + 32 * t;
+        if (r >= 3 && r < el) {
+          double p = sub_rank2(pl[t], a0[t], kl0);
+          if (two) p = sub_rank2(p, a1[t], kl1);
+          cl[r] = p;
+        }
+        if (r >= 3 && r < es && qs != ql) {
+          double p = sub_rank2(ps[t], a0[t], ks0);
+          if (two) p = sub_rank2(p, a1[t], ks1);
+          cs[r] = p;
+        }
+      }
     }
   }
 }
 
 /* The whole scan of one filter.  ns: columns of the packed triangle that fit the shared-memory carve-up. */
+#ifdef EKFB_TIMING
+#define BT_DECL long long bt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long bt0_ = clock64()
+#define BT_MARK(k) do { const long long n_ = clock64(); bt_[k] += n_ - bt0_; bt0_ = n_; } while (0)
+#define BT_RESET() bt0_ = clock64()
+#define BT_PRINT() do { if (blockIdx.x == 7 && (threadIdx.x == 0 || threadIdx.x == 32)) printf("k_batch_scan block 7 thread %d, cycles: load %lld predict %lld | per scan: A %lld, B(gate or cold pass) %lld, B-barrier %lld, C %lld, C-barrier %lld | tail %lld\n", (int)threadIdx.x, bt_[0], bt_[1], bt_[2], bt_[3], bt_[4], bt_[5], bt_[6], bt_[7]); } while (0)
+#else
+#define BT_DECL do { } while (0)
+#define BT_MARK(k) do { } while (0)
+#define BT_RESET() do { } while (0)
+#define BT_PRINT() do { } while (0)
+#endif
+
 template <bool ON_CHIP>
 __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int ns, double* __restrict__ Yg,
                                                 double* __restrict__ Pg, EkfBatchState* __restrict__ Sg,
@@ -136,8 +167,10 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   const BatchLayout lay = batch_layout(ns, g.n, g.cap, m);
   double* const Psm = reinterpret_cast<double*>(braw + lay.P);
   double* const ys = reinterpret_cast<double*>(braw + lay.y);
-  double2* const Ks = reinterpret_cast<double2*>(braw + lay.K);
-  double2* const KSs = reinterpret_cast<double2*>(braw + lay.KS);
+  /* pending gains: slot k & 1 holds K and K S of the scan's k-th match */
+  const int kn = ON_CHIP ? ns : g.n;
+  double2* const Ks = ON_CHIP ? reinterpret_cast<double2*>(braw + lay.K) : g.scratch + (size_t)blockIdx.x * 4 * g.n;
+  double2* const KSs = ON_CHIP ? reinterpret_cast<double2*>(braw + lay.KS) : Ks + 2 * (size_t)g.n;
   int* const ext = reinterpret_cast<int*>(braw + lay.ext);
   unsigned char* const matched = braw + lay.matched;
   __shared__ unsigned long long s_bar;
@@ -155,6 +188,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   const double* const R = Rm + 4 * (size_t)m * f;
   int* const jout = Jout ? Jout + (size_t)m * f : 0;
 
+  BT_DECL;
   int L = L0;
   const int nl = 3 + 2 * L;
   const double pose0 = st->pose[0], pose1 = st->pose[1], pose2 = st->pose[2];
@@ -174,6 +208,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   for (int j = tid; j < g.cap; j += nt) matched[j] = 0;
   __syncthreads();
   b_mbar_wait(&s_bar, 0);
+  BT_MARK(0);
 
   /* ---- prediction, Robot.cpp:130-258 ---- */
   const double u0 = u[0], u2 = u[2];
@@ -227,29 +262,35 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
 
   /* ---- the observed lines in order, Robot.cpp:298-645 ----
    * Per line, three phases separated by block barriers:
-   *   A  (all warps)  the HOT part of the previous match's update: rows 0..2 of every column, the 2x2 diagonal blocks,
-   *                   y, the pose -- everything the next gate reads;
+   *   A  (all warps)  the HOT part of the newest match's update: rows 0..2 of every column, the 2x2 diagonal blocks,
+   *                   y, the pose -- everything a gate reads;
    *   B  warp 0       associates this line (pre-test of every landmark, full gate of the survivors, first fit), WHILE
-   *      warps 1..3   apply the previous match to the cold rest of the triangle;
-   *   C  (all warps)  the gain rows of this line's match (needs the complete P).
+   *      warps 1..3   fold the pending matches into the cold rest of the triangle -- two at a time: a match's cold update
+   *                   waits for the next match, so that P is read and written once per TWO rank-2 terms;
+   *   C  (all warps)  the gain rows of this line's match; a column entry whose pending term is not folded yet is
+   *                   corrected on the fly (same operations, same order).
    * The long dependent chain of a gate (trigonometry, 2x2 LU inverse) thus runs beside the bulk of the update. */
+  BT_MARK(1);
   int ne = 0, nmatch = 0;                                    /* uniform across the block */
   const double gate2x4 = 4.0 * g.gate * g.gate;
-  bool have_prev = false;                                    /* a match whose update of P is still to be applied */
+  int np = 0;                                                /* matches nmatch-np .. nmatch-1: cold part of their update pending */
+  bool have_new = false;                                     /* match nmatch-1: hot part pending too */
   for (int i = 0; i <= m; ++i) {
     const bool gating = i < m;
-    if (!gating && !have_prev) break;
+    if (!gating && np == 0) break;
     /* ---- phase A ---- */
-    if (have_prev) {
+    if (have_new) {
+      const double2* Kn = Ks + (size_t)((nmatch - 1) & 1) * kn;
+      const double2* KSn = KSs + (size_t)((nmatch - 1) & 1) * kn;
       const double v0 = sG.v[0], v1 = sG.v[1];
       for (int q = tid; q < nl; q += nt) {
         double* c = Ps + tri(q);
-        const double2 kq = Ks[q];
+        const double2 kq = Kn[q];
         const int top = q < 3 ? q + 1 : 3;
-        for (int r = 0; r < top; ++r) c[r] = sub_rank2(c[r], KSs[r], kq);           /* :564-568, rows 0..2 */
+        for (int r = 0; r < top; ++r) c[r] = sub_rank2(c[r], KSn[r], kq);           /* :564-568, rows 0..2 */
         if (q >= 3) {
-          if (q & 1) c[q] = sub_rank2(c[q], KSs[q], kq);                             /* (a,a) */
-          else { c[q - 1] = sub_rank2(c[q - 1], KSs[q - 1], kq); c[q] = sub_rank2(c[q], KSs[q], kq); }   /* (a,b), (b,b) */
+          if (q & 1) c[q] = sub_rank2(c[q], KSn[q], kq);                             /* (a,a) */
+          else { c[q - 1] = sub_rank2(c[q - 1], KSn[q - 1], kq); c[q] = sub_rank2(c[q], KSn[q], kq); }   /* (a,b), (b,b) */
           double t = 0.0;                                                            /* :585-589  y += K * delta */
           axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
           ys[q] = add_rn(ys[q], t);
@@ -258,7 +299,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
       if (tid == 0) {
         double yn[3];
         for (int r = 0; r < 3; ++r) {
-          const double2 kk = Ks[r];
+          const double2 kk = Kn[r];
           double t = 0.0;
           axpy_skip(t, kk.x, v0); axpy_skip(t, kk.y, v1);
           yn[r] = add_rn(s_xpre[r], t);
@@ -266,9 +307,12 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
         normalize_radian(yn[2]);                                      /* :596-602 */
         for (int r = 0; r < 3; ++r) { ys[r] = yn[r]; s_xpre[r] = yn[r]; }
       }
+      have_new = false;
       __syncthreads();
     }
+    BT_MARK(2);
     /* ---- phase B ---- */
+    const bool fold = np == 2 || (np == 1 && !gating);
     if (warp == 0 && gating) {
       const double z0 = z[2 * i], z1 = z[2 * i + 1];
       const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
@@ -321,33 +365,51 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
         if (best == EKF_NO_MATCH) { ext[ne] = i; if (jout) jout[i] = -1; }           /* :309 / :325 / :493 */
         else { matched[best] = 1; if (jout) jout[i] = best; }                       /* :501 */
       }
-    } else if (have_prev && (warp != 0 || !gating)) {
-      /* the cold rest of the previous match's update (Robot.cpp:564-568): column q, rows 3 .. its diagonal block */
+    } else if (fold && (warp != 0 || !gating)) {
       const int w0 = gating ? warp - 1 : warp, nw = gating ? nt / 32 - 1 : nt / 32;
-      batch_update_cold(Ps, Ks, KSs, nl, w0, nw, lane);
+      const int s0 = (nmatch - np) & 1;                               /* the older pending match first */
+      batch_update_cold(Ps, Ks + (size_t)s0 * kn, KSs + (size_t)s0 * kn, Ks + (size_t)(s0 ^ 1) * kn, KSs + (size_t)(s0 ^ 1) * kn,
+                        np == 2, nl, w0, nw, lane);
     }
+    BT_MARK(3);
     __syncthreads();
+    BT_MARK(4);
+    if (fold) np = 0;
     if (!gating) break;
     const int jb = s_best;
-    if (jb == EKF_NO_MATCH) { ne += 1; have_prev = false; continue; }
+    if (jb == EKF_NO_MATCH) { ne += 1; continue; }
     /* ---- phase C: Robot.cpp:516-560 ---- */
-    const int a = 3 + 2 * jb, bb = a + 1;
-    const int ta = tri(a), tb = tri(bb);
-    for (int r = tid; r < nl; r += nt) {
-      const int tr_ = tri(r);
-      const double p0 = (r <= 0) ? Ps[r] : Ps[tr_];                   /* P[r,0..2] through the upper storage */
-      const double p1 = (r <= 1) ? Ps[tri(1) + r] : Ps[tr_ + 1];
-      const double p2 = (r <= 2) ? Ps[tri(2) + r] : Ps[tr_ + 2];
-      const double pa = (r <= a) ? Ps[ta + r] : Ps[tr_ + a];
-      const double pb = (r <= bb) ? Ps[tb + r] : Ps[tr_ + bb];
-      double2 Kr, KSr;
-      gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
-      Ks[r] = Kr; KSs[r] = KSr;
+    {
+      const int a = 3 + 2 * jb, bb = a + 1;
+      const int ta = tri(a), tb = tri(bb);
+      const double2* Kp = Ks + (size_t)((nmatch - 1) & 1) * kn;       /* the pending match, if any (np == 1) */
+      const double2* KSp = KSs + (size_t)((nmatch - 1) & 1) * kn;
+      double2* Kw = Ks + (size_t)(nmatch & 1) * kn;
+      double2* KSw = KSs + (size_t)(nmatch & 1) * kn;
+      double2 kpa = make_double2(0.0, 0.0), kpb = kpa, kspa = kpa, kspb = kpa;
+      if (np == 1) { kpa = Kp[a]; kpb = Kp[bb]; kspa = KSp[a]; kspb = KSp[bb]; }
+      for (int r = tid; r < nl; r += nt) {
+        const int tr_ = tri(r);
+        const double p0 = (r <= 0) ? Ps[r] : Ps[tr_];                 /* P[r,0..2] through the upper storage */
+        const double p1 = (r <= 1) ? Ps[tri(1) + r] : Ps[tr_ + 1];
+        const double p2 = (r <= 2) ? Ps[tri(2) + r] : Ps[tr_ + 2];
+        double pa = (r <= a) ? Ps[ta + r] : Ps[tr_ + a];
+        double pb = (r <= bb) ? Ps[tb + r] : Ps[tr_ + bb];
+        if (np == 1 && r > 2 && r != a && r != bb) {                  /* cold entries: the pending term, on the fly */
+          if (r < a) { const double2 ksr = KSp[r]; pa = sub_rank2(pa, ksr, kpa); pb = sub_rank2(pb, ksr, kpb); }
+          else { const double2 kr = Kp[r]; pa = sub_rank2(pa, kspa, kr); pb = sub_rank2(pb, kspb, kr); }
+        }
+        double2 Kr, KSr;
+        gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
+        Kw[r] = Kr; KSw[r] = KSr;
+      }
     }
-    have_prev = true;
-    nmatch += 1;
+    nmatch += 1; np += 1; have_new = true;
+    BT_MARK(5);
     __syncthreads();
+    BT_MARK(6);
   }
+  BT_RESET();
 
   /* ---- Robot.cpp:702-716 ---- */
   const double ps0 = s_xpre[0], ps1 = s_xpre[1];
@@ -439,6 +501,8 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     st->resets += resets;
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
+  BT_MARK(7);
+  BT_PRINT();
 }
 
 /* Robot::localize for filter blockIdx.x */
@@ -466,6 +530,7 @@ struct ekf_batch {
   EkfBatchGeom g;
   cudaStream_t stream;
   double* d_y; double* d_P; EkfBatchState* d_st;
+  double2* d_scratch;               /* pending gains of filters running off chip: [B][4][n] */
   int max_m;
   double* d_in; double* h_in;       /* [u (3B) | z (2 m B) | R (4 m B)] */
   int* d_jout; int* h_jout;
@@ -585,6 +650,8 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   CUB(cudaMalloc(&b->d_y, B * (size_t)g.ystride * sizeof(double)));
   CUB(cudaMalloc(&b->d_P, B * (size_t)g.pstride * sizeof(double)));
   CUB(cudaMalloc(&b->d_st, B * sizeof(EkfBatchState)));
+  CUB(cudaMalloc(&b->d_scratch, B * 4 * (size_t)g.n * sizeof(double2)));
+  g.scratch = b->d_scratch;
   CUB(cudaMallocHost(&b->h_st, B * sizeof(EkfBatchState)));
   CUB(cudaMallocHost(&b->h_P, (size_t)g.pstride * sizeof(double)));
   CUB(cudaMemsetAsync(b->d_y, 0, B * (size_t)g.ystride * sizeof(double), b->stream));
@@ -603,7 +670,7 @@ int ekf_batch_destroy(ekf_batch* b) {
   if (!b) return EKF_EINVAL;
   cudaSetDevice(b->cfg.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_in); cudaFree(b->d_jout);
+  cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_scratch); cudaFree(b->d_in); cudaFree(b->d_jout);
   cudaFreeHost(b->h_in); cudaFreeHost(b->h_jout); cudaFreeHost(b->h_st); cudaFreeHost(b->h_P);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;

@@ -110,6 +110,7 @@ cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const vo
                                  const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
                                  int num_sms, cudaStream_t s);
 void ekf_sweep_shape(int shape, int* tr, int* tc);
+void ekf_sweep_pbox(int shape, int* rows, int* cols);
 int ekf_sweep_terms_per_pass(int shape, int np_ub);
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                 int m, int L_ub, int slot0, EkfScanView* view, cudaStream_t s);

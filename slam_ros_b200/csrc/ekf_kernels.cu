@@ -825,7 +825,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
 
 /* The producer of both pipelined sweep kernels: ONE thread streams the CTA's tiles (and the matching slices of
  * the pending lists) into the shared-memory ring. */
-template <int TR, int TC, int STAGES, int C>
+template <int TR, int TC, int STAGES, int C, bool BOX8 = false>
 __device__ __forceinline__ void sweep_producer(SweepShared<TR, TC, STAGES, C>& sh, const EkfGeom& g, const EkfBuffers& b,
                                                const CUtensorMap& tmapP, const CUtensorMap& tmapK, const CUtensorMap& tmapKS,
                                                int c0, int slot0, int np, int nl, unsigned long long* tile_counter, int sentinels) {
@@ -864,7 +864,14 @@ __device__ __forceinline__ void sweep_producer(SweepShared<TR, TC, STAGES, C>& s
     sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
     unsigned long long* fullb = &sh.full[s][sentinels > 1 ? (it & 1) : 0];     /* the barrier of the group that consumes tile `it` */
     mbar_expect_tx(fullb, bytes);
-    tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, fullb, pol);
+    if (BOX8) {
+      /* the tile as eight 64-row x 8-column boxes, each dense in shared memory (row pitch 64 B): the layout the
+       * tensor-core consumers read their 8x8 accumulator fragments from without bank conflicts (k_sweep_dmma) */
+#pragma unroll
+      for (int bx = 0; bx < TC / 8; ++bx) tma_load_tile_hint(sh.stage[s].P + bx * TR * 8, &tmapP, col0 + 8 * bx, lrow0, fullb, pol);
+    } else {
+      tma_load_tile_hint(sh.stage[s].P, &tmapP, col0, lrow0, fullb, pol);
+    }
     if (band) {
       for (int bi = 0; bi < nbands; ++bi) {
         tma_load_tile(sh.stage[s].K[8 * bi], &tmapK, 2 * col0, slot0 + c0 + 8 * bi, fullb);
@@ -1062,6 +1069,104 @@ k_sweep_quad(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
           const int qa = col0 + cA, qb = col0 + cB;
           if (qa + 1 < nl) __stcs(reinterpret_cast<double2*>(Pr + cA), pa[i]); else if (qa < nl) Pr[cA] = pa[i].x;
           if (qb + 1 < nl) __stcs(reinterpret_cast<double2*>(Pr + cB), pb[i]); else if (qb < nl) Pr[cB] = pb[i].x;
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* k_sweep_dmma: the same pass on the fp64 tensor cores (north_star: "DMMA only if batched observations make the update a
+ * genuine dense contraction" -- from ~12 pending terms on the DFMA form above is bound by fp64 issue and shared-memory
+ * operand delivery, not by HBM).  P_tile(64x64) -= KS_tile(64 x 2m) * K_tile'(2m x 64) as mma.sync.m8n8k4.f64:
+ *   A[row][k]  = -(K S)_{c + k/2}[row].{x, y}      B[k][col] = K_{c + k/2}[col].{x, y}      k = 0..3: two pending terms
+ * Measured on B200 (scripts/dmma_probe.cu, profiles/r2_dmma_probe.log): the instruction accumulates as the chain
+ * d = fma(a_k, b_k, d), k = 0..3 in order, one rounding per step -- bit for bit sub_rank2() applied term after term -- at
+ * 37 TFLOP/s against 34 for DFMA, with 8x fewer issue slots per flop and operands that stay in registers across 16 MMAs.
+ * Same ring and producer as k_sweep_quad; the producer lands the P tile as eight 64 x 8 boxes (row pitch 64 B) so that
+ * a warp's accumulator-fragment load -- lane (g, t) takes row g, columns 2t, 2t+1 of an 8x8 block -- is one conflict-free
+ * LDS.128.  A warp owns 16 rows x 64 columns: 2 x 8 blocks, 32 doubles per lane; per two terms it loads 2 + 8 operand
+ * words and issues 16 MMAs. */
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+template <int STAGES, int C>
+__global__ void __launch_bounds__(9 * 32, 1)
+k_sweep_dmma(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapK,
+             const __grid_constant__ CUtensorMap tmapKS, double* __restrict__ dst, int c0,
+             int slot0, const EkfScanView* __restrict__ view, unsigned long long* __restrict__ tile_counter) {
+  constexpr int TR = 64, TC = 64, CW = 8;
+  typedef SweepShared<TR, TC, STAGES, C> Shared;
+  extern __shared__ unsigned char sw_raw[];
+  Shared& sh = *reinterpret_cast<Shared*>(sw_raw + ((1024u - (smem_u32(sw_raw) & 1023u)) & 1023u));
+  const int np_all = view ? view->cnt : b.st->np;
+  const int np = max(0, min(C, np_all - c0));
+  if (np <= 0 && (dst == b.P || c0 > 0)) return;
+  const int nl = 3 + 2 * (view ? view->L : b.st->L);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s][0], 1); mbar_init(&sh.full[s][1], 1); mbar_init(&sh.empty[s], CW / 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == CW) {
+    if (lane == 0) sweep_producer<TR, TC, STAGES, C, true>(sh, g, b, tmapP, tmapK, tmapKS, c0, slot0, np, nl, tile_counter, 2);
+    return;
+  }
+  /* ---------------- consumers: 2 groups x 4 warps, a warp = rows 16 (warp & 3) .. + 15 of the tile ---------------- */
+  const int grp = warp >> 2;
+  const int gq = lane >> 2, tq = lane & 3;                   /* fragment coordinates of this lane */
+  const int row0 = 16 * (warp & 3) + gq;                     /* its rows: row0, row0 + 8 */
+  const int comp = tq & 1, tsel = tq >> 1;                   /* operand word: component x / y of term (k0 + tsel) */
+  constexpr int PERIOD = (STAGES % 2) ? 2 * STAGES : STAGES;
+  for (int it = grp;; it += 2) {
+    const int s = it % STAGES;
+    const unsigned ph = (it / PERIOD) & 1;
+    mbar_wait(&sh.full[s][grp], ph);
+    if (!sh.meta[s][3]) break;
+    const SweepStage<TR, TC, C>& st = sh.stage[s];
+    const int lrow0 = sh.meta[s][0], grow0 = sh.meta[s][1], col0 = sh.meta[s][2];
+    double2 acc[2][8];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+        acc[mb][nb] = *reinterpret_cast<const double2*>(&st.P[(nb * TR + row0 + 8 * mb) * 8 + 2 * tq]);
+    const double* KSw = reinterpret_cast<const double*>(&st.KS[0][0]);
+    const double* Kw = reinterpret_cast<const double*>(&st.K[0][0]);
+#pragma unroll 2
+    for (int k0 = 0; k0 < np; k0 += 2) {
+      const int term = k0 + tsel;
+      const bool valid = term < np;                          /* odd count: the last step's second term is zero */
+      double a[2], bq[8];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) a[mb] = valid ? -KSw[(term * TR + row0 + 8 * mb) * 2 + comp] : 0.0;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) bq[nb] = valid ? Kw[(term * TC + 8 * nb + gq) * 2 + comp] : 0.0;
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) dmma884(acc[mb][nb].x, acc[mb][nb].y, a[mb], bq[nb]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sh.empty[s]);
+    double* Pt = dst + ((size_t)lrow0 + row0) * g.ld + (size_t)col0 + 2 * tq;
+    if (grow0 + TR <= nl && col0 + TC <= nl) {
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) __stcs(reinterpret_cast<double2*>(Pt + (size_t)(8 * mb) * g.ld + 8 * nb), acc[mb][nb]);
+    } else {
+      /* edge tile: dead rows / columns are left alone (see k_sweep_pipe) */
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        if (grow0 + row0 + 8 * mb < nl) {
+          double* Pr = Pt + (size_t)(8 * mb) * g.ld;
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) {
+            const int q = col0 + 8 * nb + 2 * tq;
+            if (q + 1 < nl) __stcs(reinterpret_cast<double2*>(Pr + 8 * nb), acc[mb][nb]); else if (q < nl) Pr[8 * nb] = acc[mb][nb].x;
+          }
         }
       }
     }
@@ -1447,12 +1552,41 @@ static cudaError_t launch_sweep_quad(const EkfGeom& g, const EkfBuffers& b, cons
   }
   return cudaSuccess;
 }
+template <int STAGES, int C>
+static cudaError_t launch_sweep_dmma(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, const CUtensorMap* mK,
+                                     const CUtensorMap* mKS, double* dst, int slot0,
+                                     const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s) {
+  const size_t smem = sizeof(SweepShared<64, 64, STAGES, C>) + 1024;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_dmma<STAGES, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  if (counters) {   /* one tile counter per pass */
+    cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * ((np_ub + C - 1) / C), s);
+    if (e != cudaSuccess) return e;
+  }
+  for (int c0 = 0; c0 < np_ub; c0 += C) {
+    k_sweep_dmma<STAGES, C><<<grid, 9 * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+/* box of the TMA map of P: the tile itself, except for the tensor-core sweep (shape 10: eight 64 x 8 boxes per tile) */
+void ekf_sweep_pbox(int shape, int* rows, int* cols) {
+  if (shape == 10) { *rows = 64; *cols = 8; return; }
+  ekf_sweep_shape(shape, rows, cols);
+}
 void ekf_sweep_shape(int shape, int* tr, int* tc) {
   switch (shape) { case 1: case 5: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }
 }
 /* terms one pass of the sweep folds for a scan with np_ub pending terms */
 int ekf_sweep_terms_per_pass(int shape, int np_ub) {
-  if (shape != 0 && shape != 9) return SW_C;
+  if (shape != 0 && shape != 9 && shape != 10) return SW_C;
   static int cap = -1;
   if (cap < 0) { const char* e = getenv("EKF_SWEEP_MAXC"); cap = e ? atoi(e) : 32; if (cap != 8 && cap != 16 && cap != 32) cap = 32; }
   const int want = np_ub <= 8 ? 8 : (np_ub <= 16 ? 16 : 32);
@@ -1476,6 +1610,10 @@ cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const vo
     case 4: return launch_sweep_shape<64, 64, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
     case 5: return launch_sweep_shape<32, 128, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
     case 8: return launch_sweep_shape<64, 64, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);   /* 148 KB: leaves room for a co-resident line-loop CTA */
+    case 10:       /* fp64 tensor cores (k_sweep_dmma) */
+      if (C == 32) return launch_sweep_dmma<2, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (C == 16) return launch_sweep_dmma<3, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      return launch_sweep_dmma<4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
     case 9:        /* the 8-rows x 2-columns-per-lane consumers (A/B against k_sweep_quad) */
       if (C == 32) return launch_sweep_shape<64, 64, 2, 8, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
       if (C == 16) return launch_sweep_shape<64, 64, 3, 8, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);

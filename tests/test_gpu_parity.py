@@ -480,6 +480,52 @@ def test_overlapped_pipeline_interleaved_with_stepwise_calls(libekf, oracle_cls)
     compare_state(f, so, "interleaved final")
 
 
+@pytest.mark.parametrize("shape", [0, 9, 10])
+def test_sweep_kernels_give_identical_bits(libekf, shape):
+    """EKF_SWEEP_SHAPE selects the consumers of the pipelined sweep: 0 = k_sweep_quad (8x4 register tiles, DFMA),
+    9 = k_sweep_pipe (8x2), 10 = k_sweep_dmma (fp64 tensor cores: mma.sync.m8n8k4.f64 accumulates as the k-ordered FMA
+    chain, i.e. sub_rank2 term after term -- measured, scripts/dmma_probe.cu).  Same scans, m = 8 / 13 / 32 / 40 lines
+    (odd counts: the tensor-core step's zero-padded second term; > 32: two passes): the downloaded state must equal the
+    default build's bit for bit, and the oracle's within 1e-9."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from slam_ros_b200 import EkfFilter, scenario as sc\n"
+        "out = {}\n"
+        "for N, m in ((700, 8), (700, 13), (3300, 32), (3300, 40)):\n"
+        "    scn = sc.map_scenario(N, 5, m=m, seed=3)\n"
+        "    f = EkfFilter(capacity_lines=N + 96)\n"
+        "    f.scan(np.zeros(3), scn['seed_z'], scn['seed_R'])\n"
+        "    J = [f.scan(scn['u'][s], scn['z'][s], scn['R'][s])[1] for s in range(5)]\n"
+        "    y, P, L = f.download_live()\n"
+        "    out['J_%%d_%%d' %% (N, m)] = np.stack(J); out['y_%%d_%%d' %% (N, m)] = y; out['P_%%d_%%d' %% (N, m)] = P\n"
+        "    f.close()\n"
+        "np.savez(sys.argv[1], **out)\n"
+    ) % ROOT
+    res = []
+    for sh in (0, shape):
+        path = "/tmp/ekf_shape_%d_%d.npz" % (sh, os.getpid())
+        env = dict(os.environ, EKF_SWEEP_SHAPE=str(sh))
+        out = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, timeout=600, env=env)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        res.append(dict(np.load(path)))
+        os.remove(path)
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+    # and against the oracle, for the largest case
+    from oracle.oracle import StructuredOracle
+    N, m = 3300, 40
+    scn = sc.map_scenario(N, 5, m=m, seed=3)
+    so = StructuredOracle(N + 96, threads=0)
+    so.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
+    Jo = np.stack([so.scan(scn["u"][s], scn["z"][s], scn["R"][s])[1] for s in range(5)])
+    yo, Po = so.live()
+    assert np.array_equal(res[1]["J_3300_40"], Jo)
+    assert rel(res[1]["P_3300_40"], Po) < TOL and rel(res[1]["y_3300_40"], yo) < TOL
+
+
 @pytest.mark.parametrize("maxc", [8, 16, 32])
 def test_sweep_ring_for_every_pending_count_and_pass_width(libekf, maxc):
     """The stand-alone sweep for every pending-term count 1..64 and every pass width (EKF_SWEEP_MAXC), state
