@@ -752,9 +752,14 @@ def run_monte_carlo(args, rank, world, local):
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         dist.barrier()
+    # end to end: every step's inputs come from host memory and its matches + poses go back to host memory; the host
+    # path is pipelined two deep (ekf_batch_submit / ekf_batch_collect: the inputs of step s+1 travel under step s's kernel)
     t0 = time.perf_counter()
-    for s in range(W + K, W + 2 * K):
-        rc, jj, pose = bt.scan(U[s], Z[s], Rr[s])
+    bt.submit(U[W + K], Z[W + K], Rr[W + K])
+    for s in range(W + K + 1, W + 2 * K):
+        bt.submit(U[s], Z[s], Rr[s])
+        rc, jj, pose = bt.collect()
+    rc, jj, pose = bt.collect()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     bt.close()
     del d_u, d_z, d_R, d_j

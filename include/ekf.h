@@ -194,6 +194,11 @@ int ekf_batch_destroy(ekf_batch* b);
 /* One localize per filter.  u: B x 3, z: B x m x 2, R: B x m x 4, j_out (nullable): B x m, pose (nullable): B x 3. */
 int ekf_batch_scan(ekf_batch* b, const double* u, int m, const double* z, const double* R, int* j_out,
                    double* pose);
+/* The same, pipelined: ekf_batch_submit stages the step's inputs and returns at once (at most two steps in flight: the
+ * inputs of step s+1 are copied while the kernel of step s runs); ekf_batch_collect waits for the OLDEST submitted step
+ * and returns its matches, poses and status.  ekf_batch_scan == submit + collect. */
+int ekf_batch_submit(ekf_batch* b, const double* u, int m, const double* z, const double* R);
+int ekf_batch_collect(ekf_batch* b, int* j_out, double* pose);
 int ekf_batch_scan_device(ekf_batch* b, const double* d_u, int m, const double* d_z, const double* d_R,
                           int* d_j_out);
 int ekf_batch_sync(ekf_batch* b);

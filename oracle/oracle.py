@@ -210,8 +210,10 @@ class LiteralReference:
     (Robot.h:13); big=True: the same sources with LINESIZE = 1000 / SLAMSIZE = 2003 (oracle/_ref/libslamref1k.so,
     BASELINE configs[1]) -- its localize needs ~300 MB of stack and runs on a dedicated thread."""
 
-    def __init__(self, big=False, opt0=False):
-        so = _REF1K_SO if big else (_REF_O0_SO if opt0 else _REF_SO)
+    def __init__(self, big=False, opt0=False, so_path=None):
+        """so_path: another library with the same harness ABI (oracle/_ref/libslamdropin.so: the drop-in built on the
+        reference's headers)."""
+        so = so_path or (_REF1K_SO if big else (_REF_O0_SO if opt0 else _REF_SO))
         self._big = bool(big)
         if not os.path.exists(so):
             build()
@@ -236,6 +238,20 @@ class LiteralReference:
 
     __del__ = close
 
+    def localize_intervals(self, z, R, encoder, intervals):
+        """Robot::localize with line::lineInterval set (intervals: m x 4 = two (alfa, r) end points per line);
+        returns Robot::lineIntervals.data as the call left it (Robot.cpp:868-879), float32."""
+        ea, ep = _d(encoder)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 4)
+        iv = np.ascontiguousarray(intervals, dtype=np.float64).reshape(-1, 4)
+        assert iv.shape[0] == z.shape[0] and not self._big
+        out = np.zeros(4 * z.shape[0] + 4, dtype=np.float32)
+        self._lib.ref_localize_iv.restype = C.c_int
+        n = self._lib.ref_localize_iv(self._h, C.c_int(z.shape[0]), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp), ep,
+                                      iv.ctypes.data_as(_dp), out.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(out.size))
+        return out[:n].copy()
+
     def localize(self, z, R, encoder):
         ea, ep = _d(encoder)
         z = np.ascontiguousarray(z, dtype=np.float64).reshape(-1, 2)
@@ -247,8 +263,12 @@ class LiteralReference:
         else:
             self._lib.ref_localize(self._h, C.c_int(z.shape[0]), z.ctypes.data_as(_dp), R.ctypes.data_as(_dp), ep)
 
-    def state(self):
-        y = np.zeros(self.n); P = np.zeros((self.n, self.n)); L = C.c_int(0); pose = np.zeros(3)
+    def state(self, want_cov=True):
+        L = C.c_int(0); pose = np.zeros(3)
+        if not want_cov:
+            self._lib.ref_get(self._h, None, None, C.byref(L), pose.ctypes.data_as(_dp))
+            return None, None, int(L.value), pose
+        y = np.zeros(self.n); P = np.zeros((self.n, self.n))
         self._lib.ref_get(self._h, y.ctypes.data_as(_dp), P.ctypes.data_as(_dp), C.byref(L), pose.ctypes.data_as(_dp))
         return y, P, int(L.value), pose
 

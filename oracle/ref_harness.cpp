@@ -44,8 +44,13 @@ int ref_slamsize(void) { return SLAMSIZE; }
 double ref_gate(void) { return MAHALANOBIS; }
 double ref_encoder_noise(void) { return ENCODERNOISE; }
 
-/* one Robot::localize call; z = m x (alfa, r), R = m x 4 (row-major C_AR), encoder = 3 doubles */
-int ref_localize(void* h, int m, const double* z, const double* R, const double* encoder) {
+/* one Robot::localize call; z = m x (alfa, r), R = m x 4 (row-major C_AR), encoder = 3 doubles.
+ * iv (nullable) = m x 4: the two end points (alfa, r) of every line, i.e. what LineExtraction leaves in
+ * line::lineInterval (simplifyPath.h:75; written field by field: the polar_point(alfa, r) constructor would scale alfa).
+ * out_iv (nullable, max_out floats) receives Robot::lineIntervals.data as the call left it (Robot.cpp:868-879: four
+ * floats per appended line); the return value is its length. */
+int ref_localize_iv(void* h, int m, const double* z, const double* R, const double* encoder, const double* iv,
+                    float* out_iv, int max_out) {
   Robot* rb = (Robot*)h;
   std::vector<line> lines((size_t)m);
   for (int i = 0; i < m; ++i) {
@@ -53,11 +58,22 @@ int ref_localize(void* h, int m, const double* z, const double* R, const double*
     lines[i].r = z[2 * i + 1];
     lines[i].C_AR = gsl_matrix_alloc(2, 2);
     for (int t = 0; t < 4; ++t) lines[i].C_AR->data[t] = R[4 * i + t];
+    if (iv) {
+      polar_point p0, p1;
+      p0.alfa = iv[4 * i]; p0.r = iv[4 * i + 1]; p1.alfa = iv[4 * i + 2]; p1.r = iv[4 * i + 3];
+      lines[i].lineInterval.push_back(p0); lines[i].lineInterval.push_back(p1);
+    }
   }
   float rot[2] = {0.f, 0.f};
   rb->localize(lines, rot, encoder);
   for (int i = 0; i < m; ++i) gsl_matrix_free(lines[i].C_AR);
-  rb->lineIntervals.data.clear();
+  const int n = (int)rb->lineIntervals.data.size();
+  if (out_iv) for (int i = 0; i < n && i < max_out; ++i) out_iv[i] = rb->lineIntervals.data[i];
+  rb->lineIntervals.data.clear();                 /* main.cpp:172-174 publishes, then clears */
+  return n;
+}
+int ref_localize(void* h, int m, const double* z, const double* R, const double* encoder) {
+  ref_localize_iv(h, m, z, R, encoder, 0, 0, 0);
   return 0;
 }
 /* The same call on a thread with a stack of `stack_mb` MB: Robot::localize keeps ~8 SLAMSIZE^2 arrays of doubles on
@@ -78,6 +94,9 @@ int ref_localize_bigstack(void* h, int m, const double* z, const double* R, cons
 }
 void ref_get(void* h, double* y, double* P, int* L, double* pose) {
   Robot* rb = (Robot*)h;
+#ifdef EKF_DROPIN
+  if (y || P) rb->measure();      /* dropin/Robot_cuda.cpp: the covariance lives in HBM, host mirrors on demand */
+#endif
   if (y) std::memcpy(y, rb->y, sizeof(double) * SLAMSIZE);
   if (P) std::memcpy(P, rb->P_t0, sizeof(double) * SLAMSIZE * SLAMSIZE);
   if (L) *L = rb->savedLineCount;

@@ -80,6 +80,8 @@ struct ekf_ctx {
   cudaStream_t wstream;
   double* Pbuf[2];
   CUtensorMap tmap2[2];
+  CUtensorMap tmap8[2];        /* the same buffers as 64-row x 8-column boxes (tensor-core sweep, k_sweep_dmma) */
+  int have_tmap8;
   CUtensorMap tmapK[2];        /* [0]: K bands (box = tile columns x 8 slots), [1]: K S bands (box = tile rows x 8 slots) */
   int rd, par, group;
   int pg_valid, pg_slot0;
@@ -196,7 +198,7 @@ int ensure_lines(ekf_ctx* ctx, int m) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_tensor_map(ekf_ctx* ctx, size_t p_rows, double* base, CUtensorMap* out) {
+int make_tensor_map(ekf_ctx* ctx, size_t p_rows, double* base, CUtensorMap* out, int pshape = -1) {
   void* fn = 0;
   cudaDriverEntryPointQueryResult q;
   CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -204,7 +206,7 @@ int make_tensor_map(ekf_ctx* ctx, size_t p_rows, double* base, CUtensorMap* out)
   const cuuint64_t gdim[2] = {(cuuint64_t)ctx->g.ld, (cuuint64_t)p_rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ctx->g.ld * sizeof(double)};
   int tr = 64, tc = 64;
-  ekf_sweep_pbox(ctx->sweep_shape, &tr, &tc);
+  ekf_sweep_pbox(pshape >= 0 ? pshape : ctx->sweep_shape, &tr, &tc);
   const cuuint32_t box[2] = {(cuuint32_t)tc, (cuuint32_t)tr};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
@@ -236,7 +238,7 @@ int launch_sweep(ekf_ctx* ctx, int np_ub) {
     CU(ekf_launch_sweep(ctx->g, ctx->b, 0, np_ub, ctx->L_ub, ctx->stream));
     ctx->launches++;
   } else {
-    CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmap2[ctx->rd], &ctx->tmapK[0], &ctx->tmapK[1], ctx->b.P, 0, 0, ctx->d_counters, ctx->sweep_shape, np_ub,
+    CU(ekf_launch_sweep_tma(ctx->g, ctx->b, &ctx->tmap2[ctx->rd], ctx->have_tmap8 ? &ctx->tmap8[ctx->rd] : 0, &ctx->tmapK[0], &ctx->tmapK[1], ctx->b.P, 0, 0, ctx->d_counters, ctx->sweep_shape, np_ub,
                             ctx->L_ub, ctx->num_sms, ctx->stream));
     const int per_pass = ekf_sweep_terms_per_pass(ctx->sweep_shape, np_ub);
     ctx->launches += (np_ub + per_pass - 1) / per_pass;
@@ -375,7 +377,7 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
   }
   long long lub = (long long)ctx->L_ub + m;
   const int L_after_ub = (int)(lub > ctx->g.cap ? ctx->g.cap : lub);
-  CU(ekf_launch_sweep_tma(ctx->g, bt, &ctx->tmap2[tgt], &ctx->tmapK[0], &ctx->tmapK[1], ctx->Pbuf[tgt ^ 1], slot0, &ctx->d_view[par], ctx->d_counters + 16,
+  CU(ekf_launch_sweep_tma(ctx->g, bt, &ctx->tmap2[tgt], ctx->have_tmap8 ? &ctx->tmap8[tgt] : 0, &ctx->tmapK[0], &ctx->tmapK[1], ctx->Pbuf[tgt ^ 1], slot0, &ctx->d_view[par], ctx->d_counters + 16,
                           ctx->sweep_shape, m, L_after_ub, ctx->num_sms - EKF_LINE_SMS, ctx->wstream));
   ctx->launches += 1;
   if (ctx->prof) {
@@ -481,6 +483,7 @@ int enable_overlap(ekf_ctx* ctx) {
   CU(cudaEventCreateWithFlags(&ctx->evF[0], cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&ctx->evF[1], cudaEventDisableTiming));
   { int rc = make_tensor_map(ctx, (size_t)ekf_local_tile_rows(ctx->g) * EKF_TILE, ctx->Pbuf[1], &ctx->tmap2[1]); if (rc) return rc; }
+  if (ctx->have_tmap8) { int rc = make_tensor_map(ctx, (size_t)ekf_local_tile_rows(ctx->g) * EKF_TILE, ctx->Pbuf[1], &ctx->tmap8[1], 10); if (rc) return rc; }
   ekf_prefer_max_smem_carveout();
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->rd = 0; ctx->par = 0; ctx->pg_valid = 0;
@@ -541,9 +544,11 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9 && ctx->sweep_shape != 10) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
+  { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9 && ctx->sweep_shape != 10 && ctx->sweep_shape != 11) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
   { const int cap = ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
   { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
+  ctx->have_tmap8 = (ctx->sweep_shape == 0 || ctx->sweep_shape == 10);
+  if (ctx->have_tmap8) { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap8[0], 10); if (rc) return rc; }
   { int tr = 64, tc = 64; ekf_sweep_shape(ctx->sweep_shape, &tr, &tc);
     int rc = make_band_map(ctx, ctx->b.Kp, tc, &ctx->tmapK[0]); if (rc) return rc;
     rc = make_band_map(ctx, ctx->b.KSp, tr, &ctx->tmapK[1]); if (rc) return rc; }

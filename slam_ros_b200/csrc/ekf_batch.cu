@@ -528,12 +528,18 @@ __global__ void k_batch_init(EkfBatchGeom g, double* Pg) {
 struct ekf_batch {
   ekf_config cfg;
   EkfBatchGeom g;
-  cudaStream_t stream;
+  cudaStream_t stream;              /* kernels and read-backs */
+  cudaStream_t cstream;             /* input copies of the pipelined host path (overlap the previous step's kernel) */
   double* d_y; double* d_P; EkfBatchState* d_st;
   double2* d_scratch;               /* pending gains of filters running off chip: [B][4][n] */
   int max_m;
-  double* d_in; double* h_in;       /* [u (3B) | z (2 m B) | R (4 m B)] */
-  int* d_jout; int* h_jout;
+  /* two staging slots: ekf_batch_scan uses slot 0; ekf_batch_submit / ekf_batch_collect alternate */
+  double* d_in[2]; double* h_in[2];       /* [u (3B) | z (2 m B) | R (4 m B)] */
+  int* d_jout[2]; int* h_jout[2];
+  EkfBatchState* h_sts[2];
+  cudaEvent_t ev_in[2], ev_done[2];
+  int slot_m[2];
+  int head, inflight;               /* oldest submitted slot, submitted-but-not-collected steps (0..2) */
   EkfBatchState* h_st;
   double* h_P;                      /* pinned staging of one filter's packed covariance (ekf_batch_download) */
   int L_hint;                       /* largest map of the batch when the states were last read back (sizes the on-chip triangle) */
@@ -578,15 +584,21 @@ int batch_ensure_m(ekf_batch* b, int m) {
     snprintf(b->err, sizeof b->err, "scan of %d lines does not fit shared memory", m);
     return EKF_EINVAL;
   }
+  if (b->inflight) { snprintf(b->err, sizeof b->err, "a scan with more lines than any before (%d) while steps are in flight: collect them first", m); return EKF_ESTATE; }
   CUB(cudaStreamSynchronize(b->stream));
-  cudaFree(b->d_in); cudaFree(b->d_jout); cudaFreeHost(b->h_in); cudaFreeHost(b->h_jout);
-  b->d_in = 0; b->d_jout = 0; b->h_in = 0; b->h_jout = 0;
+  CUB(cudaStreamSynchronize(b->cstream));
   b->max_m = 0;                       /* until every buffer below exists, the next call must come back here */
   const size_t B = b->g.B;
-  CUB(cudaMalloc(&b->d_in, (3 + 6 * (size_t)cap) * B * sizeof(double)));
-  CUB(cudaMallocHost(&b->h_in, (3 + 6 * (size_t)cap) * B * sizeof(double)));
-  CUB(cudaMalloc(&b->d_jout, (size_t)cap * B * sizeof(int)));
-  CUB(cudaMallocHost(&b->h_jout, (size_t)cap * B * sizeof(int)));
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(b->d_in[k]); cudaFree(b->d_jout[k]); cudaFreeHost(b->h_in[k]); cudaFreeHost(b->h_jout[k]);
+    b->d_in[k] = 0; b->d_jout[k] = 0; b->h_in[k] = 0; b->h_jout[k] = 0;
+  }
+  for (int k = 0; k < 2; ++k) {
+    CUB(cudaMalloc(&b->d_in[k], (3 + 6 * (size_t)cap) * B * sizeof(double)));
+    CUB(cudaMallocHost(&b->h_in[k], (3 + 6 * (size_t)cap) * B * sizeof(double)));
+    CUB(cudaMalloc(&b->d_jout[k], (size_t)cap * B * sizeof(int)));
+    CUB(cudaMallocHost(&b->h_jout[k], (size_t)cap * B * sizeof(int)));
+  }
   b->max_m = cap;
   return EKF_OK;
 }
@@ -646,7 +658,13 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   }
   { const char* e = getenv("EKF_BATCH_NS"); b->ns_forced = e ? atoi(e) : 0; if (b->ns_forced < 0) b->ns_forced = 0; if (b->ns_forced > 0 && b->ns_forced < 3) b->ns_forced = 3; }
   CUB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  CUB(cudaStreamCreateWithFlags(&b->cstream, cudaStreamNonBlocking));
   const size_t B = g.B;
+  for (int k = 0; k < 2; ++k) {
+    CUB(cudaEventCreateWithFlags(&b->ev_in[k], cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&b->ev_done[k], cudaEventDisableTiming));
+    CUB(cudaMallocHost(&b->h_sts[k], B * sizeof(EkfBatchState)));
+  }
   CUB(cudaMalloc(&b->d_y, B * (size_t)g.ystride * sizeof(double)));
   CUB(cudaMalloc(&b->d_P, B * (size_t)g.pstride * sizeof(double)));
   CUB(cudaMalloc(&b->d_st, B * sizeof(EkfBatchState)));
@@ -670,9 +688,16 @@ int ekf_batch_destroy(ekf_batch* b) {
   if (!b) return EKF_EINVAL;
   cudaSetDevice(b->cfg.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_scratch); cudaFree(b->d_in); cudaFree(b->d_jout);
-  cudaFreeHost(b->h_in); cudaFreeHost(b->h_jout); cudaFreeHost(b->h_st); cudaFreeHost(b->h_P);
+  if (b->cstream) cudaStreamSynchronize(b->cstream);
+  cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_scratch);
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(b->d_in[k]); cudaFree(b->d_jout[k]); cudaFreeHost(b->h_in[k]); cudaFreeHost(b->h_jout[k]); cudaFreeHost(b->h_sts[k]);
+    if (b->ev_in[k]) cudaEventDestroy(b->ev_in[k]);
+    if (b->ev_done[k]) cudaEventDestroy(b->ev_done[k]);
+  }
+  cudaFreeHost(b->h_st); cudaFreeHost(b->h_P);
   if (b->stream) cudaStreamDestroy(b->stream);
+  if (b->cstream) cudaStreamDestroy(b->cstream);
   delete b;
   return EKF_OK;
 }
@@ -685,35 +710,68 @@ int ekf_batch_scan_device(ekf_batch* b, const double* d_u, int m, const double* 
   return batch_launch(b, d_u, m, d_z, d_R, d_j_out);
 }
 
-int ekf_batch_scan(ekf_batch* b, const double* u, int m, const double* z, const double* R, int* j_out, double* pose) {
+/* Pipelined host path.  ekf_batch_submit copies one step's inputs into a pinned staging slot and enqueues its H2D copy
+ * (on the copy stream), the kernel and the read-back of the matches and states; it returns at once.  Two steps may be
+ * in flight: the inputs of step s+1 travel while the kernel of step s runs.  ekf_batch_collect waits for the OLDEST
+ * submitted step. */
+int ekf_batch_submit(ekf_batch* b, const double* u, int m, const double* z, const double* R) {
   if (!b || !u || m < 0 || (m > 0 && (!z || !R))) return EKF_EINVAL;
+  if (b->inflight >= 2) { snprintf(b->err, sizeof b->err, "two steps are already in flight: ekf_batch_collect first"); return EKF_ESTATE; }
   CUB(cudaSetDevice(b->cfg.device));
   int rc = batch_ensure_m(b, m);
   if (rc) return rc;
+  const int k = (b->head + b->inflight) & 1;
   const size_t B = b->g.B;
-  double* h = b->h_in;
+  double* h = b->h_in[k];
   memcpy(h, u, 3 * B * sizeof(double));
   if (m > 0) {
     memcpy(h + 3 * B, z, 2 * (size_t)m * B * sizeof(double));
     memcpy(h + 3 * B + 2 * (size_t)m * B, R, 4 * (size_t)m * B * sizeof(double));
   }
   const size_t total = (3 + 6 * (size_t)m) * B;
-  CUB(cudaMemcpyAsync(b->d_in, h, total * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-  rc = batch_launch(b, b->d_in, m, b->d_in + 3 * B, b->d_in + 3 * B + 2 * (size_t)m * B, b->d_jout);
+  CUB(cudaMemcpyAsync(b->d_in[k], h, total * sizeof(double), cudaMemcpyHostToDevice, b->cstream));
+  CUB(cudaEventRecord(b->ev_in[k], b->cstream));
+  CUB(cudaStreamWaitEvent(b->stream, b->ev_in[k], 0));
+  rc = batch_launch(b, b->d_in[k], m, b->d_in[k] + 3 * B, b->d_in[k] + 3 * B + 2 * (size_t)m * B, b->d_jout[k]);
   if (rc) return rc;
-  if (j_out && m > 0) CUB(cudaMemcpyAsync(b->h_jout, b->d_jout, (size_t)m * B * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  CUB(cudaMemcpyAsync(b->h_st, b->d_st, B * sizeof(EkfBatchState), cudaMemcpyDeviceToHost, b->stream));
-  CUB(cudaStreamSynchronize(b->stream));
-  if (j_out && m > 0) memcpy(j_out, b->h_jout, (size_t)m * B * sizeof(int));
+  if (m > 0) CUB(cudaMemcpyAsync(b->h_jout[k], b->d_jout[k], (size_t)m * B * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUB(cudaMemcpyAsync(b->h_sts[k], b->d_st, B * sizeof(EkfBatchState), cudaMemcpyDeviceToHost, b->stream));
+  CUB(cudaEventRecord(b->ev_done[k], b->stream));
+  b->slot_m[k] = m;
+  b->inflight += 1;
+  return EKF_OK;
+}
+
+int ekf_batch_collect(ekf_batch* b, int* j_out, double* pose) {
+  if (!b) return EKF_EINVAL;
+  if (b->inflight <= 0) { snprintf(b->err, sizeof b->err, "ekf_batch_collect: nothing was submitted"); return EKF_ESTATE; }
+  CUB(cudaSetDevice(b->cfg.device));
+  const int k = b->head;
+  CUB(cudaEventSynchronize(b->ev_done[k]));
+  const size_t B = b->g.B;
+  const int m = b->slot_m[k];
+  if (j_out && m > 0) memcpy(j_out, b->h_jout[k], (size_t)m * B * sizeof(int));
   int status = EKF_OK, mx = 0;
+  const EkfBatchState* hs = b->h_sts[k];
   for (size_t f = 0; f < B; ++f) {
-    if (pose) memcpy(pose + 3 * f, b->h_st[f].pose, 3 * sizeof(double));
-    if (b->h_st[f].L > mx) mx = b->h_st[f].L;
-    if (b->h_st[f].sticky & EKF_STICKY_CAPACITY) status = EKF_ECAPACITY;
-    else if ((b->h_st[f].sticky & EKF_STICKY_SINGULAR) && status == EKF_OK) status = EKF_ESINGULAR;
+    if (pose) memcpy(pose + 3 * f, hs[f].pose, 3 * sizeof(double));
+    if (hs[f].L > mx) mx = hs[f].L;
+    if (hs[f].sticky & EKF_STICKY_CAPACITY) status = EKF_ECAPACITY;
+    else if ((hs[f].sticky & EKF_STICKY_SINGULAR) && status == EKF_OK) status = EKF_ESINGULAR;
   }
-  b->L_hint = mx; b->L_exact = 1;     /* the states just came back */
+  b->head ^= 1;
+  b->inflight -= 1;
+  b->L_hint = mx;                     /* the largest map as of that step: sizes the on-chip triangle of the next launches */
+  b->L_exact = b->inflight == 0;
   return status;
+}
+
+int ekf_batch_scan(ekf_batch* b, const double* u, int m, const double* z, const double* R, int* j_out, double* pose) {
+  if (!b) return EKF_EINVAL;
+  if (b->inflight) { snprintf(b->err, sizeof b->err, "ekf_batch_scan while submitted steps are in flight: collect them first"); return EKF_ESTATE; }
+  const int rc = ekf_batch_submit(b, u, m, z, R);
+  if (rc) return rc;
+  return ekf_batch_collect(b, j_out, pose);
 }
 
 int ekf_batch_sync(ekf_batch* b) {

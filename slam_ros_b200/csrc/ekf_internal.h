@@ -105,7 +105,7 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
                              cudaStream_t s);
 /* pipelined (TMA + mbarrier) form of the sweep; tmap = CUtensorMap of this rank's P with box (tc, tr) of
  * ekf_sweep_shape(shape); one pass per 8 pending terms */
-cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmapK, const void* tmapKS,
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmap8, const void* tmapK, const void* tmapKS,
                                  double* dst, int slot0,
                                  const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
                                  int num_sms, cudaStream_t s);

@@ -1579,20 +1579,20 @@ static cudaError_t launch_sweep_dmma(const EkfGeom& g, const EkfBuffers& b, cons
 /* box of the TMA map of P: the tile itself, except for the tensor-core sweep (shape 10: eight 64 x 8 boxes per tile) */
 void ekf_sweep_pbox(int shape, int* rows, int* cols) {
   if (shape == 10) { *rows = 64; *cols = 8; return; }
-  ekf_sweep_shape(shape, rows, cols);
+  ekf_sweep_shape(shape == 11 ? 0 : shape, rows, cols);
 }
 void ekf_sweep_shape(int shape, int* tr, int* tc) {
   switch (shape) { case 1: case 5: *tr = 32; *tc = 128; break; case 2: *tr = 16; *tc = 256; break; default: *tr = 64; *tc = 64; }
 }
 /* terms one pass of the sweep folds for a scan with np_ub pending terms */
 int ekf_sweep_terms_per_pass(int shape, int np_ub) {
-  if (shape != 0 && shape != 9 && shape != 10) return SW_C;
+  if (shape != 0 && shape != 9 && shape != 10 && shape != 11) return SW_C;
   static int cap = -1;
   if (cap < 0) { const char* e = getenv("EKF_SWEEP_MAXC"); cap = e ? atoi(e) : 32; if (cap != 8 && cap != 16 && cap != 32) cap = 32; }
   const int want = np_ub <= 8 ? 8 : (np_ub <= 16 ? 16 : 32);
   return want < cap ? want : cap;
 }
-cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmapK, const void* tmapKS,
+cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmap8, const void* tmapK, const void* tmapKS,
                                  double* dst, int slot0,
                                  const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
                                  int num_sms, cudaStream_t s) {
@@ -1602,7 +1602,13 @@ cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const vo
   if (dst != b.P && np_ub > C) return cudaErrorInvalidValue;   /* out-of-place form: one pass only */
   const int grid = tiles < num_sms ? tiles : num_sms;      /* num_sms: SMs this sweep may occupy */
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmap);
+  const CUtensorMap* m8 = reinterpret_cast<const CUtensorMap*>(tmap8);
   const CUtensorMap* mK = reinterpret_cast<const CUtensorMap*>(tmapK);
+  /* default (shape 0): up to 8 pending terms the pass is HBM-bound on the DFMA consumers (k_sweep_quad, 0.96 of the
+   * measured peak inside a step); beyond, the fp64 tensor-core consumers take over (k_sweep_dmma: 1.04 ms against
+   * 1.22 ms at 32 terms, 10k landmarks).  Shape 10 forces the tensor cores for every count, shape 11 never uses them. */
+  if (shape == 11) shape = 0;
+  else if (shape == 0 && np_ub > 8 && m8) shape = 10;
   const CUtensorMap* mKS = reinterpret_cast<const CUtensorMap*>(tmapKS);
   switch (shape) {       /* shape % 4: tile shape; shape / 4: 0 = 8 consumer warps, 1 = 16 */
     case 1: return launch_sweep_shape<32, 128, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
@@ -1611,9 +1617,10 @@ cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const vo
     case 5: return launch_sweep_shape<32, 128, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
     case 8: return launch_sweep_shape<64, 64, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);   /* 148 KB: leaves room for a co-resident line-loop CTA */
     case 10:       /* fp64 tensor cores (k_sweep_dmma) */
-      if (C == 32) return launch_sweep_dmma<2, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      if (C == 16) return launch_sweep_dmma<3, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      return launch_sweep_dmma<4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (!m8) return cudaErrorInvalidValue;
+      if (C == 32) return launch_sweep_dmma<2, 32>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (C == 16) return launch_sweep_dmma<3, 16>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      return launch_sweep_dmma<4, 8>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
     case 9:        /* the 8-rows x 2-columns-per-lane consumers (A/B against k_sweep_quad) */
       if (C == 32) return launch_sweep_shape<64, 64, 2, 8, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
       if (C == 16) return launch_sweep_shape<64, 64, 3, 8, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);

@@ -47,7 +47,7 @@ SYMBOLS = [
     "ekf_get_robot_cov", "ekf_get_ellipse", "ekf_download", "ekf_upload", "ekf_download_live",
     "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_profile_read_lines", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
     "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_shard_ipc_handle", "ekf_shard_connect", "ekf_shard_use_fused", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
-    "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
+    "ekf_batch_submit", "ekf_batch_collect", "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
     "ekf_lx_create", "ekf_lx_destroy", "ekf_lx_last_error", "ekf_lx_extract", "ekf_lx_extract_device", "ekf_lx_sync",
 ]
 
@@ -100,6 +100,8 @@ def load_library():
     lib.ekf_batch_create.argtypes = [C.POINTER(vp), C.POINTER(EkfConfig), C.c_int]
     lib.ekf_batch_destroy.argtypes = [vp]
     lib.ekf_batch_scan.argtypes = [vp, _dp, C.c_int, _dp, _dp, _ip, _dp]
+    lib.ekf_batch_submit.argtypes = [vp, _dp, C.c_int, _dp, _dp]
+    lib.ekf_batch_collect.argtypes = [vp, _ip, _dp]
     lib.ekf_batch_scan_device.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     lib.ekf_batch_sync.argtypes = [vp]
     lib.ekf_batch_download.argtypes = [vp, C.c_int, _dp, _dp, _ip, _dp]
@@ -386,6 +388,22 @@ class EkfBatch:
         j = np.full((self.B, max(m, 1)), -1, dtype=np.int32); pose = np.zeros((self.B, 3))
         rc = self._check(self._lib.ekf_batch_scan(self._h, _p(ua), m, _p(za) if m else None, _p(Ra) if m else None,
                                                   j.ctypes.data_as(_ip), _p(pose)), "ekf_batch_scan",
+                         allow=(EKF_ECAPACITY, EKF_ESINGULAR))
+        return rc, j[:, :m], pose
+
+    def submit(self, u, z, R):
+        """Pipelined host path: stage one step and return at once (at most two in flight); results come from collect()."""
+        ua = _arr(u, (self.B, 3)); za = _arr(z).reshape(self.B, -1, 2); Ra = _arr(R).reshape(self.B, -1, 4)
+        m = za.shape[1]
+        self._check(self._lib.ekf_batch_submit(self._h, _p(ua), m, _p(za) if m else None, _p(Ra) if m else None), "ekf_batch_submit")
+        self._pending = getattr(self, "_pending", [])
+        self._pending.append(m)
+
+    def collect(self):
+        """(status, j_out (B,m), pose (B,3)) of the OLDEST submitted step."""
+        m = self._pending.pop(0)
+        j = np.full((self.B, max(m, 1)), -1, dtype=np.int32); pose = np.zeros((self.B, 3))
+        rc = self._check(self._lib.ekf_batch_collect(self._h, j.ctypes.data_as(_ip), _p(pose)), "ekf_batch_collect",
                          allow=(EKF_ECAPACITY, EKF_ESINGULAR))
         return rc, j[:, :m], pose
 

@@ -32,6 +32,35 @@ class Line:
     lineInterval: List[Tuple[float, float]] = field(default_factory=list)
 
 
+def _libm_float_trig():
+    """cosf / sinf of the C library: `cos(alpha)` with `float alpha` inside Robot.cpp resolves to std::cos(float)
+    (<cmath> + `using namespace std`, simplifyPath.h:16-24), and numpy's float32 kernels round differently."""
+    import ctypes
+    import ctypes.util
+    try:
+        lm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        lm.cosf.restype = ctypes.c_float; lm.cosf.argtypes = [ctypes.c_float]
+        lm.sinf.restype = ctypes.c_float; lm.sinf.argtypes = [ctypes.c_float]
+        return lm.cosf, lm.sinf
+    except Exception:                                     # no C library to ask: numpy's float32 kernels (<= 1 ulp apart)
+        return (lambda a: float(np.cos(np.float32(a)))), (lambda a: float(np.sin(np.float32(a))))
+
+
+_cosf, _sinf = _libm_float_trig()
+
+
+def interval_end_point(alpha, r, x, y, theta):
+    """One end point of an appended line as the node publishes it on `lines` (Robot.cpp:870-873), two float32 values:
+    `float alpha` (:871); cos / sin of that float are the FLOAT functions; polar_point(alfa, r) scales its first
+    argument by PI/180 with PI = 3.14159265 (lineFitting.cpp:71-77, lineFitting.h:12) -- reproduced, it is what the
+    node publishes; polar2descart (lineFitting.cpp:170-176); the result is pushed into a std::vector<float>.
+    Checked float for float against the reference itself (tests/test_oracle.py: 5304 values, 0 differ)."""
+    alpha = float(np.float32(alpha))
+    rad = r + x * float(_cosf(alpha)) + y * float(_sinf(alpha))
+    a = (alpha + theta) * (3.14159265 / 180)
+    return float(np.float32(math.cos(a) * rad)), float(np.float32(math.sin(a) * rad))
+
+
 class Robot:
     def __init__(self, x=0.0, y=0.0, theta=0.0, linesize=LINESIZE, device=0, **cfg):
         self._f = EkfFilter(capacity_lines=linesize, gate=cfg.pop("gate", MAHALANOBIS),
@@ -84,14 +113,7 @@ class Robot:
             added += 1
             if len(ln.lineInterval) == 2:
                 for (alpha, rr) in (ln.lineInterval[0], ln.lineInterval[-1]):
-                    alpha = np.float32(alpha)                                           # `float alpha` at :871
-                    ca, sa = float(np.cos(alpha)), float(np.sin(alpha))                 # cos(float) -> float
-                    rad = rr + self.xPos * ca + self.yPos * sa
-                    # polar_point(alfa, r) scales its first argument by PI/180 with PI = 3.14159265
-                    # (lineFitting.cpp:71-77, lineFitting.h:12): reproduced, it is what the node publishes
-                    a = (float(alpha) + self.thetaPos) * (3.14159265 / 180)
-                    self.lineIntervals.append(float(np.float32(math.cos(a) * rad)))    # polar2descart, :170-176
-                    self.lineIntervals.append(float(np.float32(math.sin(a) * rad)))
+                    self.lineIntervals.extend(interval_end_point(alpha, rr, self.xPos, self.yPos, self.thetaPos))
         return rc
 
     def getEllipse(self):

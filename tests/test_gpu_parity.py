@@ -482,11 +482,12 @@ def test_overlapped_pipeline_interleaved_with_stepwise_calls(libekf, oracle_cls)
 
 @pytest.mark.parametrize("shape", [0, 9, 10])
 def test_sweep_kernels_give_identical_bits(libekf, shape):
-    """EKF_SWEEP_SHAPE selects the consumers of the pipelined sweep: 0 = k_sweep_quad (8x4 register tiles, DFMA),
-    9 = k_sweep_pipe (8x2), 10 = k_sweep_dmma (fp64 tensor cores: mma.sync.m8n8k4.f64 accumulates as the k-ordered FMA
-    chain, i.e. sub_rank2 term after term -- measured, scripts/dmma_probe.cu).  Same scans, m = 8 / 13 / 32 / 40 lines
-    (odd counts: the tensor-core step's zero-padded second term; > 32: two passes): the downloaded state must equal the
-    default build's bit for bit, and the oracle's within 1e-9."""
+    """EKF_SWEEP_SHAPE selects the consumers of the pipelined sweep: 11 = k_sweep_quad for every count (8x4 register
+    tiles, DFMA), 0 = the default (quad up to 8 pending terms, tensor cores beyond), 9 = k_sweep_pipe (8x2),
+    10 = k_sweep_dmma for every count (fp64 tensor cores: mma.sync.m8n8k4.f64 accumulates as the k-ordered FMA chain,
+    i.e. sub_rank2 term after term -- measured, scripts/dmma_probe.cu).  Same scans, m = 8 / 13 / 32 / 40 lines (odd
+    counts: the tensor-core step's zero-padded second term; > 32: two passes): the downloaded state must equal the
+    all-DFMA run's bit for bit, and the oracle's within 1e-9."""
     import subprocess
     import sys
     code = (
@@ -505,7 +506,7 @@ def test_sweep_kernels_give_identical_bits(libekf, shape):
         "np.savez(sys.argv[1], **out)\n"
     ) % ROOT
     res = []
-    for sh in (0, shape):
+    for sh in (11, shape):
         path = "/tmp/ekf_shape_%d_%d.npz" % (sh, os.getpid())
         env = dict(os.environ, EKF_SWEEP_SHAPE=str(sh))
         out = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, timeout=600, env=env)

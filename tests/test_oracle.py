@@ -235,3 +235,40 @@ def test_structured_oracle_against_golden_vectors_of_the_1k_reference():
     assert np.array_equal(np.diag(P)[:nl], g["diag"]) and np.array_equal(P[:3, :nl], g["top"])
     for (r, c), blk in zip(g["corners"], g["blocks"]):
         assert np.array_equal(P[r:r + blk.shape[0], c:c + blk.shape[1]], blk)
+
+
+def test_line_interval_end_points_value_for_value_against_the_reference():
+    """SURVEY 8(a) row a16: Robot::lineIntervals (Robot.cpp:868-879, the node's `lines` topic).  The literal reference is
+    driven with line::lineInterval set; what it leaves in lineIntervals.data must equal, float for float, the host-side
+    formula of the drop-ins (slam_ros_b200/robot.py interval_end_point == include/ekf_robot.hpp push_endpoint) evaluated
+    at the reference's own post-update pose, for exactly the lines it appended, in order."""
+    from oracle.oracle import LiteralReference, have_literal
+    from slam_ros_b200.robot import interval_end_point
+    if not have_literal():
+        pytest.skip("oracle/_ref/libslamref.so not present")
+    steps = 200
+    room = sc.room_scenario(steps=steps, seed=7, range_sigma=5e-5)
+    rng = np.random.default_rng(3)
+    lit = LiteralReference()
+    so = StructuredOracle(100)
+    total = 0
+    for s in range(steps):
+        m = room["count"][s]
+        z, R = room["z"][s, :m], room["R"][s, :m]
+        iv = np.column_stack([z[:, 0] - 0.3 + 0.05 * rng.standard_normal(m), z[:, 1] * 1.07,
+                              z[:, 0] + 0.4 + 0.05 * rng.standard_normal(m), z[:, 1] * 1.11])
+        _, _, L0, pose0 = lit.state(want_cov=False)
+        enc = sc.encoder_for(pose0, room["u"][s])
+        got = lit.localize_intervals(z, R, enc, iv)
+        st, j = so.localize(z, R, enc)                  # the structured oracle says which lines were appended
+        _, _, L1, pose1 = lit.state(want_cov=False)
+        want = []
+        for i in range(m):
+            if j[i] < 0:
+                want.extend(interval_end_point(iv[i, 0], iv[i, 1], *pose1))
+                want.extend(interval_end_point(iv[i, 2], iv[i, 3], *pose1))
+        want = np.array(want, dtype=np.float32)
+        assert got.shape == want.shape, "step %d: %d vs %d floats" % (s, got.size, want.size)
+        assert np.array_equal(got, want), "step %d: %s vs %s" % (s, got[:8], want[:8])
+        total += got.size
+    assert total >= 4 * 20
