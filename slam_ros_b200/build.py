@@ -66,10 +66,13 @@ def _compile(out, extra, verbose=False):
     return out
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
-        return OUT
-    return _compile(OUT, os.environ.get("EKF_NVCC_EXTRA", "").split(), verbose)
+def build(force=False, verbose=False, variants=("exact",)):
+    """Builds libekfcuda.so and the A/B variants the tests load (each only when stale)."""
+    if force or stale():
+        _compile(OUT, os.environ.get("EKF_NVCC_EXTRA", "").split(), verbose)
+    for v in variants:
+        build_variant(v, force=force)
+    return OUT
 
 
 def build_variant(name, force=False):

@@ -520,6 +520,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   g.ld = ((g.n + EKF_LD_ALIGN - 1) / EKF_LD_ALIGN) * EKF_LD_ALIGN;
   g.rank = rank; g.world = world;
   g.gate = cfg->gate; g.enc_noise = cfg->encoder_noise; g.headroom = cfg->reset_headroom;
+  g.gate_d2max = ekf_gate_d2max(cfg->gate);
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   const size_t ld = g.ld;
   const size_t p_rows = (size_t)ekf_local_tile_rows(g) * EKF_TILE;

@@ -40,7 +40,7 @@ struct EkfBatchState {
 struct EkfBatchGeom {
   double2* scratch;         /* [B][4][n]: the pending gains of filters that run off chip */
   int B, cap, n, headroom;
-  double gate, enc_noise;
+  double gate, enc_noise, gate_d2max;
   long long pstride;        /* doubles per filter in the packed covariance array (even: 16-byte aligned filters) */
   int ystride;              /* doubles per filter in the state array (even) */
   int full_gates;           /* A/B: evaluate the full gate for every landmark (no lower-bound pre-test) */
@@ -355,7 +355,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
           Cm[3][3] = ca_[a]; Cm[3][4] = Cm[4][3] = cb_[a]; Cm[4][4] = cb_[bb];
           gate_from_block(Cm, ys[a], ys[bb], xp, z0, z1, Rl, Gj);
           if (Gj.singular) atomicOr(&s_sticky, EKF_STICKY_SINGULAR);
-          else if (!(sqrt(fabs(Gj.d2)) > g.gate)) mine = jj;                           /* :489 */
+          else if (!gate_rejects_d2(Gj.d2, g.gate_d2max)) mine = jj;                   /* :489 */
         }
         best = __reduce_min_sync(0xffffffffu, mine);
         if (mine != EKF_NO_MATCH && mine == best) sG = Gj;            /* the winner publishes its gate record */
@@ -648,7 +648,7 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   CUB(cudaSetDevice(cfg->device));
   EkfBatchGeom& g = b->g;
   g.B = n_filters; g.cap = cfg->capacity_lines; g.n = 3 + 2 * g.cap; g.headroom = cfg->reset_headroom;
-  g.gate = cfg->gate; g.enc_noise = cfg->encoder_noise;
+  g.gate = cfg->gate; g.enc_noise = cfg->encoder_noise; g.gate_d2max = ekf_gate_d2max(cfg->gate);
   g.pstride = (tri(g.n) + 2) & ~1;
   g.ystride = (g.n + 1) & ~1;
   g.full_gates = (cfg->flags & EKF_FLAG_FULL_GATES) ? 1 : 0;

@@ -80,7 +80,13 @@ __device__ __forceinline__ int inv2x2_lu(const double S[4], double Si[4]) {
 
 
 /* Robot.cpp:367-489 for one (line, landmark) pair, given P gathered at rows/cols {0,1,2,a,b} (Cm), the
- * landmark (m0, m1) = (y[a], y[b]), the predicted pose, the observed line z and its covariance R. */
+ * landmark (m0, m1) = (y[a], y[b]), the predicted pose, the observed line z and its covariance R.
+ *
+ * The reference-BLAS loops the reference calls multiply by the structural +-1 entries of H and start every sum from
+ * 0.0; those operations are exact (x*1 = x, x*(-1) = -x, 0 + x = x) and are not issued here: every value is bit for bit
+ * what the literal sequence produces, except that a zero result may carry the other sign (0.0 + (-0.0) = +0.0), which no
+ * comparison, product or sum downstream can tell apart.  What is kept is every operation that rounds, in the
+ * reference's order, and the zero skips of the NN / TN loops. */
 __device__ __forceinline__ void gate_from_block(const double Cm[5][5], double m0, double m1, const double x_pre[3],
                                                 double z0, double z1, const double R[4], Gate& G) {
   const double c = cos(m0), s = sin(m0);
@@ -90,27 +96,22 @@ __device__ __forceinline__ void gate_from_block(const double Cm[5][5], double m0
   double HP0[5], HP1[5];
 #pragma unroll
   for (int t = 0; t < 5; ++t) {                                       /* :397  H * P  (NN, k = 0,1,2,a,b) */
-    double h0 = 0.0, h1 = 0.0;
-    axpy_skip(h1, H10, Cm[0][t]);
+    double h1 = (H10 != 0.0) ? mul_rn(H10, Cm[0][t]) : 0.0;
     axpy_skip(h1, H11, Cm[1][t]);
-    axpy_skip(h0, -1.0, Cm[2][t]);
-    axpy_skip(h0, 1.0, Cm[3][t]); axpy_skip(h1, gg, Cm[3][t]);
-    axpy_skip(h1, 1.0, Cm[4][t]);
-    HP0[t] = h0; HP1[t] = h1;
+    axpy_skip(h1, gg, Cm[3][t]);
+    h1 = add_rn(h1, Cm[4][t]);
+    HP0[t] = sub_rn(Cm[3][t], Cm[2][t]);                              /* (0 + -P[2,t]) + P[a,t] */
+    HP1[t] = h1;
   }
 #pragma unroll
   for (int p = 0; p < 2; ++p) {                                       /* :401  HP * H'  (NT) */
     const double* HP = p ? HP1 : HP0;
-    double t0 = 0.0;
-    t0 = add_rn(t0, mul_rn(HP[2], -1.0));
-    t0 = add_rn(t0, mul_rn(HP[3], 1.0));
-    double t1 = 0.0;
-    t1 = add_rn(t1, mul_rn(HP[0], H10));
+    double t1 = mul_rn(HP[0], H10);
     t1 = add_rn(t1, mul_rn(HP[1], H11));
     t1 = add_rn(t1, mul_rn(HP[3], gg));
-    t1 = add_rn(t1, mul_rn(HP[4], 1.0));
-    G.S[p * 2 + 0] = add_rn(0.0, t0);
-    G.S[p * 2 + 1] = add_rn(0.0, t1);
+    t1 = add_rn(t1, HP[4]);
+    G.S[p * 2 + 0] = sub_rn(HP[3], HP[2]);
+    G.S[p * 2 + 1] = t1;
   }
 #pragma unroll
   for (int t = 0; t < 4; ++t) G.S[t] = add_rn(G.S[t], R[t]);            /* :405 */
@@ -125,32 +126,33 @@ __device__ __forceinline__ void gate_from_block(const double Cm[5][5], double m0
   else if (fabs(add_rn(v0, two_pi)) < fabs(v0)) v0 = add_rn(v0, two_pi);
   G.v[0] = v0; G.v[1] = v1;
   double w0 = 0.0, w1 = 0.0;                                          /* :479  v' * Sinv  (TN) */
-  axpy_skip(w0, v0, G.Si[0]); axpy_skip(w1, v0, G.Si[1]);
+  if (v0 != 0.0) { w0 = mul_rn(v0, G.Si[0]); w1 = mul_rn(v0, G.Si[1]); }
   axpy_skip(w0, v1, G.Si[2]); axpy_skip(w1, v1, G.Si[3]);
-  double d2 = 0.0;                                                    /* :483 */
-  axpy_skip(d2, w0, v0); axpy_skip(d2, w1, v1);
+  double d2 = (w0 != 0.0) ? mul_rn(w0, v0) : 0.0;                     /* :483 */
+  axpy_skip(d2, w1, v1);
   G.d2 = d2;
 }
 
-/* gain row r of Robot.cpp:522-560 from the five entries P[r,{0,1,2,a,b}] */
+/* gain row r of Robot.cpp:522-560 from the five entries P[r,{0,1,2,a,b}] (exact operations elided as above) */
 __device__ __forceinline__ void gain_row(const Gate& G, double p0, double p1, double p2, double pa, double pb,
                                          double2& K, double2& KS) {
   const double H10 = -G.c, H11 = -G.s, gg = G.g;
-  double t0 = 0.0;                                                    /* :522  P * H'  (NT) */
-  t0 = add_rn(t0, mul_rn(p2, -1.0));
-  t0 = add_rn(t0, mul_rn(pa, 1.0));
-  double t1 = 0.0;
-  t1 = add_rn(t1, mul_rn(p0, H10));
-  t1 = add_rn(t1, mul_rn(p1, H11));
-  t1 = add_rn(t1, mul_rn(pa, gg));
-  t1 = add_rn(t1, mul_rn(pb, 1.0));
-  const double ph0 = add_rn(0.0, t0), ph1 = add_rn(0.0, t1);
+  const double ph0 = sub_rn(pa, p2);                                  /* :522  P * H'  (NT) */
+  double ph1 = mul_rn(p0, H10);
+  ph1 = add_rn(ph1, mul_rn(p1, H11));
+  ph1 = add_rn(ph1, mul_rn(pa, gg));
+  ph1 = add_rn(ph1, pb);
   double k0 = 0.0, k1 = 0.0;                                          /* :526  PHt * Sinv  (NN) */
-  axpy_skip(k0, ph0, G.Si[0]); axpy_skip(k1, ph0, G.Si[1]);
+  if (ph0 != 0.0) { k0 = mul_rn(ph0, G.Si[0]); k1 = mul_rn(ph0, G.Si[1]); }
   axpy_skip(k0, ph1, G.Si[2]); axpy_skip(k1, ph1, G.Si[3]);
   double s0 = 0.0, s1 = 0.0;                                          /* :560  K * S  (NN) */
-  axpy_skip(s0, k0, G.S[0]); axpy_skip(s1, k0, G.S[1]);
+  if (k0 != 0.0) { s0 = mul_rn(k0, G.S[0]); s1 = mul_rn(k0, G.S[1]); }
   axpy_skip(s0, k1, G.S[2]); axpy_skip(s1, k1, G.S[3]);
   K = make_double2(k0, k1); KS = make_double2(s0, s1);
 }
+
+/* Robot.cpp:489 rejects when sqrt(|d2|) > gate.  sqrt is correctly rounded and monotone, so the test is the same as
+ * |d2| > T with T the largest double whose square root does not exceed the gate: one comparison instead of the
+ * square root's dependent chain.  (NaN: both forms compare false -- the pair passes, as in the reference.) */
+__host__ __device__ inline bool gate_rejects_d2(double d2, double d2max) { return fabs(d2) > d2max; }
 #endif

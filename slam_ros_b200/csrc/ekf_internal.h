@@ -58,6 +58,7 @@ struct EkfGeom {
   int rank, world;
   double gate, enc_noise;
   int headroom;
+  double gate_d2max;   /* largest |d2| that passes: sqrt(|d2|) > gate  <=>  |d2| > gate_d2max (ekf_gate_d2max) */
 };
 
 struct EkfBuffers {
@@ -122,6 +123,17 @@ cudaError_t ekf_launch_cov_stats(const EkfGeom& g, const EkfBuffers& b, double* 
                                  double* d_out3, cudaStream_t s);
 cudaError_t ekf_launch_zero_pending(const EkfGeom& g, const EkfBuffers& b, int m, int* d_np, cudaStream_t s);
 int ekf_sweep_grid_ub(const EkfGeom& g, int L_ub);
+
+/* The largest double T with sqrt(T) <= gate (sqrt correctly rounded): Robot.cpp:489's `sqrt(fabs(d2)) > MAHALANOBIS`
+ * is then exactly `fabs(d2) > T`. */
+#include <math.h>
+static inline double ekf_gate_d2max(double gate) {
+  if (!(gate >= 0.0)) return -1.0;                        /* a negative or NaN gate rejects everything / nothing as sqrt would */
+  double t = gate * gate;
+  while (sqrt(t) > gate) t = nextafter(t, 0.0);
+  for (;;) { const double u = nextafter(t, INFINITY); if (!(sqrt(u) <= gate)) break; t = u; }
+  return t;
+}
 
 /* rows of P this rank stores */
 static inline int ekf_local_tile_rows(const EkfGeom& g) {

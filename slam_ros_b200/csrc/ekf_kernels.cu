@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_associate(EkfGeom g, EkfBuffers b
     Gate G;
     eval_gate(g, b, xp, j, z[2 * line], z[2 * line + 1], Rl, G);
     if (G.singular) atomicOr(&b.st->sticky, EKF_STICKY_SINGULAR);
-    else if (!(sqrt(fabs(G.d2)) > g.gate)) cand = j;                  /* :489 */
+    else if (!gate_rejects_d2(G.d2, g.gate_d2max)) cand = j;          /* :489 */
   }
   cand = __reduce_min_sync(0xffffffffu, cand);
   if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_
         Gate G;
         gate_from_block(Cm, ya, yb, xp, z0, z1, Rl, G);
         if (G.singular) atomicOr(&st->sticky, EKF_STICKY_SINGULAR);
-        else if (!(sqrt(fabs(G.d2)) > g.gate)) { cand = j; gate_store(b.gates + (size_t)GATE_REC * j, G); }
+        else if (!gate_rejects_d2(G.d2, g.gate_d2max)) { cand = j; gate_store(b.gates + (size_t)GATE_REC * j, G); }
       }
     }
     if (!robot_done) update_robot_block(kk, ks, pv0, pv1, A, xp);    /* threads without a landmark of their own */

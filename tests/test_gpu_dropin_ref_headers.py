@@ -50,9 +50,10 @@ def test_dropin_built_on_reference_headers_matches_the_literal_reference(libekf)
         z, R = room["z"][s, :m], room["R"][s, :m]
         iv = _end_points(z, rng)
         _, _, _, pose_l = lit.state(want_cov=False)
-        enc = sc.encoder_for(pose_l, room["u"][s])
-        out_l = lit.localize_intervals(z, R, enc, iv)
-        out_d = drp.localize_intervals(z, R, enc, iv)
+        _, _, _, pose_d = drp.state(want_cov=False)
+        # the same odometry u for both: each robot gets the encoder pose that makes Robot.cpp:140-145 recover u from ITS pose
+        out_l = lit.localize_intervals(z, R, sc.encoder_for(pose_l, room["u"][s]), iv)
+        out_d = drp.localize_intervals(z, R, sc.encoder_for(pose_d, room["u"][s]), iv)
         _, _, L_l, pose_l = lit.state(want_cov=False)
         _, _, L_d, pose_d = drp.state(want_cov=False)
         assert L_l == L_d, "savedLineCount at step %d: %d vs %d" % (s, L_l, L_d)
