@@ -296,7 +296,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
           ys[q] = add_rn(ys[q], t);
         }
       }
-      if (tid == 0) {
+      if (tid == nt - 1) {            /* the robot pose: on the last thread, which has no column of its own up to 127 rows */
         double yn[3];
         for (int r = 0; r < 3; ++r) {
           const double2 kk = Kn[r];

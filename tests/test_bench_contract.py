@@ -26,6 +26,11 @@ def test_reference_arm_prints_one_contract_line(workload, unit):
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["gpu_launches"] == 0
+    # both arms print the SAME `config` object (the driver compares them): it is built by one function from the workload
+    # and the GPU count alone; what a run measured goes to the own arm's `run` object
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.static_config(workload, 1)
 
 
 def test_product_arm_needs_a_gpu():
