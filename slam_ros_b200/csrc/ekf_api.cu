@@ -84,6 +84,7 @@ struct ekf_ctx {
   int have_tmap8;
   CUtensorMap tmapK[2];        /* [0]: K bands (box = tile columns x 8 slots), [1]: K S bands (box = tile rows x 8 slots) */
   int rd, par, group;
+  int slots;                   /* rows of Kp / KSp: max(max_batch, 2 * group) */
   int pg_valid, pg_slot0;
   EkfScanView* d_view;        /* [2] */
   unsigned long long* d_counters;   /* tile counters of the sweep passes: [0,16) line stream, [16,32) sweep stream */
@@ -222,7 +223,7 @@ int make_band_map(ekf_ctx* ctx, double2* base, int box_entries, CUtensorMap* out
   cudaDriverEntryPointQueryResult q;
   CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
   if (!fn || q != cudaDriverEntryPointSuccess) { snprintf(ctx->err, sizeof ctx->err, "cuTensorMapEncodeTiled not available"); return EKF_ECUDA; }
-  const cuuint64_t gdim[2] = {(cuuint64_t)2 * ctx->g.ld, (cuuint64_t)ctx->cfg.max_batch};
+  const cuuint64_t gdim[2] = {(cuuint64_t)2 * ctx->g.ld, (cuuint64_t)ctx->slots};
   const cuuint64_t gstride[1] = {(cuuint64_t)ctx->g.ld * sizeof(double2)};
   const cuuint32_t box[2] = {(cuuint32_t)(2 * box_entries), 8};
   const cuuint32_t estr[2] = {1, 1};
@@ -378,8 +379,9 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
   long long lub = (long long)ctx->L_ub + m;
   const int L_after_ub = (int)(lub > ctx->g.cap ? ctx->g.cap : lub);
   CU(ekf_launch_sweep_tma(ctx->g, bt, &ctx->tmap2[tgt], ctx->have_tmap8 ? &ctx->tmap8[tgt] : 0, &ctx->tmapK[0], &ctx->tmapK[1], ctx->Pbuf[tgt ^ 1], slot0, &ctx->d_view[par], ctx->d_counters + 16,
-                          ctx->sweep_shape, m, L_after_ub, ctx->num_sms - EKF_LINE_SMS, ctx->wstream));
-  ctx->launches += 1;
+                          ctx->sweep_shape, m, L_after_ub, ctx->num_sms - EKF_LINE_SMS, ctx->wstream,
+                          &ctx->tmap2[tgt ^ 1], ctx->have_tmap8 ? &ctx->tmap8[tgt ^ 1] : 0));
+  { const int per_pass = ekf_sweep_terms_per_pass(ctx->sweep_shape, m); ctx->launches += (m + per_pass - 1) / per_pass; }
   if (ctx->prof) {
     CU(cudaEventRecord(e1, ctx->wstream));
     ctx->ev_used += 2;
@@ -533,20 +535,22 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->overlap = 0;
   /* lines per overlapped scan: the pending-slot ring holds two scans' terms ([2][group] slots) and one out-of-place
    * sweep pass folds at most 32 */
-  ctx->group = ctx->cfg.max_batch / 2 < 32 ? ctx->cfg.max_batch / 2 : 32;
+  /* from max_batch = 64 on (the default) an overlapped scan may hold up to 64 lines: its sweep is then two chained passes */
+  ctx->group = ctx->cfg.max_batch >= 64 ? 64 : (ctx->cfg.max_batch / 2 < 32 ? ctx->cfg.max_batch / 2 : 32);
+  ctx->slots = ctx->cfg.max_batch > 2 * ctx->group ? ctx->cfg.max_batch : 2 * ctx->group;
   CU(cudaMalloc(&ctx->d_counters, 32 * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_view, 2 * sizeof(EkfScanView)));
   CU(cudaMemsetAsync(ctx->d_view, 0, 2 * sizeof(EkfScanView), ctx->stream));
   CU(cudaMalloc(&ctx->b.matched, (size_t)g.cap * sizeof(int)));
-  CU(cudaMalloc(&ctx->b.Kp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
-  CU(cudaMalloc(&ctx->b.KSp, (size_t)ctx->cfg.max_batch * ld * sizeof(double2)));
+  CU(cudaMalloc(&ctx->b.Kp, (size_t)ctx->slots * ld * sizeof(double2)));
+  CU(cudaMalloc(&ctx->b.KSp, (size_t)ctx->slots * ld * sizeof(double2)));
   CU(cudaMalloc(&ctx->b.gates, 16 * (size_t)g.cap * sizeof(double)));
   CU(cudaMalloc(&ctx->b.colA, 2 * ld * sizeof(double)));
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9 && ctx->sweep_shape != 10 && ctx->sweep_shape != 11) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
-  { const int cap = ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
+  { const int cap = 2 * ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
   { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
   ctx->have_tmap8 = (ctx->sweep_shape == 0 || ctx->sweep_shape == 10);
   if (ctx->have_tmap8) { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap8[0], 10); if (rc) return rc; }
@@ -564,8 +568,8 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMemsetAsync(ctx->b.diag, 0, 4 * (size_t)g.cap * sizeof(double), ctx->stream));
   CU(cudaMemsetAsync(ctx->b.P, 0, p_rows * ld * sizeof(double), ctx->stream));
   CU(cudaMemsetAsync(ctx->b.matched, 0, (size_t)g.cap * sizeof(int), ctx->stream));
-  CU(cudaMemsetAsync(ctx->b.Kp, 0, (size_t)ctx->cfg.max_batch * ld * sizeof(double2), ctx->stream));
-  CU(cudaMemsetAsync(ctx->b.KSp, 0, (size_t)ctx->cfg.max_batch * ld * sizeof(double2), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.Kp, 0, (size_t)ctx->slots * ld * sizeof(double2), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b.KSp, 0, (size_t)ctx->slots * ld * sizeof(double2), ctx->stream));
   CU(cudaMemsetAsync(ctx->b.colA, 0, 2 * ld * sizeof(double), ctx->stream));
   int rc = ensure_lines(ctx, 64);
   if (rc) return rc;

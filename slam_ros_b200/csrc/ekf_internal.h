@@ -109,7 +109,7 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
 cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmap8, const void* tmapK, const void* tmapKS,
                                  double* dst, int slot0,
                                  const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
-                                 int num_sms, cudaStream_t s);
+                                 int num_sms, cudaStream_t s, const void* tmap_dst = 0, const void* tmap8_dst = 0);
 void ekf_sweep_shape(int shape, int* tr, int* tc);
 void ekf_sweep_pbox(int shape, int* rows, int* cols);
 int ekf_sweep_terms_per_pass(int shape, int np_ub);

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, in
  * bookkeeping) are separated by hardware cluster barriers instead of kernel boundaries.  The phases are
  * the bodies of k_associate / k_gain(mode 0) / k_apply; the winner's gate record travels through
  * b.gates so it is evaluated once, as in the reference (Robot.cpp:367-489 feeds :516-602). */
-#define FL_MAXP 64                    /* upper bound of max_batch for the fused path */
+#define FL_MAXP 128                   /* most pending terms a line can see: the previous scan's (<= 64) + this scan's (<= 64) */
 #define GATE_REC 16                   /* doubles per landmark in b.gates */
 
 __device__ __forceinline__ void gate_store(double* rec, const Gate& G) {
@@ -1507,7 +1507,8 @@ cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* n
 template <int TR, int TC, int STAGES, int CW, int C>
 static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, const CUtensorMap* mK,
                                       const CUtensorMap* mKS, double* dst, int slot0,
-                                      const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s) {
+                                      const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s,
+                                      const CUtensorMap* m_dst = 0) {
   const size_t smem = sizeof(SweepShared<TR, TC, STAGES, C>) + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -1522,7 +1523,11 @@ static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, con
     if (e != cudaSuccess) return e;
   }
   for (int c0 = 0; c0 < np_ub; c0 += C) {
-    k_sweep_pipe<TR, TC, STAGES, CW, C><<<grid, (CW + 1) * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
+    /* an out-of-place sweep of more than C terms: the first pass goes source -> destination, the others fold the rest in
+     * place on the destination (m_dst = its tensor map) */
+    EkfBuffers bb = b;
+    if (c0 > 0 && dst != b.P) { bb.P = dst; m = m_dst; }
+    k_sweep_pipe<TR, TC, STAGES, CW, C><<<grid, (CW + 1) * 32, smem, s>>>(g, bb, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -1531,7 +1536,8 @@ static cudaError_t launch_sweep_shape(const EkfGeom& g, const EkfBuffers& b, con
 template <int STAGES, int C>
 static cudaError_t launch_sweep_quad(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, const CUtensorMap* mK,
                                      const CUtensorMap* mKS, double* dst, int slot0,
-                                     const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s) {
+                                     const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s,
+                                     const CUtensorMap* m_dst = 0) {
   const size_t smem = sizeof(SweepShared<64, 64, STAGES, C>) + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -1546,7 +1552,9 @@ static cudaError_t launch_sweep_quad(const EkfGeom& g, const EkfBuffers& b, cons
     if (e != cudaSuccess) return e;
   }
   for (int c0 = 0; c0 < np_ub; c0 += C) {
-    k_sweep_quad<STAGES, C><<<grid, 9 * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
+    EkfBuffers bb = b;
+    if (c0 > 0 && dst != b.P) { bb.P = dst; m = m_dst; }
+    k_sweep_quad<STAGES, C><<<grid, 9 * 32, smem, s>>>(g, bb, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -1555,7 +1563,8 @@ static cudaError_t launch_sweep_quad(const EkfGeom& g, const EkfBuffers& b, cons
 template <int STAGES, int C>
 static cudaError_t launch_sweep_dmma(const EkfGeom& g, const EkfBuffers& b, const CUtensorMap* m, const CUtensorMap* mK,
                                      const CUtensorMap* mKS, double* dst, int slot0,
-                                     const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s) {
+                                     const EkfScanView* view, unsigned long long* counters, int np_ub, int grid, cudaStream_t s,
+                                     const CUtensorMap* m_dst = 0) {
   const size_t smem = sizeof(SweepShared<64, 64, STAGES, C>) + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -1570,7 +1579,9 @@ static cudaError_t launch_sweep_dmma(const EkfGeom& g, const EkfBuffers& b, cons
     if (e != cudaSuccess) return e;
   }
   for (int c0 = 0; c0 < np_ub; c0 += C) {
-    k_sweep_dmma<STAGES, C><<<grid, 9 * 32, smem, s>>>(g, b, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
+    EkfBuffers bb = b;
+    if (c0 > 0 && dst != b.P) { bb.P = dst; m = m_dst; }
+    k_sweep_dmma<STAGES, C><<<grid, 9 * 32, smem, s>>>(g, bb, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -1595,11 +1606,14 @@ int ekf_sweep_terms_per_pass(int shape, int np_ub) {
 cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const void* tmap, const void* tmap8, const void* tmapK, const void* tmapKS,
                                  double* dst, int slot0,
                                  const EkfScanView* view, unsigned long long* counters, int shape, int np_ub, int L_ub,
-                                 int num_sms, cudaStream_t s) {
+                                 int num_sms, cudaStream_t s, const void* tmap_dst, const void* tmap8_dst) {
   const int tiles = ekf_sweep_grid_ub(g, L_ub);
   if (tiles <= 0 || np_ub <= 0) return cudaSuccess;
   const int C = ekf_sweep_terms_per_pass(shape, np_ub);
-  if (dst != b.P && np_ub > C) return cudaErrorInvalidValue;   /* out-of-place form: one pass only */
+  /* out-of-place form with more terms than one pass folds: needs the destination's tensor maps for the in-place rest */
+  if (dst != b.P && np_ub > C && !tmap_dst) return cudaErrorInvalidValue;
+  const CUtensorMap* md = reinterpret_cast<const CUtensorMap*>(tmap_dst);
+  const CUtensorMap* md8 = reinterpret_cast<const CUtensorMap*>(tmap8_dst);
   const int grid = tiles < num_sms ? tiles : num_sms;      /* num_sms: SMs this sweep may occupy */
   const CUtensorMap* m = reinterpret_cast<const CUtensorMap*>(tmap);
   const CUtensorMap* m8 = reinterpret_cast<const CUtensorMap*>(tmap8);
@@ -1611,24 +1625,25 @@ cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const vo
   else if (shape == 0 && np_ub > 8 && m8) shape = 10;
   const CUtensorMap* mKS = reinterpret_cast<const CUtensorMap*>(tmapKS);
   switch (shape) {       /* shape % 4: tile shape; shape / 4: 0 = 8 consumer warps, 1 = 16 */
-    case 1: return launch_sweep_shape<32, 128, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 2: return launch_sweep_shape<16, 256, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 4: return launch_sweep_shape<64, 64, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 5: return launch_sweep_shape<32, 128, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-    case 8: return launch_sweep_shape<64, 64, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);   /* 148 KB: leaves room for a co-resident line-loop CTA */
+    case 1: return launch_sweep_shape<32, 128, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+    case 2: return launch_sweep_shape<16, 256, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+    case 4: return launch_sweep_shape<64, 64, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+    case 5: return launch_sweep_shape<32, 128, 4, 16, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+    case 8: return launch_sweep_shape<64, 64, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);   /* 148 KB: leaves room for a co-resident line-loop CTA */
     case 10:       /* fp64 tensor cores (k_sweep_dmma) */
       if (!m8) return cudaErrorInvalidValue;
-      if (C == 32) return launch_sweep_dmma<2, 32>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      if (C == 16) return launch_sweep_dmma<3, 16>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      return launch_sweep_dmma<4, 8>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (dst != b.P && np_ub > C && !md8) return cudaErrorInvalidValue;
+      if (C == 32) return launch_sweep_dmma<2, 32>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md8);
+      if (C == 16) return launch_sweep_dmma<3, 16>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md8);
+      return launch_sweep_dmma<4, 8>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md8);
     case 9:        /* the 8-rows x 2-columns-per-lane consumers (A/B against k_sweep_quad) */
-      if (C == 32) return launch_sweep_shape<64, 64, 2, 8, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      if (C == 16) return launch_sweep_shape<64, 64, 3, 8, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      return launch_sweep_shape<64, 64, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (C == 32) return launch_sweep_shape<64, 64, 2, 8, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+      if (C == 16) return launch_sweep_shape<64, 64, 3, 8, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+      return launch_sweep_shape<64, 64, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
     default:
-      if (C == 32) return launch_sweep_quad<2, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      if (C == 16) return launch_sweep_quad<3, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
-      return launch_sweep_quad<4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s);
+      if (C == 32) return launch_sweep_quad<2, 32>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+      if (C == 16) return launch_sweep_quad<3, 16>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+      return launch_sweep_quad<4, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
   }
 }
 cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
