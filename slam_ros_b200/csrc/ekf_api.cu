@@ -544,7 +544,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMalloc(&ctx->b.matched, (size_t)g.cap * sizeof(int)));
   CU(cudaMalloc(&ctx->b.Kp, (size_t)ctx->slots * ld * sizeof(double2)));
   CU(cudaMalloc(&ctx->b.KSp, (size_t)ctx->slots * ld * sizeof(double2)));
-  CU(cudaMalloc(&ctx->b.gates, 16 * (size_t)g.cap * sizeof(double)));
+  CU(cudaMalloc(&ctx->b.gates, 24 * (size_t)g.cap * sizeof(double)));     /* GATE_REC doubles per landmark */
   CU(cudaMalloc(&ctx->b.colA, 2 * ld * sizeof(double)));
   ctx->b.colB = ctx->b.colA + ld;
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_apply(EkfGeom g, EkfBuffers b, in
  * the bodies of k_associate / k_gain(mode 0) / k_apply; the winner's gate record travels through
  * b.gates so it is evaluated once, as in the reference (Robot.cpp:367-489 feeds :516-602). */
 #define FL_MAXP 128                   /* most pending terms a line can see: the previous scan's (<= 64) + this scan's (<= 64) */
-#define GATE_REC 16                   /* doubles per landmark in b.gates */
+#define GATE_REC 24                   /* doubles per landmark in b.gates: the gate (14), P[0..2, a], P[0..2, b] (6) */
 
 __device__ __forceinline__ void gate_store(double* rec, const Gate& G) {
   rec[0] = G.c; rec[1] = G.s; rec[2] = G.g;
@@ -665,6 +665,192 @@ __global__ void __launch_bounds__(FL_THREADS, FL_THREADS == 256 ? 3 : 1) k_scan_
     for (int t = 0; t < 4; ++t) pS[t] = G.S[t];
   }
   if (SHARD && gtid == 0) st->xseq = xseq0 + xdone;   /* every thread read xseq0 before the first barrier */
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* k_scan_lines2: the line loop with ONE barrier per line (single GPU; the row-sharded form stays on k_scan_lines).
+ *
+ * What made the first form need two barriers and several L2 round trips per line was the split of the work: landmarks
+ * were gated by one thread, their gain rows formed by another, and the hot update of the next line waited for both.
+ * Here a thread OWNS its landmarks (j = gtid, gtid + gstride, ...): their hot covariance entries (rows 0..2 of the two
+ * columns, the 2x2 diagonal block), their state entries, AND their two gain rows.  The three robot rows of the gain are
+ * formed redundantly by every thread from the 3x3 block it carries and the winner's six top entries, which travel with
+ * the winner's gate record.  So after the one barrier that settles the first fit, a thread has everything it needs to
+ * form its gain rows, apply the whole hot update to what it owns (Robot.cpp:564-602) and go straight to the next line's
+ * gate: per line one barrier and one dependent round trip to L2 (the winner's record + the two column entries of the
+ * owned rows) instead of two barriers and four.  While every thread owns at most one landmark (L <= threads: 8192 in
+ * the cluster form, 10240 beside an overlapped sweep) the hot entries live in registers for the whole scan and memory
+ * sees only write-through stores.  Same functions, same order of operations per element as k_scan_lines: identical bits
+ * (test_all_launch_strategies_give_identical_bits). */
+struct HotLm { double t0a, t0b, t1a, t1b, t2a, t2b, daa, dab, dbb, ya, yb; int mt; };
+__device__ __forceinline__ void hot_load(const EkfGeom& g, const EkfBuffers& b, int j, HotLm& h) {
+  const int a = 3 + 2 * j;
+  h.t0a = b.top[a]; h.t0b = b.top[a + 1];
+  h.t1a = b.top[(size_t)g.ld + a]; h.t1b = b.top[(size_t)g.ld + a + 1];
+  h.t2a = b.top[(size_t)2 * g.ld + a]; h.t2b = b.top[(size_t)2 * g.ld + a + 1];
+  h.daa = b.diag[4 * j]; h.dab = b.diag[4 * j + 1]; h.dbb = b.diag[4 * j + 2];
+  h.ya = b.y[a]; h.yb = b.y[a + 1];
+  h.mt = b.matched[j];
+}
+__device__ __forceinline__ void hot_store(const EkfGeom& g, const EkfBuffers& b, int j, const HotLm& h) {
+  const int a = 3 + 2 * j;
+  b.top[a] = h.t0a; b.top[a + 1] = h.t0b;
+  b.top[(size_t)g.ld + a] = h.t1a; b.top[(size_t)g.ld + a + 1] = h.t1b;
+  b.top[(size_t)2 * g.ld + a] = h.t2a; b.top[(size_t)2 * g.ld + a + 1] = h.t2b;
+  b.diag[4 * j] = h.daa; b.diag[4 * j + 1] = h.dab; b.diag[4 * j + 2] = h.dbb;
+  b.y[a] = h.ya; b.y[a + 1] = h.yb;
+}
+
+template <int FL_THREADS, bool COOP>
+__global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
+                                                               const double* __restrict__ R, int line0, int line1,
+                                                               int own_slot0, int prev_slot0, const int* __restrict__ prev_cnt_ptr) {
+  __shared__ int s_min[FL_THREADS / 32];
+  __shared__ double2 s_ka[FL_MAXP], s_kb[FL_MAXP], s_ksa[FL_MAXP], s_ksb[FL_MAXP];
+  const int prev_cnt = prev_cnt_ptr ? *prev_cnt_ptr : 0;   /* previous scan's terms not yet folded into b.P */
+  EkfDevState* st = b.st;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gstride = gridDim.x * blockDim.x;
+  auto group_sync = [] () {
+    if (COOP) cg::this_grid().sync(); else cg::this_cluster().sync();
+  };
+  const int L = st->L, epoch = st->epoch, pbase = st->pbase;
+  int nm = b.pidx[line0];             /* matches of this scan so far: tracked identically by every thread */
+  int ne = b.eidx[line0];
+  double A[3][3], xp[3];              /* every thread's own copy of P[0:3,0:3] (mirrored) and x_pre */
+  load_rr(g, b.top, A);
+  xp[0] = st->x_pre[0]; xp[1] = st->x_pre[1]; xp[2] = st->x_pre[2];
+  const bool cached = L <= gstride;   /* at most one landmark per thread: its hot entries stay in registers */
+  HotLm h;
+  if (cached && gtid < L) hot_load(g, b, gtid, h);
+  PendingList pl;
+  pl.prev_cnt = prev_cnt; pl.prev_slot0 = prev_slot0; pl.own_slot0 = own_slot0;
+  for (int line = line0; line < line1; ++line) {
+    TS(0);
+    /* ---- phase 1: gate of the owned landmarks (Robot.cpp:313-501) ---- */
+    const double Rl[4] = {R[4 * line], R[4 * line + 1], R[4 * line + 2], R[4 * line + 3]};
+    const double z0 = z[2 * line], z1 = z[2 * line + 1];
+    int cand = EKF_NO_MATCH;
+    for (int j = gtid; j < L; j += gstride) {
+      if (!cached) hot_load(g, b, j, h);
+      if (cand == EKF_NO_MATCH && h.mt != epoch) {
+        double Cm[5][5];
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) Cm[r][q] = A[r][q];
+        Cm[0][3] = Cm[3][0] = h.t0a; Cm[0][4] = Cm[4][0] = h.t0b;
+        Cm[1][3] = Cm[3][1] = h.t1a; Cm[1][4] = Cm[4][1] = h.t1b;
+        Cm[2][3] = Cm[3][2] = h.t2a; Cm[2][4] = Cm[4][2] = h.t2b;
+        Cm[3][3] = h.daa; Cm[3][4] = Cm[4][3] = h.dab; Cm[4][4] = h.dbb;
+        Gate G;
+        gate_from_block(Cm, h.ya, h.yb, xp, z0, z1, Rl, G);
+        if (G.singular) atomicOr(&st->sticky, EKF_STICKY_SINGULAR);
+        else if (!gate_rejects_d2(G.d2, g.gate_d2max)) {
+          cand = j;
+          double* rec = b.gates + (size_t)GATE_REC * j;
+          gate_store(rec, G);
+          rec[14] = h.t0a; rec[15] = h.t0b; rec[16] = h.t1a; rec[17] = h.t1b; rec[18] = h.t2a; rec[19] = h.t2b;
+        }
+      }
+    }
+    TS(1);
+    cand = __reduce_min_sync(0xffffffffu, cand);
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = cand;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int v = (threadIdx.x < FL_THREADS / 32) ? s_min[threadIdx.x] : EKF_NO_MATCH;
+      v = __reduce_min_sync(0xffffffffu, v);
+      if (threadIdx.x == 0 && v != EKF_NO_MATCH) atomicMin(&b.jbest[line], v);
+    }
+    TS(2);
+    group_sync();                                                     /* the winner is known; last line's gains are visible */
+    TS(3);
+    const int jw = b.jbest[line];
+    const int np = nm - pbase;
+    if (jw == EKF_NO_MATCH) {                                         /* :309 / :325 / :493 */
+      if (gtid == 0) { b.ext[ne] = line; b.eidx[line + 1] = ne + 1; b.pidx[line + 1] = nm; b.jout[line] = -1; }
+      ne += 1;
+      continue;
+    }
+    /* ---- phase 2: gain rows (Robot.cpp:516-560) and the whole hot update (:564-602) of what this thread owns ---- */
+    const int aw = 3 + 2 * jw, bw = aw + 1;
+    const double* rec = b.gates + (size_t)GATE_REC * jw;
+    Gate G;
+    gate_load(rec, G);
+    const double wt[3][2] = {{rec[14], rec[15]}, {rec[16], rec[17]}, {rec[18], rec[19]}};   /* P[0..2, aw], P[0..2, bw] */
+    const int npt = prev_cnt + np;
+    for (int i = threadIdx.x; i < npt; i += blockDim.x) {            /* the pending terms' entries at aw, bw: once per CTA */
+      const int slot = pl.slot(i);
+      s_ka[i] = b.Kp[(size_t)slot * g.ld + aw]; s_kb[i] = b.Kp[(size_t)slot * g.ld + bw];
+      s_ksa[i] = b.KSp[(size_t)slot * g.ld + aw]; s_ksb[i] = b.KSp[(size_t)slot * g.ld + bw];
+    }
+    const int out_slot = own_slot0 + np;
+    double2 kk[3], ks[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) gain_row(G, A[r][0], A[r][1], A[r][2], wt[r][0], wt[r][1], kk[r], ks[r]);
+    if (gtid == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { b.Kp[(size_t)out_slot * g.ld + r] = kk[r]; b.KSp[(size_t)out_slot * g.ld + r] = ks[r]; }
+    }
+    const double v0 = G.v[0], v1 = G.v[1];
+    __syncthreads();                                                  /* staging complete */
+    TS(4);
+    for (int j = gtid; j < L; j += gstride) {
+      const int a = 3 + 2 * j, bb = a + 1;
+      if (!cached) hot_load(g, b, j, h);
+      /* rows a and b of this landmark, one after the other (the prefetched correction chunk is 32 registers) */
+      double2 Ka, KSa, Kb, KSb;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = a + half;
+        GainRow d;
+        d.p0 = half ? h.t0b : h.t0a; d.p1 = half ? h.t1b : h.t1a; d.p2 = half ? h.t2b : h.t2a;
+        d.kind = 0;
+        if (j == jw) { d.pa = half ? h.dab : h.daa; d.pb = half ? h.dbb : h.dab; }
+        else if (j < jw) {                                            /* column part: P[r, aw], P[r, bw] */
+          const double* Pr = b.P + local_row(g, r) * g.ld;
+          d.pa = Pr[aw]; d.pb = Pr[bw];
+          d.kind = 1;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.KSp[(size_t)pl.slot(t) * g.ld + r];
+        } else {                                                      /* row part: P[aw, r], P[bw, r] */
+          d.pa = b.P[local_row(g, aw) * g.ld + r]; d.pb = b.P[local_row(g, bw) * g.ld + r];
+          d.kind = 2;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.Kp[(size_t)pl.slot(t) * g.ld + r];
+        }
+        gain_row_correct(g, b, r, npt, d, pl, s_ka, s_kb, s_ksa, s_ksb);
+        if (half) gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Kb, KSb);
+        else gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Ka, KSa);
+      }
+      b.Kp[(size_t)out_slot * g.ld + a] = Ka; b.KSp[(size_t)out_slot * g.ld + a] = KSa;
+      b.Kp[(size_t)out_slot * g.ld + bb] = Kb; b.KSp[(size_t)out_slot * g.ld + bb] = KSb;
+      /* Robot.cpp:564-589 on this landmark's hot elements */
+      h.t0a = sub_rank2(h.t0a, ks[0], Ka); h.t0b = sub_rank2(h.t0b, ks[0], Kb);
+      h.t1a = sub_rank2(h.t1a, ks[1], Ka); h.t1b = sub_rank2(h.t1b, ks[1], Kb);
+      h.t2a = sub_rank2(h.t2a, ks[2], Ka); h.t2b = sub_rank2(h.t2b, ks[2], Kb);
+      h.daa = sub_rank2(h.daa, KSa, Ka); h.dab = sub_rank2(h.dab, KSa, Kb); h.dbb = sub_rank2(h.dbb, KSb, Kb);
+      double ta = 0.0, tb = 0.0;
+      axpy_skip(ta, Ka.x, v0); axpy_skip(ta, Ka.y, v1);
+      axpy_skip(tb, Kb.x, v0); axpy_skip(tb, Kb.y, v1);
+      h.ya = add_rn(h.ya, ta); h.yb = add_rn(h.yb, tb);
+      if (j == jw) { h.mt = epoch; b.matched[j] = epoch; }            /* :501 */
+      hot_store(g, b, j, h);                                          /* write-through: other kernels read the hot arrays */
+    }
+    TS(5);
+    update_robot_block(kk, ks, v0, v1, A, xp);                        /* every thread's copy of the 3x3 block and the pose */
+    if (gtid == 0) {                                                  /* one writer publishes them; bookkeeping :501-504 */
+      for (int r = 0; r < 3; ++r) {
+        for (int q = r; q < 3; ++q) b.top[(size_t)r * g.ld + q] = A[r][q];
+        b.y[r] = xp[r]; st->pose[r] = xp[r]; st->x_pre[r] = xp[r];
+      }
+      st->v[0] = v0; st->v[1] = v1;
+      for (int t = 0; t < 4; ++t) st->S[t] = G.S[t];
+      b.jout[line] = jw;
+      b.pidx[line + 1] = nm + 1; b.eidx[line + 1] = ne;
+      st->np = np + 1;
+    }
+    TS(6);
+    nm += 1;
+  }
 }
 
 /* after a sweep in the middle of a scan: the pending list restarts empty */
@@ -1429,14 +1615,19 @@ void ekf_prefer_max_smem_carveout(void) {
   cudaFuncSetAttribute(k_scan_lines<512, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_scan_lines<512, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_scan_lines<512, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines2<512, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines2<512, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_a, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_b, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_c, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_queue_all, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   (void)cudaGetLastError();
 }
+/* EKF_LINE_LOOP=1 keeps the first, two-barrier form of the line loop on one GPU too (A/B measurement and bit checks) */
+static int line_loop_v1() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_LOOP"); v = (e && atoi(e) == 1) ? 1 : 0; } return v; }
 int ekf_pick_cluster(void) {
   cudaFuncSetAttribute(k_scan_lines<512, false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_scan_lines2<512, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   { const char* e = getenv("EKF_CLUSTER"); const int v = e ? atoi(e) : 0; if (v == 1 || v == 2 || v == 4 || v == 8) return v; }   /* A/B measurements */
   const int tries[2] = {16, 8};
   for (int t = 0; t < 2; ++t) {
@@ -1448,7 +1639,9 @@ int ekf_pick_cluster(void) {
     attr[0].val.clusterDim.x = tries[t]; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines<512, false, false>, &cfg) == cudaSuccess && n >= 1) return tries[t];
+    int n2 = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines<512, false, false>, &cfg) == cudaSuccess && n >= 1 &&
+        cudaOccupancyMaxActiveClusters(&n2, k_scan_lines2<512, false>, &cfg) == cudaSuccess && n2 >= 1) return tries[t];
   }
   (void)cudaGetLastError();
   return 8;
@@ -1466,7 +1659,11 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
                     (void*)&prev_slot0, (void*)&prev_cnt_ptr, (void*)&pe};
     if (peers && peers->world > 1)
       return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, true>, dim3(ctas), dim3(512), args, 0, s);
-    return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, false>, dim3(ctas), dim3(512), args, 0, s);
+    if (line_loop_v1())
+      return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, false>, dim3(ctas), dim3(512), args, 0, s);
+    void* args2[] = {(void*)&g, (void*)&b, (void*)&d_z, (void*)&d_R, (void*)&line0, (void*)&line1, (void*)&own_slot0,
+                     (void*)&prev_slot0, (void*)&prev_cnt_ptr};
+    return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<512, true>, dim3(ctas), dim3(512), args2, 0, s);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -1475,7 +1672,9 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_scan_lines<512, false, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr, pe);
+  if (line_loop_v1())
+    return cudaLaunchKernelEx(&cfg, k_scan_lines<512, false, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr, pe);
+  return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
 }
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
   k_flush_done<<<1, 32, 0, s>>>(b, next_line);

@@ -480,6 +480,48 @@ def test_overlapped_pipeline_interleaved_with_stepwise_calls(libekf, oracle_cls)
     compare_state(f, so, "interleaved final")
 
 
+def test_line_loop_forms_give_identical_bits(libekf):
+    """The one-barrier line loop (k_scan_lines2: a thread owns its landmarks' hot entries AND gain rows) against the
+    first two-barrier form (EKF_LINE_LOOP=1): cluster launch on a small map, cooperative launch beside the overlapped
+    sweep on a large one, more landmarks than threads (several landmarks per thread: hot entries from memory), scans with
+    unmatched lines (augmentation) in between -- matches, state and covariance bit for bit."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from slam_ros_b200 import EkfFilter, scenario as sc\n"
+        "out = {}\n"
+        "for N, m, steps in ((700, 8, 12), (3300, 8, 10), (3300, 24, 6), (12000, 8, 4)):\n"
+        "    scn = sc.map_scenario(N, steps, m=m, seed=5)\n"
+        "    f = EkfFilter(capacity_lines=N + 96)\n"
+        "    f.scan(np.zeros(3), scn['seed_z'], scn['seed_R'])\n"
+        "    J = []\n"
+        "    for s in range(steps):\n"
+        "        z = scn['z'][s].copy()\n"
+        "        if s %% 4 == 2: z[1::2, 1] += 3.0\n"
+        "        J.append(f.scan(scn['u'][s], z, scn['R'][s])[1])\n"
+        "    y = f.download_y()\n"
+        "    k = '%%d_%%d' %% (N, m)\n"
+        "    out['J_' + k] = np.stack(J); out['y_' + k] = y\n"
+        "    out['B_' + k] = np.stack([f.download_block(r0, c0, 64, 64) for r0, c0 in ((0, 0), (3, 3), (5, 900), (700, 1100), (len(y) - 64, len(y) - 64))])\n"
+        "    out['S_' + k] = np.array(f.cov_stats())\n"
+        "    f.close()\n"
+        "np.savez(sys.argv[1], **out)\n"
+    ) % ROOT
+    res = []
+    for v in ("1", "0"):
+        path = "/tmp/ekf_lineloop_%s_%d.npz" % (v, os.getpid())
+        env = dict(os.environ, EKF_LINE_LOOP=v)
+        out = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, timeout=900, env=env)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        res.append(dict(np.load(path)))
+        os.remove(path)
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert (res[0]["J_700_8"] >= 0).sum() > 50 and (res[0]["J_700_8"] < 0).sum() > 5
+
+
 @pytest.mark.parametrize("shape", [0, 9, 10])
 def test_sweep_kernels_give_identical_bits(libekf, shape):
     """EKF_SWEEP_SHAPE selects the consumers of the pipelined sweep: 11 = k_sweep_quad for every count (8x4 register
