@@ -14,10 +14,17 @@ lib = load_library()
 buf = (C.c_ulonglong * (16 * 16))()
 print("rc", lib.ekf_debug_line_timing(buf, 16 * 16))
 t = np.array(list(buf), dtype=np.int64).reshape(16, 16)
-names = ["start", "after landmark loop", "after block min/atomic", "after barrier1", "before row load", "after staging sync", "after rows", "after barrier2"]
+import os
+if os.environ.get("EKF_LINE_LOOP", "0") == "1":      # the first form's stamps
+    names = ["start", "after landmark loop", "after block min/atomic", "after barrier1", "before row load", "after staging sync", "after rows", "after barrier2"]
+    order = list(range(8))
+else:                                               # k_scan_lines2
+    names = {0: "start", 1: "gate done", 2: "min+atomic", 3: "barrier", 8: "jbest read", 9: "record read", 10: "robot gains", 11: "own loads issued",
+             4: "staging sync", 12: "corrections", 13: "own gains", 5: "hot update+stores", 6: "robot block"}
+    order = [0, 1, 2, 3, 8, 9, 10, 11, 4, 12, 13, 5, 6]
 for line in range(9):
-    row = t[line, :8]
+    row = t[line]
     if row[0] == 0: continue
     base = row[0]
-    print("line", line, " ".join("%s=%+.2fus" % (names[i][:14], (row[i] - base) / 1e3) for i in range(8) if row[i] > 0),
+    print("line", line, " ".join("%s=%+.2f" % (names[i][:16], (row[i] - base) / 1e3) for i in order if row[i] > 0),
           "| next start %+.2fus" % ((t[line + 1, 0] - base) / 1e3) if t[line + 1, 0] > 0 else "")

@@ -360,7 +360,7 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
   /* The line loop runs as EKF_LINE_SMS cooperative CTAs on the SMs the in-flight sweep leaves free (its
    * persistent grid is num_sms - EKF_LINE_SMS): no register / FP64-issue sharing with the sweep. */
   CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, 0, m, EKF_LINE_SMS, 1, slot0, ctx->pg_slot0,
-                           ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->stream));
+                           ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream));
   const int tgt = ctx->pg_valid ? (ctx->rd ^ 1) : ctx->rd;      /* source of this scan's sweep */
   EkfBuffers bt = ctx->b;
   bt.P = ctx->Pbuf[tgt];
@@ -426,7 +426,7 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
       /* row-sharded: the same kernel, launched cooperatively (its CTAs spin on the peers' arrival flags, so they
        * must all be resident), exchanges the H-column slices over NVLink peer memory between its phases */
       CU(ekf_launch_scan_lines(ctx->g, ctx->b, d_z, d_R, i0, i0 + cnt, ctx->cluster, ctx->peers_ok ? 1 : 0, 0, 0, 0,
-                               ctx->peers_ok ? &ctx->peers : 0, ctx->stream));
+                               ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream));
       ctx->launches++;
       ctx->pend_ub += cnt;
       i0 += cnt;
@@ -746,9 +746,15 @@ int ekf_scan(ekf_ctx* ctx, const double x_t0[3], const double u[3], int m, const
   if (x_t0) memcpy(h + 3, x_t0, 3 * sizeof(double));
   const size_t ml = ctx->max_lines;
   if (m > 0) { memcpy(h + 6, z, 2 * (size_t)m * sizeof(double)); memcpy(h + 6 + 2 * ml, R, 4 * (size_t)m * sizeof(double)); }
-  /* two H2D copies from pinned memory: [u|x|z] and [R] */
-  CU(cudaMemcpyAsync(ctx->d_in, h, (6 + 2 * (size_t)m) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (m > 0) CU(cudaMemcpyAsync(in_R(ctx), h + 6 + 2 * ml, 4 * (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  /* H2D from pinned memory: [u|x|z] and [R] -- as ONE copy spanning the unused z slots in between while that stays small
+   * (one driver call less on the latency path of small maps), else as two */
+  const size_t span = 6 + 2 * ml + 4 * (size_t)m;
+  if (m > 0 && span * sizeof(double) <= 8192) {
+    CU(cudaMemcpyAsync(ctx->d_in, h, span * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    CU(cudaMemcpyAsync(ctx->d_in, h, (6 + 2 * (size_t)m) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (m > 0) CU(cudaMemcpyAsync(in_R(ctx), h + 6 + 2 * ml, 4 * (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
   rc = enqueue_scan(ctx, in_u(ctx), x_t0 ? in_x(ctx) : 0, m, in_z(ctx), in_R(ctx));
   if (rc) return rc;
   if (m > 0 && j_out) CU(cudaMemcpyAsync(ctx->h_jout, ctx->b.jout, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -13,9 +13,18 @@
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
-/* acc += t*b with reference-BLAS NN/TN zero skip (t == 0 contributes nothing) */
+/* acc += t*b as the reference-BLAS NN/TN loops do it.  Those loops skip a term whose multiplier t is exactly zero; for
+ * finite b the skipped update acc + 0*b leaves acc bit for bit unchanged (only a zero acc can change sign), so the
+ * test-and-select is not issued: on B200 a DSETP + select in a dependent chain costs 18 cycles against 8 for the plain
+ * DMUL / DADD (profiles/r2_fp64_latency.log), and these chains ARE the per-line latency.  -DEKF_ZERO_SKIP restores the
+ * literal skip (it only differs when the covariance already holds Inf / NaN). */
+#ifdef EKF_ZERO_SKIP
+#define EKF_NZ(t) ((t) != 0.0)
+#else
+#define EKF_NZ(t) true
+#endif
 __device__ __forceinline__ void axpy_skip(double& acc, double t, double b) {
-  if (t != 0.0) acc = add_rn(acc, mul_rn(t, b));
+  if (EKF_NZ(t)) acc = add_rn(acc, mul_rn(t, b));
 }
 /* one rank-2 term of Robot.cpp:564:  (0 + ks.x*k.x) + ks.y*k.y  */
 __device__ __forceinline__ double rank2(double2 ks, double2 k) {
@@ -86,7 +95,7 @@ __device__ __forceinline__ int inv2x2_lu(const double S[4], double Si[4]) {
  * 0.0; those operations are exact (x*1 = x, x*(-1) = -x, 0 + x = x) and are not issued here: every value is bit for bit
  * what the literal sequence produces, except that a zero result may carry the other sign (0.0 + (-0.0) = +0.0), which no
  * comparison, product or sum downstream can tell apart.  What is kept is every operation that rounds, in the
- * reference's order, and the zero skips of the NN / TN loops. */
+ * reference's order (the zero skips of the NN / TN loops: see axpy_skip). */
 __device__ __forceinline__ void gate_from_block(const double Cm[5][5], double m0, double m1, const double x_pre[3],
                                                 double z0, double z1, const double R[4], Gate& G) {
   const double c = cos(m0), s = sin(m0);
@@ -96,7 +105,7 @@ __device__ __forceinline__ void gate_from_block(const double Cm[5][5], double m0
   double HP0[5], HP1[5];
 #pragma unroll
   for (int t = 0; t < 5; ++t) {                                       /* :397  H * P  (NN, k = 0,1,2,a,b) */
-    double h1 = (H10 != 0.0) ? mul_rn(H10, Cm[0][t]) : 0.0;
+    double h1 = EKF_NZ(H10) ? mul_rn(H10, Cm[0][t]) : 0.0;
     axpy_skip(h1, H11, Cm[1][t]);
     axpy_skip(h1, gg, Cm[3][t]);
     h1 = add_rn(h1, Cm[4][t]);
@@ -126,9 +135,9 @@ __device__ __forceinline__ void gate_from_block(const double Cm[5][5], double m0
   else if (fabs(add_rn(v0, two_pi)) < fabs(v0)) v0 = add_rn(v0, two_pi);
   G.v[0] = v0; G.v[1] = v1;
   double w0 = 0.0, w1 = 0.0;                                          /* :479  v' * Sinv  (TN) */
-  if (v0 != 0.0) { w0 = mul_rn(v0, G.Si[0]); w1 = mul_rn(v0, G.Si[1]); }
+  if (EKF_NZ(v0)) { w0 = mul_rn(v0, G.Si[0]); w1 = mul_rn(v0, G.Si[1]); }
   axpy_skip(w0, v1, G.Si[2]); axpy_skip(w1, v1, G.Si[3]);
-  double d2 = (w0 != 0.0) ? mul_rn(w0, v0) : 0.0;                     /* :483 */
+  double d2 = EKF_NZ(w0) ? mul_rn(w0, v0) : 0.0;                      /* :483 */
   axpy_skip(d2, w1, v1);
   G.d2 = d2;
 }
@@ -143,10 +152,10 @@ __device__ __forceinline__ void gain_row(const Gate& G, double p0, double p1, do
   ph1 = add_rn(ph1, mul_rn(pa, gg));
   ph1 = add_rn(ph1, pb);
   double k0 = 0.0, k1 = 0.0;                                          /* :526  PHt * Sinv  (NN) */
-  if (ph0 != 0.0) { k0 = mul_rn(ph0, G.Si[0]); k1 = mul_rn(ph0, G.Si[1]); }
+  if (EKF_NZ(ph0)) { k0 = mul_rn(ph0, G.Si[0]); k1 = mul_rn(ph0, G.Si[1]); }
   axpy_skip(k0, ph1, G.Si[2]); axpy_skip(k1, ph1, G.Si[3]);
   double s0 = 0.0, s1 = 0.0;                                          /* :560  K * S  (NN) */
-  if (k0 != 0.0) { s0 = mul_rn(k0, G.S[0]); s1 = mul_rn(k0, G.S[1]); }
+  if (EKF_NZ(k0)) { s0 = mul_rn(k0, G.S[0]); s1 = mul_rn(k0, G.S[1]); }
   axpy_skip(s0, k1, G.S[2]); axpy_skip(s1, k1, G.S[3]);
   K = make_double2(k0, k1); KS = make_double2(s0, s1);
 }

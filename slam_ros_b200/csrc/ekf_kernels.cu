@@ -86,11 +86,21 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_predict(EkfGeom g, EkfBuffers b, 
   const double F02 = mul_rn(-u0, sa), F12 = mul_rn(u0, ca);               /* :157, :160 */
   const int nl = 3 + 2 * st->L;
   double* t0p = b.top; double* t1p = b.top + g.ld; const double* t2p = b.top + 2 * (size_t)g.ld;
-  for (int q = 3 + gid; q < nl; q += stride) {                        /* :242 rows 0,1 of Fx*P (== cols 0,1 of (.)Fx') */
+  /* :242 rows 0,1 of Fx*P (== cols 0,1 of (.)Fx'): P[0,q] += F02 P[2,q], P[1,q] += F12 P[2,q] over the live columns, as a
+   * coalesced sweep of 16-byte column pairs (the rows start on 2 KB boundaries; column 3 is the one unpaired entry) */
+  if (gid < 2 && nl > 3) {                                            /* the two unpaired ends: columns 3 and nl - 1 */
+    const int q = gid ? nl - 1 : 3;
     const double p2 = t2p[q];
     double a0 = add_rn(0.0, t0p[q]); axpy_skip(a0, F02, p2);
     double a1 = add_rn(0.0, t1p[q]); axpy_skip(a1, F12, p2);
     t0p[q] = a0; t1p[q] = a1;
+  }
+  for (int q = 4 + 2 * gid; q + 1 < nl - 1; q += 2 * stride) {        /* aligned pairs (4,5) .. (nl-3, nl-2) */
+    const double2 p2 = *reinterpret_cast<const double2*>(t2p + q);
+    double2 r0 = *reinterpret_cast<const double2*>(t0p + q), r1 = *reinterpret_cast<const double2*>(t1p + q);
+    r0.x = add_rn(0.0, r0.x); axpy_skip(r0.x, F02, p2.x); r0.y = add_rn(0.0, r0.y); axpy_skip(r0.y, F02, p2.y);
+    r1.x = add_rn(0.0, r1.x); axpy_skip(r1.x, F12, p2.x); r1.y = add_rn(0.0, r1.y); axpy_skip(r1.y, F12, p2.y);
+    *reinterpret_cast<double2*>(t0p + q) = r0; *reinterpret_cast<double2*>(t1p + q) = r1;
   }
   for (int i = gid; i < m; i += stride) { b.jbest[i] = EKF_NO_MATCH; b.jout[i] = -1; }
   if (gid == 0) {
@@ -701,7 +711,7 @@ __device__ __forceinline__ void hot_store(const EkfGeom& g, const EkfBuffers& b,
   b.y[a] = h.ya; b.y[a + 1] = h.yb;
 }
 
-template <int FL_THREADS, bool COOP>
+template <int FL_THREADS, bool COOP, bool CACHED>
 __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
                                                                const double* __restrict__ R, int line0, int line1,
                                                                int own_slot0, int prev_slot0, const int* __restrict__ prev_cnt_ptr) {
@@ -711,6 +721,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuf
   EkfDevState* st = b.st;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gstride = gridDim.x * blockDim.x;
+  const int scribe = gstride - 1;      /* the thread that writes the replicated results (last of the grid: on small maps it owns no landmark) */
   auto group_sync = [] () {
     if (COOP) cg::this_grid().sync(); else cg::this_cluster().sync();
   };
@@ -720,7 +731,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuf
   double A[3][3], xp[3];              /* every thread's own copy of P[0:3,0:3] (mirrored) and x_pre */
   load_rr(g, b.top, A);
   xp[0] = st->x_pre[0]; xp[1] = st->x_pre[1]; xp[2] = st->x_pre[2];
-  const bool cached = L <= gstride;   /* at most one landmark per thread: its hot entries stay in registers */
+  constexpr bool cached = CACHED;     /* host guarantee: at most one landmark per thread (L <= threads): its hot entries stay in registers */
   HotLm h;
   if (cached && gtid < L) hot_load(g, b, gtid, h);
   PendingList pl;
@@ -765,8 +776,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuf
     TS(3);
     const int jw = b.jbest[line];
     const int np = nm - pbase;
+    if (jw != EKF_NO_MATCH) TS(8);
     if (jw == EKF_NO_MATCH) {                                         /* :309 / :325 / :493 */
-      if (gtid == 0) { b.ext[ne] = line; b.eidx[line + 1] = ne + 1; b.pidx[line + 1] = nm; b.jout[line] = -1; }
+      if (gtid == scribe) { b.ext[ne] = line; b.eidx[line + 1] = ne + 1; b.pidx[line + 1] = nm; b.jout[line] = -1; }
       ne += 1;
       continue;
     }
@@ -775,6 +787,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuf
     const double* rec = b.gates + (size_t)GATE_REC * jw;
     Gate G;
     gate_load(rec, G);
+    TS(9);
     const double wt[3][2] = {{rec[14], rec[15]}, {rec[16], rec[17]}, {rec[18], rec[19]}};   /* P[0..2, aw], P[0..2, bw] */
     const int npt = prev_cnt + np;
     for (int i = threadIdx.x; i < npt; i += blockDim.x) {            /* the pending terms' entries at aw, bw: once per CTA */
@@ -786,41 +799,95 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuf
     double2 kk[3], ks[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) gain_row(G, A[r][0], A[r][1], A[r][2], wt[r][0], wt[r][1], kk[r], ks[r]);
-    if (gtid == 0) {
+    if (gtid == scribe) {
 #pragma unroll
       for (int r = 0; r < 3; ++r) { b.Kp[(size_t)out_slot * g.ld + r] = kk[r]; b.KSp[(size_t)out_slot * g.ld + r] = ks[r]; }
     }
+    TS(10);
     const double v0 = G.v[0], v1 = G.v[1];
+    /* the two cold entries of each owned row (a, b) at the winner's columns, and the first pending terms' entries of
+     * those rows: everything that has to come from L2 is issued here, in one round trip, before the staging barrier */
+    constexpr int CH = 4;                                             /* pending terms fetched per row and round trip */
+    const int jc = gtid;                                              /* cached form: the one owned landmark */
+    const bool own1 = cached && jc < L;
+    double cpa[2] = {0.0, 0.0}, cpb[2] = {0.0, 0.0};
+    double2 cv[2][CH];
+    int ckind = 0;
+    if (own1 && jc != jw) {
+      const int a = 3 + 2 * jc;
+      ckind = jc < jw ? 1 : 2;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int r = a + hf;
+        if (ckind == 1) { cpa[hf] = b.P[(size_t)r * g.ld + aw]; cpb[hf] = b.P[(size_t)r * g.ld + bw]; }
+        else { cpa[hf] = b.P[(size_t)aw * g.ld + r]; cpb[hf] = b.P[(size_t)bw * g.ld + r]; }
+        const double2* src = ckind == 1 ? b.KSp : b.Kp;
+#pragma unroll
+        for (int t = 0; t < CH; ++t) if (t < npt) cv[hf][t] = src[(size_t)pl.slot(t) * g.ld + r];
+      }
+    }
+    TS(11);
     __syncthreads();                                                  /* staging complete */
     TS(4);
     for (int j = gtid; j < L; j += gstride) {
       const int a = 3 + 2 * j, bb = a + 1;
-      if (!cached) hot_load(g, b, j, h);
-      /* rows a and b of this landmark, one after the other (the prefetched correction chunk is 32 registers) */
       double2 Ka, KSa, Kb, KSb;
+      if (cached) {
+        /* rows a and b together: the pending terms in order, CH at a time (Robot.cpp:564-568 applied on the fly) */
+        double pa0 = cpa[0], pb0 = cpb[0], pa1 = cpa[1], pb1 = cpb[1];
+        if (j == jw) { pa0 = h.daa; pb0 = h.dab; pa1 = h.dab; pb1 = h.dbb; }
+        else {
+          const double2* src = ckind == 1 ? b.KSp : b.Kp;
+          for (int i0 = 0; i0 < npt; i0 += CH) {
+            if (i0 > 0) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int r = a + half;
-        GainRow d;
-        d.p0 = half ? h.t0b : h.t0a; d.p1 = half ? h.t1b : h.t1a; d.p2 = half ? h.t2b : h.t2a;
-        d.kind = 0;
-        if (j == jw) { d.pa = half ? h.dab : h.daa; d.pb = half ? h.dbb : h.dab; }
-        else if (j < jw) {                                            /* column part: P[r, aw], P[r, bw] */
-          const double* Pr = b.P + local_row(g, r) * g.ld;
-          d.pa = Pr[aw]; d.pb = Pr[bw];
-          d.kind = 1;
+              for (int t = 0; t < CH; ++t) if (i0 + t < npt) {
+                cv[0][t] = src[(size_t)pl.slot(i0 + t) * g.ld + a]; cv[1][t] = src[(size_t)pl.slot(i0 + t) * g.ld + bb];
+              }
+            }
 #pragma unroll
-          for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.KSp[(size_t)pl.slot(t) * g.ld + r];
-        } else {                                                      /* row part: P[aw, r], P[bw, r] */
-          d.pa = b.P[local_row(g, aw) * g.ld + r]; d.pb = b.P[local_row(g, bw) * g.ld + r];
-          d.kind = 2;
-#pragma unroll
-          for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.Kp[(size_t)pl.slot(t) * g.ld + r];
+            for (int t = 0; t < CH; ++t) if (i0 + t < npt) {
+              if (ckind == 1) {
+                pa0 = sub_rank2(pa0, cv[0][t], s_ka[i0 + t]); pb0 = sub_rank2(pb0, cv[0][t], s_kb[i0 + t]);
+                pa1 = sub_rank2(pa1, cv[1][t], s_ka[i0 + t]); pb1 = sub_rank2(pb1, cv[1][t], s_kb[i0 + t]);
+              } else {
+                pa0 = sub_rank2(pa0, s_ksa[i0 + t], cv[0][t]); pb0 = sub_rank2(pb0, s_ksb[i0 + t], cv[0][t]);
+                pa1 = sub_rank2(pa1, s_ksa[i0 + t], cv[1][t]); pb1 = sub_rank2(pb1, s_ksb[i0 + t], cv[1][t]);
+              }
+            }
+          }
         }
-        gain_row_correct(g, b, r, npt, d, pl, s_ka, s_kb, s_ksa, s_ksb);
-        if (half) gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Kb, KSb);
-        else gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Ka, KSa);
+        TS(12);
+        gain_row(G, h.t0a, h.t1a, h.t2a, pa0, pb0, Ka, KSa);
+        gain_row(G, h.t0b, h.t1b, h.t2b, pa1, pb1, Kb, KSb);
+      } else {
+        hot_load(g, b, j, h);
+        /* several landmarks per thread: rows a and b one after the other through the chunked loader of the first form */
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int r = a + half;
+          GainRow d;
+          d.p0 = half ? h.t0b : h.t0a; d.p1 = half ? h.t1b : h.t1a; d.p2 = half ? h.t2b : h.t2a;
+          d.kind = 0;
+          if (j == jw) { d.pa = half ? h.dab : h.daa; d.pb = half ? h.dbb : h.dab; }
+          else if (j < jw) {                                          /* column part: P[r, aw], P[r, bw] */
+            const double* Pr = b.P + (size_t)r * g.ld;
+            d.pa = Pr[aw]; d.pb = Pr[bw];
+            d.kind = 1;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.KSp[(size_t)pl.slot(t) * g.ld + r];
+          } else {                                                    /* row part: P[aw, r], P[bw, r] */
+            d.pa = b.P[(size_t)aw * g.ld + r]; d.pb = b.P[(size_t)bw * g.ld + r];
+            d.kind = 2;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) if (t < npt) d.v[t] = b.Kp[(size_t)pl.slot(t) * g.ld + r];
+          }
+          gain_row_correct(g, b, r, npt, d, pl, s_ka, s_kb, s_ksa, s_ksb);
+          if (half) gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Kb, KSb);
+          else gain_row(G, d.p0, d.p1, d.p2, d.pa, d.pb, Ka, KSa);
+        }
       }
+      TS(13);
       b.Kp[(size_t)out_slot * g.ld + a] = Ka; b.KSp[(size_t)out_slot * g.ld + a] = KSa;
       b.Kp[(size_t)out_slot * g.ld + bb] = Kb; b.KSp[(size_t)out_slot * g.ld + bb] = KSb;
       /* Robot.cpp:564-589 on this landmark's hot elements */
@@ -837,7 +904,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuf
     }
     TS(5);
     update_robot_block(kk, ks, v0, v1, A, xp);                        /* every thread's copy of the 3x3 block and the pose */
-    if (gtid == 0) {                                                  /* one writer publishes them; bookkeeping :501-504 */
+    if (gtid == scribe) {                                                  /* one writer publishes them; bookkeeping :501-504 */
       for (int r = 0; r < 3; ++r) {
         for (int q = r; q < 3; ++q) b.top[(size_t)r * g.ld + q] = A[r][q];
         b.y[r] = xp[r]; st->pose[r] = xp[r]; st->x_pre[r] = xp[r];
@@ -1615,8 +1682,11 @@ void ekf_prefer_max_smem_carveout(void) {
   cudaFuncSetAttribute(k_scan_lines<512, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_scan_lines<512, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_scan_lines<512, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(k_scan_lines2<512, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(k_scan_lines2<512, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines2<512, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines2<512, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines2<512, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines2<256, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_scan_lines2<512, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_a, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_b, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_c, cudaFuncAttributePreferredSharedMemoryCarveout, c);
@@ -1627,7 +1697,9 @@ void ekf_prefer_max_smem_carveout(void) {
 static int line_loop_v1() { static int v = -1; if (v < 0) { const char* e = getenv("EKF_LINE_LOOP"); v = (e && atoi(e) == 1) ? 1 : 0; } return v; }
 int ekf_pick_cluster(void) {
   cudaFuncSetAttribute(k_scan_lines<512, false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  cudaFuncSetAttribute(k_scan_lines2<512, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_scan_lines2<512, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_scan_lines2<256, false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_scan_lines2<512, false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   { const char* e = getenv("EKF_CLUSTER"); const int v = e ? atoi(e) : 0; if (v == 1 || v == 2 || v == 4 || v == 8) return v; }   /* A/B measurements */
   const int tries[2] = {16, 8};
   for (int t = 0; t < 2; ++t) {
@@ -1641,14 +1713,14 @@ int ekf_pick_cluster(void) {
     int n = 0;
     int n2 = 0;
     if (cudaOccupancyMaxActiveClusters(&n, k_scan_lines<512, false, false>, &cfg) == cudaSuccess && n >= 1 &&
-        cudaOccupancyMaxActiveClusters(&n2, k_scan_lines2<512, false>, &cfg) == cudaSuccess && n2 >= 1) return tries[t];
+        cudaOccupancyMaxActiveClusters(&n2, k_scan_lines2<512, false, false>, &cfg) == cudaSuccess && n2 >= 1) return tries[t];
   }
   (void)cudaGetLastError();
   return 8;
 }
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                   int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
-                                  const int* prev_cnt_ptr, const EkfPeers* peers, cudaStream_t s) {
+                                  const int* prev_cnt_ptr, const EkfPeers* peers, int L_ub, cudaStream_t s) {
   if (line1 <= line0) return cudaSuccess;
   EkfPeers pe;
   memset(&pe, 0, sizeof pe);
@@ -1663,7 +1735,9 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
       return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, false>, dim3(ctas), dim3(512), args, 0, s);
     void* args2[] = {(void*)&g, (void*)&b, (void*)&d_z, (void*)&d_R, (void*)&line0, (void*)&line1, (void*)&own_slot0,
                      (void*)&prev_slot0, (void*)&prev_cnt_ptr};
-    return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<512, true>, dim3(ctas), dim3(512), args2, 0, s);
+    /* at most one landmark per thread (host-side bound): the form that keeps the hot entries in registers */
+    if (L_ub <= ctas * 512) return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<512, true, true>, dim3(ctas), dim3(512), args2, 0, s);
+    return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<512, true, false>, dim3(ctas), dim3(512), args2, 0, s);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -1674,7 +1748,14 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (line_loop_v1())
     return cudaLaunchKernelEx(&cfg, k_scan_lines<512, false, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr, pe);
-  return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
+  if (L_ub <= ctas * 256) {
+    /* small maps: 256-thread CTAs may use up to 255 registers -- no spills on the per-line critical path */
+    cfg.blockDim = dim3(256);
+    return cudaLaunchKernelEx(&cfg, k_scan_lines2<256, false, true>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
+  }
+  if (L_ub <= ctas * 512)
+    return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false, true>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
+  return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
 }
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
   k_flush_done<<<1, 32, 0, s>>>(b, next_line);
