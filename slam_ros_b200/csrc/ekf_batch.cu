@@ -28,6 +28,9 @@
 #include <string.h>
 
 #define EKFB_THREADS 128
+#ifndef EKFB_MIN_CTAS
+#define EKFB_MIN_CTAS 4           /* CTAs per SM the register budget is cut for (4 x 128 threads x 128 registers = the whole file) */
+#endif
 
 struct EkfBatchState {
   double pose[3];
@@ -147,10 +150,10 @@ __device__ __forceinline__ void batch_update_cold(double* __restrict__ P, const 
 
 /* The whole scan of one filter.  ns: columns of the packed triangle that fit the shared-memory carve-up. */
 #ifdef EKFB_TIMING
-#define BT_DECL long long bt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long bt0_ = clock64()
+#define BT_DECL long long bt_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long bt0_ = clock64()
 #define BT_MARK(k) do { const long long n_ = clock64(); bt_[k] += n_ - bt0_; bt0_ = n_; } while (0)
 #define BT_RESET() bt0_ = clock64()
-#define BT_PRINT() do { if (blockIdx.x == 7 && (threadIdx.x == 0 || threadIdx.x == 32)) printf("k_batch_scan block 7 thread %d, cycles: load %lld predict %lld | per scan: A %lld, B(gate or cold pass) %lld, B-barrier %lld, C %lld, C-barrier %lld | tail %lld\n", (int)threadIdx.x, bt_[0], bt_[1], bt_[2], bt_[3], bt_[4], bt_[5], bt_[6], bt_[7]); } while (0)
+#define BT_PRINT() do { if (blockIdx.x == 7 && (threadIdx.x == 0 || threadIdx.x == 32)) printf("k_batch_scan block 7 thread %d, cycles: load %lld predict %lld | per scan: A %lld, B(gate or cold pass) %lld, B-barrier %lld, C %lld (setup %lld, loads+correction %lld, gain %lld, stores %lld), C-barrier %lld | tail %lld\n", (int)threadIdx.x, bt_[0], bt_[1], bt_[2], bt_[3], bt_[4], bt_[5] + bt_[8] + bt_[9] + bt_[10] + bt_[11], bt_[8], bt_[9], bt_[10], bt_[11], bt_[6], bt_[7]); } while (0)
 #else
 #define BT_DECL do { } while (0)
 #define BT_MARK(k) do { } while (0)
@@ -388,6 +391,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
       double2* KSw = KSs + (size_t)(nmatch & 1) * kn;
       double2 kpa = make_double2(0.0, 0.0), kpb = kpa, kspa = kpa, kspb = kpa;
       if (np == 1) { kpa = Kp[a]; kpb = Kp[bb]; kspa = KSp[a]; kspb = KSp[bb]; }
+      BT_MARK(8);
       for (int r = tid; r < nl; r += nt) {
         const int tr_ = tri(r);
         const double p0 = (r <= 0) ? Ps[r] : Ps[tr_];                 /* P[r,0..2] through the upper storage */
@@ -399,9 +403,12 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
           if (r < a) { const double2 ksr = KSp[r]; pa = sub_rank2(pa, ksr, kpa); pb = sub_rank2(pb, ksr, kpb); }
           else { const double2 kr = Kp[r]; pa = sub_rank2(pa, kspa, kr); pb = sub_rank2(pb, kspb, kr); }
         }
+        BT_MARK(9);
         double2 Kr, KSr;
         gain_row(sG, p0, p1, p2, pa, pb, Kr, KSr);
+        BT_MARK(10);
         Kw[r] = Kr; KSw[r] = KSr;
+        BT_MARK(11);
       }
     }
     nmatch += 1; np += 1; have_new = true;
@@ -506,7 +513,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
 }
 
 /* Robot::localize for filter blockIdx.x */
-__global__ void __launch_bounds__(EKFB_THREADS, 4) k_batch_scan(EkfBatchGeom g, int ns, double* __restrict__ Yg,
+__global__ void __launch_bounds__(EKFB_THREADS, EKFB_MIN_CTAS) k_batch_scan(EkfBatchGeom g, int ns, double* __restrict__ Yg,
                                                                 double* __restrict__ Pg, EkfBatchState* __restrict__ Sg,
                                                                 const double* __restrict__ U, const double* __restrict__ Z,
                                                                 const double* __restrict__ Rm, int m, int* __restrict__ Jout) {
