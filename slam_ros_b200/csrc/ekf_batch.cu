@@ -42,6 +42,7 @@ struct EkfBatchState {
 
 struct EkfBatchGeom {
   double2* scratch;         /* [B][4][n]: the pending gains of filters that run off chip */
+  unsigned* sm_turn;        /* [256]: per SM, CTAs started there so far -- deals the association warp round-robin over the schedulers */
   int B, cap, n, headroom;
   double gate, enc_noise, gate_d2max;
   long long pstride;        /* doubles per filter in the packed covariance array (even: 16-byte aligned filters) */
@@ -56,7 +57,7 @@ __host__ __device__ inline int tri(int q) { return (q * (q + 1)) >> 1; }        
 /* shared-memory carve-up: the packed triangle holds columns < ns (a HINT: the largest map the host last saw, plus a
  * little; a filter that has outgrown it works on its HBM copy instead -- slower, same bits); y and the gain vectors
  * are sized by the capacity */
-struct BatchLayout { int P, y, K, KS, ext, matched, bytes; };
+struct BatchLayout { int P, y, K, KS, zr, ext, matched, bytes; };
 __host__ __device__ inline BatchLayout batch_layout(int ns, int n, int cap, int m) {
   BatchLayout l;
   int o = 0;
@@ -64,6 +65,7 @@ __host__ __device__ inline BatchLayout batch_layout(int ns, int n, int cap, int 
   l.y = o; o += ((n + 1) & ~1) * 8;
   l.K = o; o += 2 * ns * 16;                         /* two pending gains: K, then K S (off-chip filters: HBM scratch) */
   l.KS = o; o += 2 * ns * 16;
+  l.zr = o; o += 6 * m * 8;                          /* the scan's lines: z (2 m), then R (4 m) */
   l.ext = o; o += ((m + 3) & ~3) * 4;
   l.matched = o; o += (cap + 15) & ~15;
   l.bytes = o;
@@ -98,62 +100,83 @@ __device__ __forceinline__ void b_bulk_store(void* dst, const void* src, unsigne
 
 /* Robot.cpp:564-568 on the COLD elements of the packed upper triangle, p <- (p - (K S)_0[r] K_0[q]) - (K S)_1[r] K_1[q] for
  * one or two pending matches in their order: column q >= 3, rows 3 up to (excluding) its landmark's 2x2 diagonal block;
- * rows 0..2 and the diagonal blocks are the hot part (phase A of the line loop).  A lane owns the rows lane, lane + 32,
- * lane + 64, lane + 96 and keeps their (K S) entries in registers for the whole pass; it walks consecutive rows of a column
- * (conflict-free) and takes the columns two at a time, a long one with a short one: per element and pass the shared
- * memory sees one 8-byte load and one 8-byte store.  Warp w0 of nw. */
+ * rows 0..2 and the diagonal blocks are the hot part (phase A of the line loop).
+ *
+ * Work is cut into bands of 32 rows: lane l of every warp owns row rb + l of the band and keeps that row's (K S) entries in
+ * registers; the columns that reach the band are dealt round-robin to the warps, and a warp takes four of its columns per
+ * step -- the four column gains and the four elements are loaded first, then updated, then stored, so that the shared-memory
+ * latency and the dependent multiply-add pairs of four independent elements overlap.  Consecutive lanes touch consecutive
+ * words of a packed column: conflict-free.  (The first form of this pass walked long/short column pairs with four rows per
+ * lane; its per-pair address and predicate arithmetic made it 2.5 k instructions per warp and pass, issued at one per ~6
+ * cycles -- the phase timers showed it, not the association gate beside it, bounding the line loop.)  Warp w0 of nw. */
+template <bool TWO, int NW>
+__device__ __forceinline__ void batch_update_cold_t(double* __restrict__ P, const double2* __restrict__ K0, const double2* __restrict__ KS0,
+                                                    const double2* __restrict__ K1, const double2* __restrict__ KS1,
+                                                    int nl, int w0, int lane) {
+  for (int rb = 0; rb + 2 < nl; rb += 32) {          /* the last column's cold rows end at nl - 3 */
+    const int r = rb + lane;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0;
+    if (r < nl) { a0 = KS0[r]; if (TWO) a1 = KS1[r]; }
+    const bool rok = r >= 3;
+    /* Column q is cold above its landmark's diagonal block, rows < e(q) = (q - 1) | 1.  It reaches this band from
+     * q = rb + 1 on and covers the whole band from q = rb + 33 on: only the columns in between need a per-row test. */
+    int q = (rb + 1 > 3 ? rb + 1 : 3) + w0;
+    const int qfull = rb + 33 < nl ? rb + 33 : nl;
+    /* tri(q + d) - tri(q) = d q + tri(d): the four columns of a step sit at e, e + (NW q + tri(NW)), ...  Everything is
+     * taken four columns at a time -- loads, then the multiply-add pairs, then stores -- so that a step costs one
+     * shared-memory latency and one dependent chain, not four; the ragged steps carry a per-column predicate. */
+    double* e = P + tri(q) + r;
+    const double2* k0p = K0 + q;
+    const double2* k1p = K1 + q;
+    const double2 zz = make_double2(0.0, 0.0);
+#define EKFB_COLD_STEP(OK0, OK1, OK2, OK3)                                                                             \
+    {                                                                                                                  \
+      const int s1 = NW * q + tri(NW), s2 = 2 * NW * q + tri(2 * NW), s3 = 3 * NW * q + tri(3 * NW);                   \
+      const bool o0 = (OK0), o1 = (OK1), o2 = (OK2), o3 = (OK3);                                                       \
+      const double p0 = o0 ? e[0] : 0.0, p1 = o1 ? e[s1] : 0.0, p2 = o2 ? e[s2] : 0.0, p3 = o3 ? e[s3] : 0.0;          \
+      const double2 g0 = o0 ? k0p[0] : zz, g1 = o1 ? k0p[NW] : zz, g2 = o2 ? k0p[2 * NW] : zz, g3 = o3 ? k0p[3 * NW] : zz; \
+      double x0 = sub_rank2(p0, a0, g0), x1 = sub_rank2(p1, a0, g1), x2 = sub_rank2(p2, a0, g2), x3 = sub_rank2(p3, a0, g3); \
+      if (TWO) {                                                                                                       \
+        const double2 h0 = o0 ? k1p[0] : zz, h1 = o1 ? k1p[NW] : zz, h2 = o2 ? k1p[2 * NW] : zz, h3 = o3 ? k1p[3 * NW] : zz; \
+        x0 = sub_rank2(x0, a1, h0); x1 = sub_rank2(x1, a1, h1); x2 = sub_rank2(x2, a1, h2); x3 = sub_rank2(x3, a1, h3); \
+      }                                                                                                                \
+      if (o0) e[0] = x0;                                                                                               \
+      if (o1) e[s1] = x1;                                                                                              \
+      if (o2) e[s2] = x2;                                                                                              \
+      if (o3) e[s3] = x3;                                                                                              \
+      e += 4 * NW * q + tri(4 * NW);                                                                                   \
+      k0p += 4 * NW; k1p += 4 * NW;                                                                                    \
+      q += 4 * NW;                                                                                                     \
+    }
+#define EKFB_COLD_OK(d) (rok && q + (d) < nl && r < ((q + (d) - 1) | 1))
+    while (q < qfull) EKFB_COLD_STEP(EKFB_COLD_OK(0), EKFB_COLD_OK(NW), EKFB_COLD_OK(2 * NW), EKFB_COLD_OK(3 * NW))
+    if (rok) {
+      while (q + 3 * NW < nl) EKFB_COLD_STEP(true, true, true, true)
+      if (q < nl) EKFB_COLD_STEP(true, q + NW < nl, q + 2 * NW < nl, q + 3 * NW < nl)
+    }
+#undef EKFB_COLD_OK
+#undef EKFB_COLD_STEP
+  }
+}
+/* nw is 3 beside an association (the fourth warp gates) and 4 after the scan's last line */
 __device__ __forceinline__ void batch_update_cold(double* __restrict__ P, const double2* __restrict__ K0, const double2* __restrict__ KS0,
                                                   const double2* __restrict__ K1, const double2* __restrict__ KS1, bool two,
                                                   int nl, int w0, int nw, int lane) {
-  const int npair = (nl - 2) >> 1;                          /* columns 3 .. nl-1 in pairs (3 + c, nl - 1 - c) */
-  for (int rb = 0; rb < nl; rb += 128) {                    /* maps beyond 128 rows: one more sweep per 128 rows */
-    double2 a0[4], a1[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int r = rb + lane + 32 * t;
-      a0[t] = make_double2(0.0, 0.0); a1[t] = a0[t];
-      if (r < nl) { a0[t] = KS0[r]; if (two) a1[t] = KS1[r]; }
-    }
-    for (int c = w0; c < npair; c += nw) {
-      const int qs = 3 + c, ql = nl - 1 - c;                /* short and long column of the pair (qs <= ql) */
-      const int es = (qs & 1) ? qs : qs - 1, el = (ql & 1) ? ql : ql - 1;      /* first hot row of each */
-      if (el <= rb) continue;
-      const double2 ks0 = K0[qs], kl0 = K0[ql];
-      double2 ks1 = ks0, kl1 = kl0;
-      if (two) { ks1 = K1[qs]; kl1 = K1[ql]; }
-      double* cs = P + tri(qs);
-      double* cl = P + tri(ql);
-      double pl[4], ps[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int r = rb + lane + 32 * t;
-        if (r >= 3 && r < el) pl[t] = cl[r];
-        if (r >= 3 && r < es && qs != ql) ps[t] = cs[r];
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int r = rb + lane + 32 * t;
-        if (r >= 3 && r < el) {
-          double p = sub_rank2(pl[t], a0[t], kl0);
-          if (two) p = sub_rank2(p, a1[t], kl1);
-          cl[r] = p;
-        }
-        if (r >= 3 && r < es && qs != ql) {
-          double p = sub_rank2(ps[t], a0[t], ks0);
-          if (two) p = sub_rank2(p, a1[t], ks1);
-          cs[r] = p;
-        }
-      }
-    }
+  if (nw == 3) {
+    if (two) batch_update_cold_t<true, 3>(P, K0, KS0, K1, KS1, nl, w0, lane);
+    else batch_update_cold_t<false, 3>(P, K0, KS0, K1, KS1, nl, w0, lane);
+  } else {
+    if (two) batch_update_cold_t<true, 4>(P, K0, KS0, K1, KS1, nl, w0, lane);
+    else batch_update_cold_t<false, 4>(P, K0, KS0, K1, KS1, nl, w0, lane);
   }
 }
 
 /* The whole scan of one filter.  ns: columns of the packed triangle that fit the shared-memory carve-up. */
 #ifdef EKFB_TIMING
-#define BT_DECL long long bt_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long bt0_ = clock64()
+#define BT_DECL long long bt_[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long bt0_ = clock64()
 #define BT_MARK(k) do { const long long n_ = clock64(); bt_[k] += n_ - bt0_; bt0_ = n_; } while (0)
 #define BT_RESET() bt0_ = clock64()
-#define BT_PRINT() do { if (blockIdx.x == 7 && (threadIdx.x == 0 || threadIdx.x == 32)) printf("k_batch_scan block 7 thread %d, cycles: load %lld predict %lld | per scan: A %lld, B(gate or cold pass) %lld, B-barrier %lld, C %lld (setup %lld, loads+correction %lld, gain %lld, stores %lld), C-barrier %lld | tail %lld\n", (int)threadIdx.x, bt_[0], bt_[1], bt_[2], bt_[3], bt_[4], bt_[5] + bt_[8] + bt_[9] + bt_[10] + bt_[11], bt_[8], bt_[9], bt_[10], bt_[11], bt_[6], bt_[7]); } while (0)
+#define BT_PRINT() do { if (blockIdx.x == 7 && (threadIdx.x == 0 || threadIdx.x == 32)) printf("k_batch_scan block 7 thread %d, cycles: load %lld predict %lld | per scan: A %lld, B(gate or cold pass) %lld, B-barrier %lld, C %lld (setup %lld, loads+correction %lld, gain %lld, stores %lld), C-barrier %lld | tail %lld | gate: pre-test %lld gather %lld gate_from_block %lld first-fit+publish %lld\n", (int)threadIdx.x, bt_[0], bt_[1], bt_[2], bt_[3] + bt_[12] + bt_[13] + bt_[14] + bt_[15], bt_[4], bt_[5] + bt_[8] + bt_[9] + bt_[10] + bt_[11], bt_[8], bt_[9], bt_[10], bt_[11], bt_[6], bt_[7], bt_[12], bt_[13], bt_[14], bt_[15]); } while (0)
 #else
 #define BT_DECL do { } while (0)
 #define BT_MARK(k) do { } while (0)
@@ -174,10 +197,13 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   const int kn = ON_CHIP ? ns : g.n;
   double2* const Ks = ON_CHIP ? reinterpret_cast<double2*>(braw + lay.K) : g.scratch + (size_t)blockIdx.x * 4 * g.n;
   double2* const KSs = ON_CHIP ? reinterpret_cast<double2*>(braw + lay.KS) : Ks + 2 * (size_t)g.n;
+  double* const zs = reinterpret_cast<double*>(braw + lay.zr);
+  double* const Rs = zs + 2 * m;
   int* const ext = reinterpret_cast<int*>(braw + lay.ext);
   unsigned char* const matched = braw + lay.matched;
   __shared__ unsigned long long s_bar;
-  __shared__ int s_best, s_sticky;
+  __shared__ int s_best, s_sticky, s_gw;
+  __shared__ int s_cand[32];                                 /* survivors of the pre-test, in index order */
   __shared__ double s_xpre[3];
   __shared__ Gate sG;
 
@@ -207,12 +233,22 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     if (on_chip) b_bulk_load(Psm, Pf, pbytes, &s_bar);
     b_bulk_load(ys, yf, ybytes, &s_bar);
     s_sticky = 0;
+    /* Which warp associates.  Warp w of every CTA issues from scheduler w of the SM; were the gate always on warp 0, one
+     * scheduler's fp64 pipe would carry the trigonometry and divisions of all four resident filters while the other three
+     * idle between cold passes.  The CTAs that start on an SM take the four warps in turn. */
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    s_gw = (int)(atomicAdd(&g.sm_turn[smid & 255u], 1u) & 3u);
   }
   for (int j = tid; j < g.cap; j += nt) matched[j] = 0;
+  /* the scan's lines travel to shared memory under the bulk copies: a gate then starts from a 29-cycle load instead of an
+   * L2 / HBM round trip at the head of every line's dependent chain */
+  for (int k = tid; k < 6 * m; k += nt) zs[k] = (k < 2 * m) ? z[k] : R[k - 2 * m];
   __syncthreads();
   b_mbar_wait(&s_bar, 0);
   BT_MARK(0);
 
+  const int gw = s_gw;
   /* ---- prediction, Robot.cpp:130-258 ---- */
   const double u0 = u[0], u2 = u[2];
   const double ang = add_rn(pose2, __ddiv_rn(u2, 2.0));
@@ -316,37 +352,57 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     BT_MARK(2);
     /* ---- phase B ---- */
     const bool fold = np == 2 || (np == 1 && !gating);
-    if (warp == 0 && gating) {
-      const double z0 = z[2 * i], z1 = z[2 * i + 1];
-      const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
+    if (warp == gw && gating) {
+      const double z0 = zs[2 * i], z1 = zs[2 * i + 1];
+      const double Rl[4] = {Rs[4 * i], Rs[4 * i + 1], Rs[4 * i + 2], Rs[4 * i + 3]};
       const double xp[3] = {s_xpre[0], s_xpre[1], s_xpre[2]};
       const double P22 = Ps[tri(2) + 2];
       int best = EKF_NO_MATCH;
-      for (int j0 = 0; j0 < L && best == EKF_NO_MATCH; j0 += 32) {    /* first fit: a match in this round ends the search */
-        const int j = j0 + lane;
-        bool keep = j < L && !matched[j];
-        if (keep && !g.full_gates) {
-          /* pre-test: v0 is the gate's own angle innovation (Robot.cpp:423-475, no trigonometry); S00 = H0 P H0' + R00
-           * with H0 = (0, 0, -1, .. 1 at a ..): d^2 = v' S^-1 v >= v0^2 / S00, so a landmark whose bound exceeds
-           * (2 gate)^2 -- twice the gate in d, far outside any rounding difference between the bound and the reference's
-           * LU expression -- cannot pass the reference's test either */
-          const int a = 3 + 2 * j;
-          const double* ca_ = Ps + tri(a);
-          double h0 = sub_rn(ys[a], xp[2]);
-          normalize_radian(h0);
-          double v0 = sub_rn(z0, h0);
-          const double two_pi = 2.0 * EKF_PI;
-          if (fabs(sub_rn(v0, two_pi)) < fabs(v0)) v0 = sub_rn(v0, two_pi);
-          else if (fabs(add_rn(v0, two_pi)) < fabs(v0)) v0 = add_rn(v0, two_pi);
-          const double S00 = (P22 - 2.0 * ca_[2]) + ca_[a] + Rl[0];
-          keep = !(S00 > 0.0) || !(v0 * v0 > gate2x4 * S00);
+      int j0 = 0;
+      while (j0 < L && best == EKF_NO_MATCH) {                        /* first fit: a match among these candidates ends the search */
+        /* rounds of 32 landmarks take the pre-test; their survivors, in index order, fill the lanes of ONE round of full
+         * gates (typically one or two survivors out of 50 landmarks: one trigonometry + LU chain per line, not one per
+         * 32 landmarks) */
+        int ncand = 0;
+        while (j0 < L) {
+          /* pre-test of two rounds of 32 landmarks at once, straight-line code (their loads and chains interleave).
+           * v is the angle innovation of Robot.cpp:423-475 as its representative of least magnitude, w - 2 pi rint(w / 2 pi)
+           * -- within rounding of, or smaller than, what the reference's wraps leave -- and S00 = H0 P H0' + R00 with
+           * H0 = (0, 0, -1, .. 1 at a ..): d^2 = v' S^-1 v >= v^2 / S00, so a landmark whose bound exceeds (2 gate)^2 --
+           * twice the gate in d, far outside any rounding difference between the bound and the reference's LU
+           * expression -- cannot pass the reference's test either */
+          bool keep[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = j0 + 32 * h + lane;
+            const bool live = j < L;
+            const int a = live ? 3 + 2 * j : 3;
+            const double* ca_ = Ps + tri(a);
+            const bool free_ = live && !matched[live ? j : 0];
+            const double w = sub_rn(z0, sub_rn(ys[a], xp[2]));
+            const double v = __fma_rn(-(2.0 * EKF_PI), rint(w * (1.0 / (2.0 * EKF_PI))), w);
+            const double S00 = (P22 - 2.0 * ca_[2]) + ca_[a] + Rl[0];
+            keep[h] = free_ && (g.full_gates || !(S00 > 0.0) || !(v * v > gate2x4 * S00));
+          }
+          bool full = false;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (full || j0 >= L) break;
+            const unsigned mask = __ballot_sync(0xffffffffu, keep[h]);
+            const int nk = __popc(mask);
+            if (ncand + nk > 32) { full = true; break; }              /* these survivors wait for the next round of full gates */
+            if (keep[h]) s_cand[ncand + __popc(mask & ((1u << lane) - 1u))] = j0 + lane;
+            ncand += nk;
+            j0 += 32;
+          }
+          if (full) break;
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        const int ncand = __popc(mask);
+        __syncwarp();
+        const int jj = lane < ncand ? s_cand[lane] : 0;
+        BT_MARK(12);
         int mine = EKF_NO_MATCH;
         Gate Gj;
         if (lane < ncand) {                                           /* the survivors, compacted onto the first lanes */
-          const int jj = j0 + (int)__fns(mask, 0, lane + 1);
           const int a = 3 + 2 * jj, bb = a + 1;
           const double* ca_ = Ps + tri(a);
           const double* cb_ = Ps + tri(bb);
@@ -356,20 +412,23 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
             Cm[r][3] = Cm[3][r] = ca_[r]; Cm[r][4] = Cm[4][r] = cb_[r];
           }
           Cm[3][3] = ca_[a]; Cm[3][4] = Cm[4][3] = cb_[a]; Cm[4][4] = cb_[bb];
+          BT_MARK(13);
           gate_from_block(Cm, ys[a], ys[bb], xp, z0, z1, Rl, Gj);
           if (Gj.singular) atomicOr(&s_sticky, EKF_STICKY_SINGULAR);
           else if (!gate_rejects_d2(Gj.d2, g.gate_d2max)) mine = jj;                   /* :489 */
+          BT_MARK(14);
         }
         best = __reduce_min_sync(0xffffffffu, mine);
         if (mine != EKF_NO_MATCH && mine == best) sG = Gj;            /* the winner publishes its gate record */
+        BT_MARK(15);
       }
       if (lane == 0) {
         s_best = best;
         if (best == EKF_NO_MATCH) { ext[ne] = i; if (jout) jout[i] = -1; }           /* :309 / :325 / :493 */
         else { matched[best] = 1; if (jout) jout[i] = best; }                       /* :501 */
       }
-    } else if (fold && (warp != 0 || !gating)) {
-      const int w0 = gating ? warp - 1 : warp, nw = gating ? nt / 32 - 1 : nt / 32;
+    } else if (fold && (warp != gw || !gating)) {
+      const int w0 = gating ? ((warp - gw - 1) & 3) : warp, nw = gating ? nt / 32 - 1 : nt / 32;
       const int s0 = (nmatch - np) & 1;                               /* the older pending match first */
       batch_update_cold(Ps, Ks + (size_t)s0 * kn, KSs + (size_t)s0 * kn, Ks + (size_t)(s0 ^ 1) * kn, KSs + (size_t)(s0 ^ 1) * kn,
                         np == 2, nl, w0, nw, lane);
@@ -432,7 +491,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     if (L >= g.cap) { if (tid == 0) s_sticky |= EKF_STICKY_CAPACITY; break; }      /* the reference overruns y[] here (Q4) */
     const int l = 3 + 2 * L;
     const int i = ext[e];
-    double alfa = z[2 * i], rr = z[2 * i + 1];
+    double alfa = zs[2 * i], rr = zs[2 * i + 1];
     rr = add_rn(rr, add_rn(mul_rn(ps0, cos(alfa)), mul_rn(ps1, sin(alfa))));          /* :792 (Q8) */
     alfa = add_rn(alfa, ps2);                                                       /* :793 */
     const double cw = cos(alfa), sw = sin(alfa);
@@ -452,7 +511,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
       c0[k] = r0; c1[k] = r1;
     }
     if (tid == 0) {
-      const double Rl[4] = {R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]};
+      const double Rl[4] = {Rs[4 * i], Rs[4 * i + 1], Rs[4 * i + 2], Rs[4 * i + 3]};
       const double Gx[2][3] = {{0.0, 0.0, 1.0}, {cw, sw, 0.0}};
       const double Gl[2][2] = {{1.0, 0.0}, {sub_rn(mul_rn(ys[1], cw), mul_rn(ys[0], sw)), 1.0}};   /* :797-798 */
       double an = alfa;
@@ -539,6 +598,7 @@ struct ekf_batch {
   cudaStream_t cstream;             /* input copies of the pipelined host path (overlap the previous step's kernel) */
   double* d_y; double* d_P; EkfBatchState* d_st;
   double2* d_scratch;               /* pending gains of filters running off chip: [B][4][n] */
+  unsigned* d_sm_turn;              /* [256] */
   int max_m;
   /* two staging slots: ekf_batch_scan uses slot 0; ekf_batch_submit / ekf_batch_collect alternate */
   double* d_in[2]; double* h_in[2];       /* [u (3B) | z (2 m B) | R (4 m B)] */
@@ -677,6 +737,9 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   CUB(cudaMalloc(&b->d_st, B * sizeof(EkfBatchState)));
   CUB(cudaMalloc(&b->d_scratch, B * 4 * (size_t)g.n * sizeof(double2)));
   g.scratch = b->d_scratch;
+  CUB(cudaMalloc(&b->d_sm_turn, 256 * sizeof(unsigned)));
+  CUB(cudaMemsetAsync(b->d_sm_turn, 0, 256 * sizeof(unsigned), b->stream));
+  g.sm_turn = b->d_sm_turn;
   CUB(cudaMallocHost(&b->h_st, B * sizeof(EkfBatchState)));
   CUB(cudaMallocHost(&b->h_P, (size_t)g.pstride * sizeof(double)));
   CUB(cudaMemsetAsync(b->d_y, 0, B * (size_t)g.ystride * sizeof(double), b->stream));
@@ -696,7 +759,7 @@ int ekf_batch_destroy(ekf_batch* b) {
   cudaSetDevice(b->cfg.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   if (b->cstream) cudaStreamSynchronize(b->cstream);
-  cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_scratch);
+  cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_scratch); cudaFree(b->d_sm_turn);
   for (int k = 0; k < 2; ++k) {
     cudaFree(b->d_in[k]); cudaFree(b->d_jout[k]); cudaFreeHost(b->h_in[k]); cudaFreeHost(b->h_jout[k]); cudaFreeHost(b->h_sts[k]);
     if (b->ev_in[k]) cudaEventDestroy(b->ev_in[k]);
