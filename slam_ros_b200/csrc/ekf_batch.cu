@@ -351,7 +351,11 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     }
     BT_MARK(2);
     /* ---- phase B ---- */
+#ifdef EKFB_FOLD_EACH
+    const bool fold = np >= 1;                                 /* A/B: one term per pass, a pass beside every gate (measured: 3 542 vs 3 714 batch steps/s) */
+#else
     const bool fold = np == 2 || (np == 1 && !gating);
+#endif
     if (warp == gw && gating) {
       const double z0 = zs[2 * i], z1 = zs[2 * i + 1];
       const double Rl[4] = {Rs[4 * i], Rs[4 * i + 1], Rs[4 * i + 2], Rs[4 * i + 3]};
