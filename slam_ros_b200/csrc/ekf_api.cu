@@ -84,6 +84,8 @@ struct ekf_ctx {
   int have_tmap8;
   CUtensorMap tmapK[2];        /* [0]: K bands (box = tile columns x 8 slots), [1]: K S bands (box = tile rows x 8 slots) */
   int rd, par, group;
+  int tabpar;                  /* per-line table set of the next overlapped scan */
+  int chunk_lines, chunk_above;/* overlapped scans of more than chunk_above lines run as chunks of chunk_lines (EKF_CHUNK, EKF_CHUNK_ABOVE; 0 = never) */
   int slots;                   /* rows of Kp / KSp: max(max_batch, 2 * group) */
   int pg_valid, pg_slot0;
   EkfScanView* d_view;        /* [2] */
@@ -349,48 +351,67 @@ int line_event(ekf_ctx* ctx) {
  * scan's line loop already executes.  Buffers: sweep(s) reads X and writes X^1; the next line loop
  * reads X (complete once sweep(s-1) is done) plus this scan's pending terms. */
 int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, const double* d_z, const double* d_R) {
-  const int par = ctx->par;
-  if (ctx->evF_used[par]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evF[par], 0));   /* sweep(s-2): slots, tables, X complete */
-  use_tables(ctx, par);
-  const int slot0 = par * ctx->group;
-  EkfBuffers b = ctx->b;
-  b.P = ctx->Pbuf[ctx->rd];
-  { int rc = line_event(ctx); if (rc) return rc; }
-  CU(ekf_launch_predict(ctx->g, b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
-  /* The line loop runs as EKF_LINE_SMS cooperative CTAs on the SMs the in-flight sweep leaves free (its
-   * persistent grid is num_sms - EKF_LINE_SMS): no register / FP64-issue sharing with the sweep. */
-  CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, 0, m, EKF_LINE_SMS, 1, slot0, ctx->pg_slot0,
-                           ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream));
-  const int tgt = ctx->pg_valid ? (ctx->rd ^ 1) : ctx->rd;      /* source of this scan's sweep */
-  EkfBuffers bt = ctx->b;
-  bt.P = ctx->Pbuf[tgt];
-  CU(ekf_launch_end_scan(ctx->g, bt, d_z, d_R, m, ctx->L_ub, slot0, &ctx->d_view[par], ctx->stream));
-  ctx->launches += 5;
-  { int rc = line_event(ctx); if (rc) return rc; }
-  CU(cudaEventRecord(ctx->evE, ctx->stream));
-  CU(cudaStreamWaitEvent(ctx->wstream, ctx->evE, 0));
-  cudaEvent_t e0 = 0, e1 = 0;
-  if (ctx->prof) {
-    if (ctx->ev_used + 2 > ctx->ev.size())
-      for (int i = 0; i < 64; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e); }
-    e0 = ctx->ev[ctx->ev_used]; e1 = ctx->ev[ctx->ev_used + 1];
-    CU(cudaEventRecord(e0, ctx->wstream));
-  }
+  /* Scans of more than kChunkAbove lines go through the pipeline as CHUNKS of kChunkLines: a chunk's sweep (16 pending terms,
+   * one tensor-core pass) runs while the next chunk's line loop executes, exactly as a scan's sweep runs under the next
+   * scan's line loop.  A line then corrects its column reads against at most 2 x 16 pending terms instead of up to 128, and
+   * the sweeps of a 64-line scan hide under its own line loop.  Prediction runs before the first chunk, the end-of-scan
+   * kernels after the last; in between k_chunk_mark snapshots the finished chunk for its sweep and restarts the pending
+   * list.  Same operations per element in the same order as one line loop + one sweep: identical bits. */
+  const int chunk = (ctx->chunk_lines > 0 && m > ctx->chunk_above && ctx->g.world == 1) ? ctx->chunk_lines : m;
+  use_tables(ctx, ctx->tabpar);
+  ctx->tabpar ^= 1;
   long long lub = (long long)ctx->L_ub + m;
   const int L_after_ub = (int)(lub > ctx->g.cap ? ctx->g.cap : lub);
-  CU(ekf_launch_sweep_tma(ctx->g, bt, &ctx->tmap2[tgt], ctx->have_tmap8 ? &ctx->tmap8[tgt] : 0, &ctx->tmapK[0], &ctx->tmapK[1], ctx->Pbuf[tgt ^ 1], slot0, &ctx->d_view[par], ctx->d_counters + 16,
-                          ctx->sweep_shape, m, L_after_ub, ctx->num_sms - EKF_LINE_SMS, ctx->wstream,
-                          &ctx->tmap2[tgt ^ 1], ctx->have_tmap8 ? &ctx->tmap8[tgt ^ 1] : 0));
-  { const int per_pass = ekf_sweep_terms_per_pass(ctx->sweep_shape, m); ctx->launches += (m + per_pass - 1) / per_pass; }
-  if (ctx->prof) {
-    CU(cudaEventRecord(e1, ctx->wstream));
-    ctx->ev_used += 2;
-    ctx->ev_bytes.push_back((double)m);
+  { int rc = line_event(ctx); if (rc) return rc; }
+  for (int line0 = 0; line0 < m; line0 += chunk) {
+    const int line1 = line0 + chunk < m ? line0 + chunk : m;
+    const bool first = line0 == 0, last = line1 == m;
+    const int par = ctx->par;
+    if (ctx->evF_used[par]) CU(cudaStreamWaitEvent(ctx->stream, ctx->evF[par], 0));   /* the sweep two back: slots free, X complete */
+    const int slot0 = par * ctx->group;
+    EkfBuffers b = ctx->b;
+    b.P = ctx->Pbuf[ctx->rd];
+    if (first) { CU(ekf_launch_predict(ctx->g, b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream)); ctx->launches++; }
+    /* The line loop runs as EKF_LINE_SMS cooperative CTAs on the SMs the in-flight sweep leaves free (its
+     * persistent grid is num_sms - EKF_LINE_SMS): no register / FP64-issue sharing with the sweep. */
+    CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, line0, line1, EKF_LINE_SMS, 1, slot0, ctx->pg_slot0,
+                             ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream));
+    ctx->launches++;
+    const int tgt = ctx->pg_valid ? (ctx->rd ^ 1) : ctx->rd;      /* source of this chunk's sweep */
+    EkfBuffers bt = ctx->b;
+    bt.P = ctx->Pbuf[tgt];
+    if (last) {
+      CU(ekf_launch_end_scan(ctx->g, bt, d_z, d_R, m, ctx->L_ub, slot0, &ctx->d_view[par], ctx->stream));
+      ctx->launches += 3;
+      int rc = line_event(ctx); if (rc) return rc;
+    } else {
+      CU(ekf_launch_chunk_mark(ctx->b, line1, &ctx->d_view[par], ctx->stream));
+      ctx->launches++;
+    }
+    CU(cudaEventRecord(ctx->evE, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->wstream, ctx->evE, 0));
+    cudaEvent_t e0 = 0, e1 = 0;
+    if (ctx->prof) {
+      if (ctx->ev_used + 2 > ctx->ev.size())
+        for (int i = 0; i < 64; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->ev.push_back(e); }
+      e0 = ctx->ev[ctx->ev_used]; e1 = ctx->ev[ctx->ev_used + 1];
+      CU(cudaEventRecord(e0, ctx->wstream));
+    }
+    const int nterms = line1 - line0;
+    CU(ekf_launch_sweep_tma(ctx->g, bt, &ctx->tmap2[tgt], ctx->have_tmap8 ? &ctx->tmap8[tgt] : 0, &ctx->tmapK[0], &ctx->tmapK[1], ctx->Pbuf[tgt ^ 1], slot0, &ctx->d_view[par], ctx->d_counters + 16,
+                            ctx->sweep_shape, nterms, L_after_ub, ctx->num_sms - EKF_LINE_SMS, ctx->wstream,
+                            &ctx->tmap2[tgt ^ 1], ctx->have_tmap8 ? &ctx->tmap8[tgt ^ 1] : 0));
+    { const int per_pass = ekf_sweep_terms_per_pass(ctx->sweep_shape, nterms); ctx->launches += (nterms + per_pass - 1) / per_pass; }
+    if (ctx->prof) {
+      CU(cudaEventRecord(e1, ctx->wstream));
+      ctx->ev_used += 2;
+      ctx->ev_bytes.push_back((double)nterms);
+    }
+    CU(cudaEventRecord(ctx->evF[par], ctx->wstream));
+    ctx->evF_used[par] = 1;
+    ctx->rd = tgt; ctx->pg_valid = 1; ctx->pg_slot0 = slot0;
+    ctx->par ^= 1;
   }
-  CU(cudaEventRecord(ctx->evF[par], ctx->wstream));
-  ctx->evF_used[par] = 1;
-  ctx->rd = tgt; ctx->pg_valid = 1; ctx->pg_slot0 = slot0;
-  ctx->par ^= 1;
   ctx->L_ub = L_after_ub;
   ctx->b.P = ctx->Pbuf[ctx->rd];
   return EKF_OK;
@@ -401,7 +422,8 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
   if (ctx->overlap) {
     /* small maps: the sweep is a few microseconds, nothing to hide -- the in-place path with the 16-CTA
      * cluster line loop is faster there (measured crossover: a few thousand state entries) */
-    if (m >= 1 && m <= ctx->group && ctx->L_ub > 0 && 3 + 2 * ctx->L_ub >= kOverlapMinN &&
+    const bool chunked = ctx->chunk_lines > 0 && m > ctx->chunk_above && ctx->g.world == 1;
+    if (m >= 1 && (m <= ctx->group || chunked) && ctx->L_ub > 0 && 3 + 2 * ctx->L_ub >= kOverlapMinN &&
         (ctx->g.world == 1 || ctx->peers_ok))     /* a row-sharded filter overlaps only on the fused exchange */
       return enqueue_scan_overlapped(ctx, d_u, d_x_t0, m, d_z, d_R);
     int rc = drain(ctx);
@@ -505,7 +527,9 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->L_ub = 0; ctx->pend_ub = 0; ctx->scan_open = 0; ctx->cursor = 0;
   ctx->prof = 0; ctx->ev_used = 0; ctx->lev_used = 0; ctx->launches = 0; ctx->comm = 0; ctx->t0 = 0; ctx->t1 = 0;
   ctx->d_stage = 0; ctx->stage_elems = 0; ctx->d_partials = 0; ctx->d_out3 = 0;
-  ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8;
+  ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8; ctx->tabpar = 0;
+  { const char* e = getenv("EKF_CHUNK"); ctx->chunk_lines = e ? atoi(e) : 16; if (ctx->chunk_lines < 0) ctx->chunk_lines = 0; }
+  { const char* e = getenv("EKF_CHUNK_ABOVE"); ctx->chunk_above = e ? atoi(e) : 32; if (ctx->chunk_above < 1) ctx->chunk_above = 1; }
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
   ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);
   ctx->xchg = 0; ctx->poisoned = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
@@ -551,6 +575,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9 && ctx->sweep_shape != 10 && ctx->sweep_shape != 11) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
   { const int cap = 2 * ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
+  if (ctx->chunk_lines > ctx->group) ctx->chunk_lines = ctx->group;          /* a chunk's terms live in one half of the slot ring */
   { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap2[0]); if (rc) return rc; }
   ctx->have_tmap8 = (ctx->sweep_shape == 0 || ctx->sweep_shape == 10);
   if (ctx->have_tmap8) { int rc = make_tensor_map(ctx, p_rows, ctx->Pbuf[0], &ctx->tmap8[0], 10); if (rc) return rc; }

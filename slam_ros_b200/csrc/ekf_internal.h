@@ -100,6 +100,7 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
                                   int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
                                   const int* prev_cnt_ptr, const EkfPeers* peers, int L_ub, cudaStream_t s);
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s);
+cudaError_t ekf_launch_chunk_mark(const EkfBuffers& b, int next_line, EkfScanView* view, cudaStream_t s);
 cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, cudaStream_t s);
 /* np_ptr: device int holding the number of pending terms (NULL = st->np); np_ub: host upper bound (selects the template) */
 cudaError_t ekf_launch_sweep(const EkfGeom& g, const EkfBuffers& b, const int* np_ptr, int np_ub, int L_ub,

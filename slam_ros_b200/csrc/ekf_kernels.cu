@@ -925,6 +925,16 @@ __global__ void k_flush_done(EkfBuffers b, int next_line) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { b.st->pbase = b.pidx[next_line]; b.st->np = 0; }
 }
 
+/* between two chunks of an overlapped scan (lines [.., next_line) done): the snapshot the finished chunk's sweep will
+ * need, then the pending list restarts empty for the next chunk */
+__global__ void k_chunk_mark(EkfBuffers b, int next_line, EkfScanView* view) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    EkfDevState* st = b.st;
+    view->cnt = b.pidx[next_line] - st->pbase; view->L = st->L;
+    st->pbase = b.pidx[next_line]; st->np = 0;
+  }
+}
+
 /* the map is empty (Robot.cpp:308-310): every line of the scan is queued */
 __global__ void k_queue_all(EkfGeom g, EkfBuffers b, int m) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1759,6 +1769,10 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
 }
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
   k_flush_done<<<1, 32, 0, s>>>(b, next_line);
+  return cudaGetLastError();
+}
+cudaError_t ekf_launch_chunk_mark(const EkfBuffers& b, int next_line, EkfScanView* view, cudaStream_t s) {
+  k_chunk_mark<<<1, 32, 0, s>>>(b, next_line, view);
   return cudaGetLastError();
 }
 cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, cudaStream_t s) {

@@ -359,16 +359,22 @@ def test_batched_multi_line_updates(libekf, oracle_cls, m):
     assert so.stats()["matches"] > 0.8 * steps * m
 
 
-@pytest.mark.parametrize("m", [16, 32])
+@pytest.mark.parametrize("m", [16, 32, 40, 64])
 def test_overlapped_pipeline_with_large_line_groups(libekf, oracle_cls, m):
     """m = 16 / 32 lines per scan on a map large enough (n = 6203) for the overlapped path: the scan's 16 / 32
     pending terms are folded by ONE out-of-place sweep pass (16- / 32-term template) while the next scan's line loop
-    corrects its column reads with up to 2m pending terms.  Checked against the oracle and, bit for bit, against
-    the non-overlapped in-place path."""
+    corrects its column reads with up to 2m pending terms.  m = 40 / 64: the scan goes through the pipeline as chunks
+    of 16 lines (16 + 16 + 8 / 4 x 16), each chunk's sweep under the next chunk's line loop; two of those scans carry
+    lines that match nothing, so the map grows at the end of a chunked scan.  Checked against the oracle and, bit for
+    bit, against the non-overlapped in-place path."""
     from slam_ros_b200 import EkfFilter
     from slam_ros_b200.ekf import EKF_FLAG_NO_OVERLAP
     N, steps = 3100, 7
     scn = sc.map_scenario(N, steps, m=m, seed=70 + m, stride=m + 3)
+    if m > 32:
+        for s, lines in ((2, (5, 20, 37)), (4, (0, 17, m - 1))):
+            for i in lines:
+                scn["z"][s][i, 1] += 3.0 + 0.1 * i
     f, so = seed_pair(N, N + 128, oracle_cls, scn)
     so._lib.ekfo_set_threads(so._h, 0)
     g = EkfFilter(capacity_lines=N + 128, flags=EKF_FLAG_NO_OVERLAP)
@@ -385,6 +391,8 @@ def test_overlapped_pipeline_with_large_line_groups(libekf, oracle_cls, m):
     yf, Pf, Lf = f.download_live()
     yg, Pg, Lg = g.download_live()
     assert Lf == Lg and np.array_equal(yf, yg) and np.array_equal(Pf, Pg)
+    if m > 32:
+        assert Lf == N + 6
 
 
 def test_empty_and_ragged_scans(libekf, oracle_cls):
