@@ -1041,6 +1041,7 @@ struct SweepShared {
   SweepStage<TR, TC, C> stage[STAGES];
   unsigned long long full[STAGES][2];  /* [stage][consumer group]: a group only ever waits on its own barrier (see k_sweep_quad) */
   unsigned long long empty[STAGES];
+  unsigned long long emptyP[STAGES];   /* k_sweep_dmma: the stage's P tile alone is free again (its accumulators are in registers) */
   int meta[STAGES][4];                /* first local row, first global row, first column, - */
 };
 
@@ -1154,6 +1155,80 @@ __device__ __forceinline__ void sweep_producer(SweepShared<TR, TC, STAGES, C>& s
     mbar_wait(&sh.empty[s], ph ^ 1);
     sh.meta[s][3] = 0;
     mbar_arrive(&sh.full[s][sentinels > 1 ? (it & 1) : 0]);
+  }
+}
+
+/* The producer of the tensor-core sweep.  Same tile order and ring as sweep_producer, but a stage is refilled in TWO steps:
+ * its P tile as soon as the consuming group has the accumulators in registers (barrier emptyP: right at the start of the
+ * group's work on the previous occupant), its K / K S bands when that group is done with them (barrier empty).  The P tile
+ * is the part that comes from HBM; with the two-stage ring of the 32-term pass a stage used to be refilled only after its
+ * group had finished, so every tile's HBM round trip was exposed (tensor pipe 70 % active).  The producer runs one tile
+ * ahead: P of tile it + 1 is requested before the bands of tile it. */
+template <int STAGES, int C>
+__device__ __forceinline__ void sweep_producer_split(SweepShared<64, 64, STAGES, C>& sh, const EkfGeom& g,
+                                                     const CUtensorMap& tmapP, const CUtensorMap& tmapK, const CUtensorMap& tmapKS,
+                                                     int c0, int slot0, int np, int nl, unsigned long long* tile_counter) {
+  constexpr int TR = 64, TC = 64;
+  const int T64 = (nl + EKF_TILE - 1) / EKF_TILE;
+  const int Tc = (nl + TC - 1) / TC;
+  const int nbands = (np + 7) / 8;
+  const unsigned long long pol = l2_policy_evict_first();
+  const unsigned bytes = TR * TC * sizeof(double) + (unsigned)(8 * nbands) * (TC + TR) * sizeof(double2);
+  int k = 0, gb = g.rank;
+  long long base = 0;
+  int cb0 = (EKF_TILE * gb) / TC;
+  long long cnt = (gb < T64) ? (long long)(Tc - cb0) : 0;
+  long long idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : (long long)blockIdx.x;
+  /* decode of the next tile this CTA draws (indices increase: incremental) */
+  auto next_tile = [&](int& lrow0, int& grow0, int& col0) -> bool {
+    while (gb < T64 && idx >= base + cnt) {
+      base += cnt; ++k; gb += g.world;
+      cb0 = (EKF_TILE * gb) / TC;
+      cnt = (gb < T64) ? (long long)(Tc - cb0) : 0;
+    }
+    if (gb >= T64) return false;
+    const int rem = (int)(idx - base);
+    lrow0 = k * EKF_TILE; grow0 = gb * EKF_TILE; col0 = (cb0 + rem) * TC;
+    idx = tile_counter ? (long long)atomicAdd(tile_counter, 1ull) : idx + gridDim.x;
+    return true;
+  };
+  auto issue_p = [&](int it, int lrow0, int grow0, int col0) {
+    const int s = it % STAGES;
+    const unsigned ph = (it / STAGES) & 1;
+    mbar_wait(&sh.emptyP[s], ph ^ 1);
+    sh.meta[s][0] = lrow0; sh.meta[s][1] = grow0; sh.meta[s][2] = col0; sh.meta[s][3] = 1;
+    unsigned long long* fullb = &sh.full[s][it & 1];
+    mbar_expect_tx(fullb, bytes);                      /* the whole stage: the phase completes only once the bands have landed too */
+#pragma unroll
+    for (int bx = 0; bx < TC / 8; ++bx) tma_load_tile_hint(sh.stage[s].P + bx * TR * 8, &tmapP, col0 + 8 * bx, lrow0, fullb, pol);
+  };
+  auto issue_bands = [&](int it, int grow0, int col0) {
+    const int s = it % STAGES;
+    const unsigned ph = (it / STAGES) & 1;
+    mbar_wait(&sh.empty[s], ph ^ 1);
+    unsigned long long* fullb = &sh.full[s][it & 1];
+    for (int bi = 0; bi < nbands; ++bi) {
+      tma_load_tile(sh.stage[s].K[8 * bi], &tmapK, 2 * col0, slot0 + c0 + 8 * bi, fullb);
+      tma_load_tile(sh.stage[s].KS[8 * bi], &tmapKS, 2 * grow0, slot0 + c0 + 8 * bi, fullb);
+    }
+  };
+  int lr = 0, gr = 0, cc = 0, it = 0;
+  bool have = next_tile(lr, gr, cc);
+  if (have) issue_p(0, lr, gr, cc);
+  while (have) {
+    int lr2 = 0, gr2 = 0, cc2 = 0;
+    const bool have2 = next_tile(lr2, gr2, cc2);
+    if (have2) issue_p(it + 1, lr2, gr2, cc2);
+    issue_bands(it, gr, cc);
+    lr = lr2; gr = gr2; cc = cc2; have = have2; ++it;
+  }
+  for (int e = 0; e < 2; ++e, ++it) {                   /* one sentinel per consumer group */
+    const int s = it % STAGES;
+    const unsigned ph = (it / STAGES) & 1;
+    mbar_wait(&sh.emptyP[s], ph ^ 1);
+    mbar_wait(&sh.empty[s], ph ^ 1);
+    sh.meta[s][3] = 0;
+    mbar_arrive(&sh.full[s][it & 1]);
   }
 }
 
@@ -1353,7 +1428,7 @@ k_sweep_quad(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-template <int STAGES, int C>
+template <int STAGES, int C, bool SPLIT>
 __global__ void __launch_bounds__(9 * 32, 1)
 k_sweep_dmma(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP, const __grid_constant__ CUtensorMap tmapK,
              const __grid_constant__ CUtensorMap tmapKS, double* __restrict__ dst, int c0,
@@ -1368,14 +1443,21 @@ k_sweep_dmma(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
   const int nl = 3 + 2 * (view ? view->L : b.st->L);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&sh.full[s][0], 1); mbar_init(&sh.full[s][1], 1); mbar_init(&sh.empty[s], CW / 2); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sh.full[s][0], 1); mbar_init(&sh.full[s][1], 1); mbar_init(&sh.empty[s], CW / 2); mbar_init(&sh.emptyP[s], CW / 2);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (warp == CW) {
-    if (lane == 0) sweep_producer<TR, TC, STAGES, C, true>(sh, g, b, tmapP, tmapK, tmapKS, c0, slot0, np, nl, tile_counter, 2);
+    if (lane == 0) {
+      /* the split refill needs the band copies (more than 4 terms: always the case where this kernel is selected) */
+      if (SPLIT && np > 4) sweep_producer_split<STAGES, C>(sh, g, tmapP, tmapK, tmapKS, c0, slot0, np, nl, tile_counter);
+      else sweep_producer<TR, TC, STAGES, C, true>(sh, g, b, tmapP, tmapK, tmapKS, c0, slot0, np, nl, tile_counter, 2);
+    }
     return;
   }
+  const bool split = SPLIT && np > 4;
   /* ---------------- consumers: 2 groups x 4 warps, a warp = rows 16 (warp & 3) .. + 15 of the tile ---------------- */
   const int grp = warp >> 2;
   const int gq = lane >> 2, tq = lane & 3;                   /* fragment coordinates of this lane */
@@ -1395,6 +1477,10 @@ k_sweep_dmma(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb)
         acc[mb][nb] = *reinterpret_cast<const double2*>(&st.P[(nb * TR + row0 + 8 * mb) * 8 + 2 * tq]);
+    if (split) {                                               /* the P tile may be refilled: its HBM round trip runs under the MMAs */
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.emptyP[s]);
+    }
     const double* KSw = reinterpret_cast<const double*>(&st.KS[0][0]);
     const double* Kw = reinterpret_cast<const double*>(&st.K[0][0]);
 #pragma unroll 2
@@ -1861,10 +1947,15 @@ static cudaError_t launch_sweep_dmma(const EkfGeom& g, const EkfBuffers& b, cons
                                      const CUtensorMap* m_dst = 0) {
   const size_t smem = sizeof(SweepShared<64, 64, STAGES, C>) + 1024;
   static bool attr_set[64] = {false};
+  /* EKF_DMMA_SPLIT=0: the stage is refilled in one step (A/B against the split refill) */
+  static int split = -1;
+  if (split < 0) { const char* e = getenv("EKF_DMMA_SPLIT"); split = (e && atoi(e) == 0) ? 0 : 1; }
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep_dmma<STAGES, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_dmma<STAGES, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sweep_dmma<STAGES, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -1875,7 +1966,8 @@ static cudaError_t launch_sweep_dmma(const EkfGeom& g, const EkfBuffers& b, cons
   for (int c0 = 0; c0 < np_ub; c0 += C) {
     EkfBuffers bb = b;
     if (c0 > 0 && dst != b.P) { bb.P = dst; m = m_dst; }
-    k_sweep_dmma<STAGES, C><<<grid, 9 * 32, smem, s>>>(g, bb, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
+    if (split) k_sweep_dmma<STAGES, C, true><<<grid, 9 * 32, smem, s>>>(g, bb, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
+    else k_sweep_dmma<STAGES, C, false><<<grid, 9 * 32, smem, s>>>(g, bb, *m, *mK, *mKS, dst, c0, slot0, view, counters ? counters + c0 / C : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
