@@ -85,6 +85,7 @@ struct ekf_ctx {
   CUtensorMap tmapK[2];        /* [0]: K bands (box = tile columns x 8 slots), [1]: K S bands (box = tile rows x 8 slots) */
   int rd, par, group;
   int tabpar;                  /* per-line table set of the next overlapped scan */
+  void* arena; size_t arena_bytes;   /* y | top | diag | gates | matched | colA,colB | Kp | KSp (one allocation: one L2 window) */
   int chunk_lines, chunk_above;/* overlapped scans of more than chunk_above lines run as chunks of chunk_lines (EKF_CHUNK, EKF_CHUNK_ABOVE; 0 = never) */
   int slots;                   /* rows of Kp / KSp: max(max_batch, 2 * group) */
   int pg_valid, pg_slot0;
@@ -512,6 +513,30 @@ int enable_overlap(ekf_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->rd = 0; ctx->par = 0; ctx->pg_valid = 0;
   ctx->overlap = 1;
+  /* L2 residency of the line loop's working set while sweeps stream the covariance through the cache (EKF_L2_PERSIST=0: off) */
+  { const char* e = getenv("EKF_L2_PERSIST");
+    const int mode = e ? atoi(e) : 0;
+    if (mode >= 1) {
+      int max_persist = 0, max_win = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->cfg.device);
+      cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->cfg.device);
+      size_t win = ctx->arena_bytes < (size_t)max_win ? ctx->arena_bytes : (size_t)max_win;
+      size_t persist = win < (size_t)max_persist ? win : (size_t)max_persist;
+      if (mode == 2) { win = (size_t)((char*)ctx->b.Kp - (char*)ctx->arena); persist = win; }        /* the small arrays only */
+      if (mode >= 3) { persist = (size_t)mode << 20; if (persist > (size_t)max_persist) persist = max_persist; }   /* mode = MB set aside */
+      if (win > 0 && persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.base_ptr = ctx->arena;
+        av.accessPolicyWindow.num_bytes = win;
+        av.accessPolicyWindow.hitRatio = (float)((double)persist / (double)win);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
+        if (getenv("EKF_VERBOSE")) fprintf(stderr, "libekfcuda: L2 window %.1f MB of arena %.1f MB, persisting %.1f MB (device max %.1f MB, window max %.1f MB)\n",
+                                           win / 1e6, ctx->arena_bytes / 1e6, persist / 1e6, max_persist / 1e6, max_win / 1e6);
+      } else (void)cudaGetLastError();
+    } }
   return EKF_OK;
 }
 
@@ -532,7 +557,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   { const char* e = getenv("EKF_CHUNK_ABOVE"); ctx->chunk_above = e ? atoi(e) : 32; if (ctx->chunk_above < 1) ctx->chunk_above = 1; }
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
   ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);
-  ctx->xchg = 0; ctx->poisoned = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
+  ctx->arena = 0; ctx->arena_bytes = 0; ctx->xchg = 0; ctx->poisoned = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
   *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -551,9 +576,6 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   const size_t ld = g.ld;
   const size_t p_rows = (size_t)ekf_local_tile_rows(g) * EKF_TILE;
   CU(cudaMalloc(&ctx->b.st, sizeof(EkfDevState)));
-  CU(cudaMalloc(&ctx->b.y, ld * sizeof(double)));
-  CU(cudaMalloc(&ctx->b.top, 3 * ld * sizeof(double)));
-  CU(cudaMalloc(&ctx->b.diag, 4 * (size_t)g.cap * sizeof(double)));
   CU(cudaMalloc(&ctx->b.P, p_rows * ld * sizeof(double)));
   ctx->Pbuf[0] = ctx->b.P; ctx->Pbuf[1] = 0;
   ctx->overlap = 0;
@@ -565,12 +587,25 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   CU(cudaMalloc(&ctx->d_counters, 32 * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_view, 2 * sizeof(EkfScanView)));
   CU(cudaMemsetAsync(ctx->d_view, 0, 2 * sizeof(EkfScanView), ctx->stream));
-  CU(cudaMalloc(&ctx->b.matched, (size_t)g.cap * sizeof(int)));
-  CU(cudaMalloc(&ctx->b.Kp, (size_t)ctx->slots * ld * sizeof(double2)));
-  CU(cudaMalloc(&ctx->b.KSp, (size_t)ctx->slots * ld * sizeof(double2)));
-  CU(cudaMalloc(&ctx->b.gates, 24 * (size_t)g.cap * sizeof(double)));     /* GATE_REC doubles per landmark */
-  CU(cudaMalloc(&ctx->b.colA, 2 * ld * sizeof(double)));
-  ctx->b.colB = ctx->b.colA + ld;
+  {
+    /* Everything the line loop reads and writes -- the hot state, the gate records, the pending lists -- lives in ONE
+     * allocation, so that one L2 access-policy window can cover it (enable_overlap): beside a sweep that streams 6.4 GB
+     * through the L2 per pass, these few MB are what every dependent round trip of a line waits for. */
+    const size_t al = 256;
+    auto up = [&](size_t x) { return (x + al - 1) / al * al; };
+    const size_t o_y = 0, o_top = o_y + up(ld * sizeof(double)), o_diag = o_top + up(3 * ld * sizeof(double)),
+                 o_gates = o_diag + up(4 * (size_t)g.cap * sizeof(double)), o_matched = o_gates + up(24 * (size_t)g.cap * sizeof(double)),
+                 o_col = o_matched + up((size_t)g.cap * sizeof(int)), o_kp = o_col + up(2 * ld * sizeof(double)),
+                 o_ksp = o_kp + up((size_t)ctx->slots * ld * sizeof(double2)), total = o_ksp + up((size_t)ctx->slots * ld * sizeof(double2));
+    CU(cudaMalloc(&ctx->arena, total));
+    ctx->arena_bytes = total;
+    char* a = (char*)ctx->arena;
+    ctx->b.y = (double*)(a + o_y); ctx->b.top = (double*)(a + o_top); ctx->b.diag = (double*)(a + o_diag);
+    ctx->b.gates = (double*)(a + o_gates);                                  /* GATE_REC doubles per landmark */
+    ctx->b.matched = (int*)(a + o_matched);
+    ctx->b.colA = (double*)(a + o_col); ctx->b.colB = ctx->b.colA + ld;
+    ctx->b.Kp = (double2*)(a + o_kp); ctx->b.KSp = (double2*)(a + o_ksp);
+  }
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9 && ctx->sweep_shape != 10 && ctx->sweep_shape != 11) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
@@ -737,13 +772,12 @@ int ekf_destroy(ekf_ctx* ctx) {
   for (int p = 0; p < 8; ++p) if (ctx->peer_map[p]) cudaIpcCloseMemHandle(ctx->peer_map[p]);
   cudaFree(ctx->xchg);
   free_line_tables(ctx);
-  cudaFree(ctx->b.st); cudaFree(ctx->b.y); cudaFree(ctx->b.top); cudaFree(ctx->b.diag); cudaFree(ctx->Pbuf[0]); cudaFree(ctx->Pbuf[1]);
+  cudaFree(ctx->b.st); cudaFree(ctx->arena); cudaFree(ctx->Pbuf[0]); cudaFree(ctx->Pbuf[1]);
   cudaFree(ctx->d_view); cudaFree(ctx->d_counters);
   if (ctx->evE) cudaEventDestroy(ctx->evE);
   if (ctx->evF[0]) cudaEventDestroy(ctx->evF[0]);
   if (ctx->evF[1]) cudaEventDestroy(ctx->evF[1]);
   if (ctx->wstream) cudaStreamDestroy(ctx->wstream);
-  cudaFree(ctx->b.matched); cudaFree(ctx->b.Kp); cudaFree(ctx->b.KSp); cudaFree(ctx->b.colA); cudaFree(ctx->b.gates);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_partials); cudaFree(ctx->d_out3);
   cudaFreeHost(ctx->h_st);
   for (size_t i = 0; i < ctx->ev.size(); ++i) cudaEventDestroy(ctx->ev[i]);

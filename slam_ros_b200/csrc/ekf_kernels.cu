@@ -1831,6 +1831,12 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
       return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, false>, dim3(ctas), dim3(512), args, 0, s);
     void* args2[] = {(void*)&g, (void*)&b, (void*)&d_z, (void*)&d_R, (void*)&line0, (void*)&line1, (void*)&own_slot0,
                      (void*)&prev_slot0, (void*)&prev_cnt_ptr};
+    /* 256-thread CTAs (EKF_LINE_THREADS=256, twice the SMs for the same map): up to 255 registers per thread -- none of the
+     * line loop's state spills */
+    static int lt = -1;
+    if (lt < 0) { const char* e = getenv("EKF_LINE_THREADS"); lt = e ? atoi(e) : 0; }
+    if (lt == 256 && L_ub <= ctas * 256)
+      return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<256, true, true>, dim3(ctas), dim3(256), args2, 0, s);
     /* at most one landmark per thread (host-side bound): the form that keeps the hot entries in registers */
     if (L_ub <= ctas * 512) return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<512, true, true>, dim3(ctas), dim3(512), args2, 0, s);
     return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<512, true, false>, dim3(ctas), dim3(512), args2, 0, s);
@@ -2010,6 +2016,17 @@ cudaError_t ekf_launch_sweep_tma(const EkfGeom& g, const EkfBuffers& b, const vo
   if (shape == 11) shape = 0;
   else if (shape == 0 && np_ub > 8 && m8) shape = 10;
   const CUtensorMap* mKS = reinterpret_cast<const CUtensorMap*>(tmapKS);
+  /* EKF_SWEEP_STAGES=2|3: a shallower ring (fewer bytes in flight per SM: lower loaded memory latency for the line loop beside
+   * the sweep, at the price of less latency tolerance in the sweep) -- measurement knob */
+  static int stg = -1;
+  if (stg < 0) { const char* e = getenv("EKF_SWEEP_STAGES"); stg = e ? atoi(e) : 0; }
+  if (stg == 2 || stg == 3) {
+    if (shape == 10 && C == 16 && stg == 2) return launch_sweep_dmma<2, 16>(g, b, m8, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md8);
+    if (shape == 0 && C == 8) {
+      if (stg == 2) return launch_sweep_quad<2, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+      return launch_sweep_quad<3, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
+    }
+  }
   switch (shape) {       /* shape % 4: tile shape; shape / 4: 0 = 8 consumer warps, 1 = 16 */
     case 1: return launch_sweep_shape<32, 128, 4, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
     case 2: return launch_sweep_shape<16, 256, 3, 8, 8>(g, b, m, mK, mKS, dst, slot0, view, counters, np_ub, grid, s, md);
