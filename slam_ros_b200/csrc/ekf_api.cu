@@ -59,6 +59,12 @@ struct ekf_ctx {
   double* h_in;        /* pinned mirror */
   int* h_jout;         /* pinned */
   EkfDevState* h_st;   /* pinned */
+  /* device-resident scans never wait for the GPU, so the host only knows an upper bound of the map size (it sizes grids and
+   * picks the line-loop form).  A snapshot of the device state is copied back asynchronously now and then; once it has
+   * landed, the bound restarts from the snapshot plus the lines enqueued after it. */
+  EkfDevState* h_snap; /* pinned */
+  cudaEvent_t ev_snap;
+  int snap_inflight, snap_added;
   /* host-side view of the device state */
   int L_ub;            /* upper bound of savedLineCount */
   int pend_ub;         /* upper bound of the pending-term count */
@@ -85,6 +91,7 @@ struct ekf_ctx {
   CUtensorMap tmapK[2];        /* [0]: K bands (box = tile columns x 8 slots), [1]: K S bands (box = tile rows x 8 slots) */
   int rd, par, group;
   int tabpar;                  /* per-line table set of the next overlapped scan */
+  int last_line_sms;           /* SMs the most recent sweep launch left free for the line loop */
   void* arena; size_t arena_bytes;   /* y | top | diag | gates | matched | colA,colB | Kp | KSp (one allocation: one L2 window) */
   int chunk_lines, chunk_above;/* overlapped scans of more than chunk_above lines run as chunks of chunk_lines (EKF_CHUNK, EKF_CHUNK_ABOVE; 0 = never) */
   int slots;                   /* rows of Kp / KSp: max(max_batch, 2 * group) */
@@ -138,8 +145,17 @@ const int kOverlapMinN = 6000;                /* below this state dimension the 
  * two on one GPU at 10k landmarks.  A row-sharded filter sweeps 1/world of the triangle but still walks every
  * landmark and every row per line, so there the line loop gets more (28 from 4 ranks up). */
 static int line_sms_env() { static int v = -2; if (v == -2) { const char* e = getenv("EKF_LINE_SMS"); v = e ? atoi(e) : -1; if (v < 1 || v > 64) v = -1; } return v; }
-static int line_sms_for(int world) { const int e = line_sms_env(); return e > 0 ? e : (world >= 4 ? 28 : 20); }
-#define EKF_LINE_SMS line_sms_for(ctx->g.world)
+/* Single GPU: when a few more SMs give the line loop one thread per landmark of the CAPACITY (up to 28 SMs = 14 336 lines),
+ * it takes them: the form that keeps a thread's landmark in registers is then valid whatever the map has grown to, also in
+ * long device-resident bursts where the host only has a drifting upper bound of the map size. */
+static int line_sms_for(int world, int cap, int m) {
+  const int e = line_sms_env();
+  if (e > 0) return e;
+  if (world >= 4) return 28;
+  const int need = (cap + 511) / 512;
+  /* up to 8 lines per scan the step is bound by the sweep, which keeps the two SMs (0.7 % of the step at 10k landmarks) */
+  return (world == 1 && m > 8 && need > 20 && need <= 28) ? need : 20;
+}
 
 double* in_u(ekf_ctx* c) { return c->d_in; }
 double* in_x(ekf_ctx* c) { return c->d_in + 3; }
@@ -359,6 +375,12 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
    * kernels after the last; in between k_chunk_mark snapshots the finished chunk for its sweep and restarts the pending
    * list.  Same operations per element in the same order as one line loop + one sweep: identical bits. */
   const int chunk = (ctx->chunk_lines > 0 && m > ctx->chunk_above && ctx->g.world == 1) ? ctx->chunk_lines : m;
+  const int line_sms = line_sms_for(ctx->g.world, ctx->g.cap, m);
+  /* the sweep still in flight was sized to leave last_line_sms SMs free: a wider line loop waits for it (only when the
+   * number of lines per scan changes class) */
+  if (line_sms > ctx->last_line_sms && ctx->pg_valid && ctx->evF_used[ctx->par ^ 1])
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->evF[ctx->par ^ 1], 0));
+  ctx->last_line_sms = line_sms;
   use_tables(ctx, ctx->tabpar);
   ctx->tabpar ^= 1;
   long long lub = (long long)ctx->L_ub + m;
@@ -373,9 +395,9 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
     EkfBuffers b = ctx->b;
     b.P = ctx->Pbuf[ctx->rd];
     if (first) { CU(ekf_launch_predict(ctx->g, b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream)); ctx->launches++; }
-    /* The line loop runs as EKF_LINE_SMS cooperative CTAs on the SMs the in-flight sweep leaves free (its
-     * persistent grid is num_sms - EKF_LINE_SMS): no register / FP64-issue sharing with the sweep. */
-    CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, line0, line1, EKF_LINE_SMS, 1, slot0, ctx->pg_slot0,
+    /* The line loop runs as line_sms cooperative CTAs on the SMs the in-flight sweep leaves free (its
+     * persistent grid is num_sms - line_sms): no register / FP64-issue sharing with the sweep. */
+    CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, line0, line1, line_sms, 1, slot0, ctx->pg_slot0,
                              ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream));
     ctx->launches++;
     const int tgt = ctx->pg_valid ? (ctx->rd ^ 1) : ctx->rd;      /* source of this chunk's sweep */
@@ -400,7 +422,7 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
     }
     const int nterms = line1 - line0;
     CU(ekf_launch_sweep_tma(ctx->g, bt, &ctx->tmap2[tgt], ctx->have_tmap8 ? &ctx->tmap8[tgt] : 0, &ctx->tmapK[0], &ctx->tmapK[1], ctx->Pbuf[tgt ^ 1], slot0, &ctx->d_view[par], ctx->d_counters + 16,
-                            ctx->sweep_shape, nterms, L_after_ub, ctx->num_sms - EKF_LINE_SMS, ctx->wstream,
+                            ctx->sweep_shape, nterms, L_after_ub, ctx->num_sms - line_sms, ctx->wstream,
                             &ctx->tmap2[tgt ^ 1], ctx->have_tmap8 ? &ctx->tmap8[tgt ^ 1] : 0));
     { const int per_pass = ekf_sweep_terms_per_pass(ctx->sweep_shape, nterms); ctx->launches += (nterms + per_pass - 1) / per_pass; }
     if (ctx->prof) {
@@ -477,6 +499,7 @@ int read_state(ekf_ctx* ctx) {
   CU(cudaMemcpyAsync(ctx->h_st, ctx->b.st, sizeof(EkfDevState), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (!ctx->scan_open) ctx->L_ub = ctx->h_st->L;
+  ctx->snap_inflight = 0;                          /* the exact value supersedes any snapshot still on its way */
   return EKF_OK;
 }
 
@@ -557,7 +580,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   { const char* e = getenv("EKF_CHUNK_ABOVE"); ctx->chunk_above = e ? atoi(e) : 32; if (ctx->chunk_above < 1) ctx->chunk_above = 1; }
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
   ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);
-  ctx->arena = 0; ctx->arena_bytes = 0; ctx->xchg = 0; ctx->poisoned = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
+  ctx->last_line_sms = 64; ctx->arena = 0; ctx->arena_bytes = 0; ctx->h_snap = 0; ctx->ev_snap = 0; ctx->snap_inflight = 0; ctx->snap_added = 0; ctx->xchg = 0; ctx->poisoned = 0; ctx->peers_ok = 0; ctx->peers_mapped = 0; memset(ctx->peer_map, 0, sizeof ctx->peer_map); memset(&ctx->peers, 0, sizeof ctx->peers);
   *out = ctx;                                  /* so the caller can read ekf_last_error on failure */
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -607,6 +630,8 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
     ctx->b.Kp = (double2*)(a + o_kp); ctx->b.KSp = (double2*)(a + o_ksp);
   }
   CU(cudaMallocHost(&ctx->h_st, sizeof(EkfDevState)));
+  CU(cudaMallocHost(&ctx->h_snap, sizeof(EkfDevState)));
+  CU(cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
   CU(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   { const char* e = getenv("EKF_SWEEP_SHAPE"); ctx->sweep_shape = e ? atoi(e) : 0; if (ctx->sweep_shape < 0 || (ctx->sweep_shape > 5 && ctx->sweep_shape != 8 && ctx->sweep_shape != 9 && ctx->sweep_shape != 10 && ctx->sweep_shape != 11) || ctx->sweep_shape == 3) ctx->sweep_shape = 0; }
   { const int cap = 2 * ekf_sweep_terms_per_pass(ctx->sweep_shape, 64); if (ctx->group > cap) ctx->group = cap; if (ctx->group < 1) ctx->group = 1; }
@@ -779,7 +804,8 @@ int ekf_destroy(ekf_ctx* ctx) {
   if (ctx->evF[1]) cudaEventDestroy(ctx->evF[1]);
   if (ctx->wstream) cudaStreamDestroy(ctx->wstream);
   cudaFree(ctx->d_stage); cudaFree(ctx->d_partials); cudaFree(ctx->d_out3);
-  cudaFreeHost(ctx->h_st);
+  cudaFreeHost(ctx->h_st); cudaFreeHost(ctx->h_snap);
+  if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
   for (size_t i = 0; i < ctx->ev.size(); ++i) cudaEventDestroy(ctx->ev[i]);
   for (size_t i = 0; i < ctx->lev.size(); ++i) cudaEventDestroy(ctx->lev[i]);
   if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -837,8 +863,19 @@ int ekf_scan_device(ekf_ctx* ctx, const double* d_u, int m, const double* d_z, c
   CU(cudaSetDevice(ctx->cfg.device));
   int rc = ensure_lines(ctx, m);
   if (rc) return rc;
+  if (ctx->snap_inflight && cudaEventQuery(ctx->ev_snap) == cudaSuccess) {
+    const long long lub = (long long)ctx->h_snap->L + ctx->snap_added;
+    if (lub < ctx->L_ub) ctx->L_ub = (int)lub;
+    ctx->snap_inflight = 0;
+  } else if (ctx->snap_inflight) (void)cudaGetLastError();            /* cudaErrorNotReady is not an error */
   rc = enqueue_scan(ctx, d_u, 0, m, d_z, d_R);
   if (rc) return rc;
+  if (ctx->snap_inflight) ctx->snap_added += m;
+  else {
+    CU(cudaMemcpyAsync(ctx->h_snap, ctx->b.st, sizeof(EkfDevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_snap, ctx->stream));
+    ctx->snap_inflight = 1; ctx->snap_added = 0;
+  }
   if (d_j_out && m > 0)
     CU(cudaMemcpyAsync(d_j_out, ctx->b.jout, (size_t)m * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
   return EKF_OK;
@@ -1105,6 +1142,7 @@ int ekf_upload(ekf_ctx* ctx, const double* y, const double* P, int n_lines) {
   CU(cudaMemcpyAsync(ctx->b.st, ctx->h_st, sizeof(EkfDevState), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->L_ub = n_lines;
+  ctx->snap_inflight = 0;
   if (y && P) ctx->poisoned = 0;      /* a complete state replaces whatever a failed exchange left behind */
   return EKF_OK;
 }

@@ -1835,6 +1835,7 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
      * line loop's state spills */
     static int lt = -1;
     if (lt < 0) { const char* e = getenv("EKF_LINE_THREADS"); lt = e ? atoi(e) : 0; }
+    if (L_ub > g.cap) L_ub = g.cap;
     if (lt == 256 && L_ub <= ctas * 256)
       return cudaLaunchCooperativeKernel((const void*)k_scan_lines2<256, true, true>, dim3(ctas), dim3(256), args2, 0, s);
     /* at most one landmark per thread (host-side bound): the form that keeps the hot entries in registers */

@@ -459,6 +459,34 @@ def test_full_size_10k_landmarks_against_oracle(libekf, oracle_cls):
         assert tr_after < tr_before + 1e-2                         # prediction adds <= 4q ~ 2e-3; updates only remove
 
 
+def test_overlapped_pipeline_with_changing_line_counts(libekf):
+    """Scans of 8 / 32 / 64 / 16 / 40 lines in turn on a map whose capacity (10 752 lines) makes the line loop of the
+    longer scans take 21 SMs instead of 20 (one thread per landmark of the capacity): the sweep in flight was sized for
+    the previous scan's class, so a wider line loop first waits for it.  Bit for bit against the in-place path."""
+    from slam_ros_b200 import EkfFilter
+    from slam_ros_b200.ekf import EKF_FLAG_NO_OVERLAP
+    N = 10400
+    ms = [8, 32, 8, 64, 16, 8, 40, 8]
+    scn = sc.map_scenario(N, len(ms), m=64, seed=5, stride=67)
+    f = EkfFilter(capacity_lines=N + 352)
+    g = EkfFilter(capacity_lines=N + 352, flags=EKF_FLAG_NO_OVERLAP)
+    for x in (f, g):
+        x.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
+    for s, m in enumerate(ms):
+        z, R = scn["z"][s][:m].copy(), scn["R"][s][:m].copy()
+        if s == 3:
+            z[11, 1] += 4.0                                         # one line of the chunked scan matches nothing
+        rc, j, pose = f.scan(scn["u"][s], z, R)
+        rg, jg, pg = g.scan(scn["u"][s], z, R)
+        assert rc == rg == 0 and np.array_equal(j, jg) and np.array_equal(pose, pg), "step %d" % s
+        assert (j >= 0).sum() >= m - 2
+    assert f.cov_stats() == g.cov_stats()
+    assert np.array_equal(f.download_y(), g.download_y())
+    nl = 3 + 2 * (N + 1)
+    for (r0, c0) in [(0, 0), (0, nl - 80), (nl - 80, nl - 80), (5000, 9000), (123, 20000)]:
+        assert np.array_equal(f.download_block(r0, c0, 80, 80), g.download_block(r0, c0, 80, 80)), (r0, c0)
+
+
 def test_overlapped_pipeline_interleaved_with_stepwise_calls(libekf, oracle_cls):
     """A map large enough (n = 6203) for the overlapped two-stream path, with fused scans, step-wise scans,
     downloads and sweep probes interleaved: every switch drains the sweep in flight."""
