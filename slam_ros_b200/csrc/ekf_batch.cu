@@ -569,7 +569,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     st->L = L; st->pose[0] = ps0; st->pose[1] = ps1; st->pose[2] = ps2;
     st->sticky = s_sticky;                        /* status reports this scan only */
     st->resets += resets;
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   /* the shared-memory source has been read: the CTA may go */
   }
   BT_MARK(7);
   BT_PRINT();
