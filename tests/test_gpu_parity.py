@@ -459,6 +459,32 @@ def test_full_size_10k_landmarks_against_oracle(libekf, oracle_cls):
         assert tr_after < tr_before + 1e-2                         # prediction adds <= 4q ~ 2e-3; updates only remove
 
 
+def test_chunked_scan_through_capacity_map_reset_and_empty_map(libekf, oracle_cls):
+    """A chunked (40-line) scan whose unmatched lines take the map beyond capacity - headroom: the map is reset at the end
+    of the scan while the sweeps of its earlier chunks may still be in flight; the next 40-line scan then meets an EMPTY
+    map (every line queued, no chunking, the in-place path), the one after a 40-landmark map, and a 100-line scan (more
+    than the 64 lines the tables start with) grows the tables.  Every step against the oracle."""
+    N, m = 3100, 40
+    scn = sc.map_scenario(N, 5, m=m, seed=91, stride=m + 3)
+    f, so = seed_pair(N, N + 20, oracle_cls, scn)
+    so._lib.ekfo_set_threads(so._h, 0)
+    wide = sc.map_scenario(N, 1, m=100, seed=92, stride=7)
+    for s in range(5):
+        z, R = scn["z"][s].copy(), scn["R"][s].copy()
+        if s == 1:
+            z[::3, 1] += 5.0 + 0.05 * np.arange(z[::3].shape[0])    # 14 lines match nothing: L = N + 14 > capacity - 10
+        if s == 4:
+            z, R = wide["z"][0].copy(), wide["R"][0].copy()          # 100 lines on a small map
+        rc, j, pose = f.scan(scn["u"][s], z, R)
+        st, jo = so.scan(scn["u"][s], z, R)
+        assert rc == st and np.array_equal(j, jo), "step %d" % s
+        assert f.lines == so.lines, "step %d" % s
+        if s == 0:
+            compare_state(f, so, "before the reset")
+    assert so.stats()["resets"] == 1 and so.lines > 40
+    compare_state(f, so, "after reset, empty map and table growth")
+
+
 def test_overlapped_pipeline_with_changing_line_counts(libekf):
     """Scans of 8 / 32 / 64 / 16 / 40 lines in turn on a map whose capacity (10 752 lines) makes the line loop of the
     longer scans take 21 SMs instead of 20 (one thread per landmark of the capacity): the sweep in flight was sized for
