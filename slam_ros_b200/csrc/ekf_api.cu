@@ -335,7 +335,7 @@ int enqueue_end(ekf_ctx* ctx, const double* d_z, const double* d_R, int m) {
   if (rc) return rc;
   ctx->pend_ub = 0;
   CU(ekf_launch_end_scan(ctx->g, ctx->b, d_z, d_R, m, ctx->L_ub, 0, 0, ctx->stream));
-  ctx->launches += (m > 0) ? 3 : 2;
+  ctx->launches += (m > 0) ? 2 : 1;
   long long lub = (long long)ctx->L_ub + m;
   ctx->L_ub = (int)(lub > ctx->g.cap ? ctx->g.cap : lub);
   ctx->scan_open = 0;
@@ -405,7 +405,7 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
     bt.P = ctx->Pbuf[tgt];
     if (last) {
       CU(ekf_launch_end_scan(ctx->g, bt, d_z, d_R, m, ctx->L_ub, slot0, &ctx->d_view[par], ctx->stream));
-      ctx->launches += 3;
+      ctx->launches += 2;
       int rc = line_event(ctx); if (rc) return rc;
     } else {
       CU(ekf_launch_chunk_mark(ctx->b, line1, &ctx->d_view[par], ctx->stream));

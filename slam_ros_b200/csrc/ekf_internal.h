@@ -42,6 +42,7 @@ struct EkfDevState {          /* one per filter, in global memory */
   int pbase;                  /* matches of this scan already folded into P by a mid-scan flush */
   int np;                     /* pending rank-2 terms = pidx[line] - pbase */
   int xseq;                   /* row-sharded mode: matched lines exchanged over NVLink so far (same on every rank) */
+  int L0;                     /* savedLineCount before the last end-of-scan's append (read by its phase B) */
 };
 
 /* what a scan's (possibly later, possibly concurrent) sweep needs to know about that scan */

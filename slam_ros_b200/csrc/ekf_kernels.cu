@@ -1526,7 +1526,7 @@ k_sweep_dmma(EkfGeom g, EkfBuffers b, const __grid_constant__ CUtensorMap tmapP,
 /* Robot.cpp:702-716 then :776-866 phase A (per unmatched line: world-frame parameters, P_ll, and the
  * rows 0..2 of its new columns -- all functions of the 3x3 robot block only). */
 __global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, const double* __restrict__ z, const double* __restrict__ R, int m,
-                                                    int slot0) {
+                                                    int slot0, EkfScanView* view) {
   EkfDevState* st = b.st;
   __shared__ double s_pose[3];
   __shared__ double s_y01[2];
@@ -1610,6 +1610,16 @@ __global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, con
       b.top[(size_t)k * g.ld + l + 1] = r1;
     }
   }
+  /* ++savedLineCount (Robot.cpp:866) for every appended line, then the reset test (:893-904).  Done here, by the one block of
+   * this kernel, instead of in a third launch after phase B: phase B takes the line count from before the append (L0). */
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->L0 = L;
+    int Ln = L + n_add;
+    if (Ln > g.cap - g.headroom) { Ln = 0; st->resets += 1; }
+    st->L = Ln;
+    if (view) { view->cnt = b.pidx[m] - st->pbase; view->L = Ln; }   /* what this scan's sweep will need */
+  }
 }
 
 /* Robot.cpp:856-860 phase B: the new landmarks' column blocks P[k, l..l+1] = Gx * P[0:3, k], 3 <= k < l.
@@ -1617,7 +1627,7 @@ __global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, con
 __global__ void __launch_bounds__(EKF_BLOCK) k_end_scan_b(EkfGeom g, EkfBuffers b) {
   const EkfDevState* st = b.st;
   const int n_add = st->n_added;
-  const int L = st->L;
+  const int L = st->L0;                                        /* lines before this scan's append (k_end_scan_a) */
   const int c_idx = blockIdx.x * blockDim.x + threadIdx.x;     /* 0 .. 2*n_add-1 */
   if (c_idx >= 2 * n_add) return;
   const int e = c_idx >> 1, tsel = c_idx & 1;
@@ -1632,15 +1642,6 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_end_scan_b(EkfGeom g, EkfBuffers 
     else { v = 0.0; axpy_skip(v, cw, t0p[k]); axpy_skip(v, sw, t1p[k]); }
     b.P[local_row(g, k) * g.ld + col] = v;
   }
-}
-
-/* ++savedLineCount (Robot.cpp:866) for every appended line, then the reset test (:893-904). */
-__global__ void k_end_scan_c(EkfGeom g, EkfBuffers b, int m, EkfScanView* view) {
-  EkfDevState* st = b.st;
-  int L = st->L + st->n_added;
-  if (L > g.cap - g.headroom) { L = 0; st->resets += 1; }
-  st->L = L;
-  if (view) { view->cnt = b.pidx[m] - st->pbase; view->L = L; }   /* what this scan's sweep will need */
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -1785,7 +1786,7 @@ void ekf_prefer_max_smem_carveout(void) {
   cudaFuncSetAttribute(k_scan_lines2<512, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_a, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_end_scan_b, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(k_end_scan_c, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  cudaFuncSetAttribute(k_chunk_mark, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   cudaFuncSetAttribute(k_queue_all, cudaFuncAttributePreferredSharedMemoryCarveout, c);
   (void)cudaGetLastError();
 }
@@ -2054,7 +2055,7 @@ cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const dou
                                 int m, int L_ub, int slot0, EkfScanView* view, cudaStream_t s) {
   /* all blocks of phase A redo the (idempotent) no-match bookkeeping only in thread 0 of block 0's
    * shared copy; to keep it race-free phase A runs as ONE block when it also has to write the pose */
-  k_end_scan_a<<<1, 512, 0, s>>>(g, b, d_z, d_R, m, slot0);
+  k_end_scan_a<<<1, 512, 0, s>>>(g, b, d_z, d_R, m, slot0, view);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (m > 0) {
@@ -2067,8 +2068,7 @@ cudaError_t ekf_launch_end_scan(const EkfGeom& g, const EkfBuffers& b, const dou
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  k_end_scan_c<<<1, 1, 0, s>>>(g, b, m, view);
-  return cudaGetLastError();
+  return cudaSuccess;
 }
 cudaError_t ekf_launch_assemble(const EkfGeom& g, const EkfBuffers& b, int r0, int nr, int c0, int nc,
                                 double* d_out, int ld_out, cudaStream_t s) {

@@ -39,8 +39,13 @@ CONFIGS = {
     "1k": dict(N=1000, steps=10000, every=50, nblk=6, bs=16, cap=1000 + 512),
     "10k": dict(N=10000, steps=100, every=10, nblk=12, bs=32, cap=10000 + 1024),
     "40k": dict(N=40000, steps=100, every=10, nblk=12, bs=32, cap=40000 + 1024),
+    # north_star's "over 1k steps" at configs[2]'s size, and configs[2]'s batched scans (m = 32, and m = 64 which the GPU path
+    # runs as four chunks of 16 lines, each chunk's sweep under the next chunk's line loop)
+    "10k_1000": dict(N=10000, steps=1000, every=50, nblk=8, bs=24, cap=10000 + 1024),
+    "10k_m32": dict(N=10000, steps=60, every=10, nblk=8, bs=24, cap=10000 + 1024, m=32),
+    "10k_m64": dict(N=10000, steps=40, every=10, nblk=8, bs=24, cap=10000 + 1024, m=64),
 }
-M, SEED = 8, 1
+SEED = 1
 
 
 def block_positions(nl, nblk, bs, seed):
@@ -67,6 +72,7 @@ def checkpoint(so, pos, bs):
 def make(name):
     c = CONFIGS[name]
     N, steps, every, bs = c["N"], c["steps"], c["every"], c["bs"]
+    M = c.get("m", 8)
     t0 = time.time()
     scn = sc.map_scenario(N, steps, m=M, seed=SEED)
     so = StructuredOracle(c["cap"], threads=0 if N > 2000 else 4)
