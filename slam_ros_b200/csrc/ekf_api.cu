@@ -92,6 +92,7 @@ struct ekf_ctx {
   int rd, par, group;
   int tabpar;                  /* per-line table set of the next overlapped scan */
   int last_line_sms;           /* SMs the most recent sweep launch left free for the line loop */
+  int no_fuse;                 /* EKF_FUSE_PREDICT=0: the prediction stays a launch of its own (A/B) */
   void* arena; size_t arena_bytes;   /* y | top | diag | gates | matched | colA,colB | Kp | KSp (one allocation: one L2 window) */
   int chunk_lines, chunk_above;/* overlapped scans of more than chunk_above lines run as chunks of chunk_lines (EKF_CHUNK, EKF_CHUNK_ABOVE; 0 = never) */
   int slots;                   /* rows of Kp / KSp: max(max_batch, 2 * group) */
@@ -394,11 +395,13 @@ int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t
     const int slot0 = par * ctx->group;
     EkfBuffers b = ctx->b;
     b.P = ctx->Pbuf[ctx->rd];
-    if (first) { CU(ekf_launch_predict(ctx->g, b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream)); ctx->launches++; }
+    const bool fuse = first && ekf_scan_lines_fuses_predict(ctx->peers_ok ? &ctx->peers : 0) && !ctx->no_fuse;
+    if (first && !fuse) { CU(ekf_launch_predict(ctx->g, b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream)); ctx->launches++; }
     /* The line loop runs as line_sms cooperative CTAs on the SMs the in-flight sweep leaves free (its
      * persistent grid is num_sms - line_sms): no register / FP64-issue sharing with the sweep. */
     CU(ekf_launch_scan_lines(ctx->g, b, d_z, d_R, line0, line1, line_sms, 1, slot0, ctx->pg_slot0,
-                             ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream));
+                             ctx->pg_valid ? &ctx->d_view[par ^ 1].cnt : 0, ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream,
+                             fuse ? d_u : 0, fuse ? d_x_t0 : 0, m));
     ctx->launches++;
     const int tgt = ctx->pg_valid ? (ctx->rd ^ 1) : ctx->rd;      /* source of this chunk's sweep */
     EkfBuffers bt = ctx->b;
@@ -454,8 +457,14 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
     use_tables(ctx, 0);
   }
   { int rc = line_event(ctx); if (rc) return rc; }
-  CU(ekf_launch_predict(ctx->g, ctx->b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
-  ctx->launches++;
+  /* fused path on a non-empty map: the prediction runs as the prologue of the line-loop launch (one launch less) */
+  const bool fused_lines = ctx->L_ub > 0 && m > 0 && (ctx->g.world == 1 || ctx->peers_ok) && ctx->cfg.max_batch <= 64 &&
+                           !(ctx->cfg.flags & (EKF_FLAG_EAGER_SWEEP | EKF_FLAG_PER_LINE_KERNELS));
+  const bool fuse = fused_lines && ekf_scan_lines_fuses_predict(ctx->peers_ok ? &ctx->peers : 0) && !ctx->no_fuse;
+  if (!fuse) {
+    CU(ekf_launch_predict(ctx->g, ctx->b, d_u, d_x_t0, m, ctx->L_ub, ctx->stream));
+    ctx->launches++;
+  }
   ctx->pend_ub = 0;
   ctx->scan_open = 1;
   if (ctx->L_ub == 0) {
@@ -471,7 +480,8 @@ int enqueue_scan(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, c
       /* row-sharded: the same kernel, launched cooperatively (its CTAs spin on the peers' arrival flags, so they
        * must all be resident), exchanges the H-column slices over NVLink peer memory between its phases */
       CU(ekf_launch_scan_lines(ctx->g, ctx->b, d_z, d_R, i0, i0 + cnt, ctx->cluster, ctx->peers_ok ? 1 : 0, 0, 0, 0,
-                               ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream));
+                               ctx->peers_ok ? &ctx->peers : 0, ctx->L_ub, ctx->stream,
+                               (fuse && i0 == 0) ? d_u : 0, (fuse && i0 == 0) ? d_x_t0 : 0, m));
       ctx->launches++;
       ctx->pend_ub += cnt;
       i0 += cnt;
@@ -577,6 +587,7 @@ int create_common(ekf_ctx** out, const ekf_config* cfg, int rank, int world, con
   ctx->d_stage = 0; ctx->stage_elems = 0; ctx->d_partials = 0; ctx->d_out3 = 0;
   ctx->overlap = 0; ctx->wstream = 0; ctx->Pbuf[0] = ctx->Pbuf[1] = 0; ctx->rd = 0; ctx->par = 0; ctx->group = 8; ctx->tabpar = 0;
   { const char* e = getenv("EKF_CHUNK"); ctx->chunk_lines = e ? atoi(e) : 16; if (ctx->chunk_lines < 0) ctx->chunk_lines = 0; }
+  { const char* e = getenv("EKF_FUSE_PREDICT"); ctx->no_fuse = (e && atoi(e) == 0) ? 1 : 0; }
   { const char* e = getenv("EKF_CHUNK_ABOVE"); ctx->chunk_above = e ? atoi(e) : 32; if (ctx->chunk_above < 1) ctx->chunk_above = 1; }
   ctx->pg_valid = 0; ctx->pg_slot0 = 0; ctx->d_view = 0; ctx->d_counters = 0; ctx->evE = 0; ctx->evF[0] = ctx->evF[1] = 0;
   ctx->evF_used[0] = ctx->evF_used[1] = 0; memset(ctx->tab, 0, sizeof ctx->tab);

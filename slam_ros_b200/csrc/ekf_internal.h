@@ -99,7 +99,11 @@ void ekf_prefer_max_smem_carveout(void);
 /* all lines [line0, line1) of the open scan in one cluster launch (single-GPU path) */
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                   int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
-                                  const int* prev_cnt_ptr, const EkfPeers* peers, int L_ub, cudaStream_t s);
+                                  const int* prev_cnt_ptr, const EkfPeers* peers, int L_ub, cudaStream_t s,
+                                  const double* pred_u = 0, const double* pred_x = 0, int pred_m = 0);
+/* pred_u != NULL: the scan's prediction (ekf_launch_predict's work for pred_m lines) runs as the prologue of this launch;
+ * only legal when ekf_scan_lines_fuses_predict(peers) */
+int ekf_scan_lines_fuses_predict(const EkfPeers* peers);
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s);
 cudaError_t ekf_launch_chunk_mark(const EkfBuffers& b, int next_line, EkfScanView* view, cudaStream_t s);
 cudaError_t ekf_launch_queue_all(const EkfGeom& g, const EkfBuffers& b, int m, cudaStream_t s);

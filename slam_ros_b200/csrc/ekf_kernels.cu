@@ -73,10 +73,10 @@ __global__ void k_init(EkfGeom g, EkfBuffers b) {
 }
 
 /* Robot.cpp:130-258 (structured: SURVEY appendix A.2).  Also opens the scan: per-line tables. */
-__global__ void __launch_bounds__(EKF_BLOCK) k_predict(EkfGeom g, EkfBuffers b, const double* __restrict__ u,
-                                                       const double* __restrict__ x_t0, int m) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int stride = gridDim.x * blockDim.x;
+/* Robot.cpp:130-258 (+ the per-scan resets of :294) for thread gid of stride: the body of k_predict, also run as the
+ * prologue of the one-barrier line loop (k_scan_lines2 with u != NULL: one launch less on the latency path of small maps) */
+__device__ __forceinline__ void predict_body(const EkfGeom& g, const EkfBuffers& b, const double* __restrict__ u,
+                                             const double* __restrict__ x_t0, int m, int gid, int stride) {
   EkfDevState* st = b.st;
   const double* x = x_t0 ? x_t0 : st->pose;
   const double x0 = x[0], x1 = x[1], x2 = x[2];
@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(EKF_BLOCK) k_predict(EkfGeom g, EkfBuffers b, 
     st->pbase = 0; st->np = 0;
     b.pidx[0] = 0; b.eidx[0] = 0;
   }
+}
+__global__ void __launch_bounds__(EKF_BLOCK) k_predict(EkfGeom g, EkfBuffers b, const double* __restrict__ u,
+                                                       const double* __restrict__ x_t0, int m) {
+  predict_body(g, b, u, x_t0, m, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 /* Robot.cpp:313-501 for one line: every un-matched landmark is gated in parallel; first fit = the
@@ -714,7 +718,8 @@ __device__ __forceinline__ void hot_store(const EkfGeom& g, const EkfBuffers& b,
 template <int FL_THREADS, bool COOP, bool CACHED>
 __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuffers b, const double* __restrict__ z,
                                                                const double* __restrict__ R, int line0, int line1,
-                                                               int own_slot0, int prev_slot0, const int* __restrict__ prev_cnt_ptr) {
+                                                               int own_slot0, int prev_slot0, const int* __restrict__ prev_cnt_ptr,
+                                                               const double* __restrict__ pred_u, const double* __restrict__ pred_x, int pred_m) {
   __shared__ int s_min[FL_THREADS / 32];
   __shared__ double2 s_ka[FL_MAXP], s_kb[FL_MAXP], s_ksa[FL_MAXP], s_ksb[FL_MAXP];
   const int prev_cnt = prev_cnt_ptr ? *prev_cnt_ptr : 0;   /* previous scan's terms not yet folded into b.P */
@@ -725,6 +730,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_scan_lines2(EkfGeom g, EkfBuf
   auto group_sync = [] () {
     if (COOP) cg::this_grid().sync(); else cg::this_cluster().sync();
   };
+  if (pred_u) {                        /* the scan's prediction as the prologue of its (first) line-loop launch */
+    predict_body(g, b, pred_u, pred_x, pred_m, gtid, gstride);
+    __threadfence();
+    group_sync();
+  }
   const int L = st->L, epoch = st->epoch, pbase = st->pbase;
   int nm = b.pidx[line0];             /* matches of this scan so far: tracked identically by every thread */
   int ne = b.eidx[line0];
@@ -1815,10 +1825,14 @@ int ekf_pick_cluster(void) {
   (void)cudaGetLastError();
   return 8;
 }
+/* whether ekf_launch_scan_lines can run the scan's prediction as the prologue of the line loop (the one-barrier form only) */
+int ekf_scan_lines_fuses_predict(const EkfPeers* peers) { return !line_loop_v1() && !(peers && peers->world > 1); }
 cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const double* d_z, const double* d_R,
                                   int line0, int line1, int ctas, int coop, int own_slot0, int prev_slot0,
-                                  const int* prev_cnt_ptr, const EkfPeers* peers, int L_ub, cudaStream_t s) {
+                                  const int* prev_cnt_ptr, const EkfPeers* peers, int L_ub, cudaStream_t s,
+                                  const double* pred_u, const double* pred_x, int pred_m) {
   if (line1 <= line0) return cudaSuccess;
+  if (pred_u && !ekf_scan_lines_fuses_predict(peers)) return cudaErrorInvalidValue;
   EkfPeers pe;
   memset(&pe, 0, sizeof pe);
   pe.world = 1;
@@ -1831,7 +1845,7 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
     if (line_loop_v1())
       return cudaLaunchCooperativeKernel((const void*)k_scan_lines<512, true, false>, dim3(ctas), dim3(512), args, 0, s);
     void* args2[] = {(void*)&g, (void*)&b, (void*)&d_z, (void*)&d_R, (void*)&line0, (void*)&line1, (void*)&own_slot0,
-                     (void*)&prev_slot0, (void*)&prev_cnt_ptr};
+                     (void*)&prev_slot0, (void*)&prev_cnt_ptr, (void*)&pred_u, (void*)&pred_x, (void*)&pred_m};
     /* 256-thread CTAs (EKF_LINE_THREADS=256, twice the SMs for the same map): up to 255 registers per thread -- none of the
      * line loop's state spills */
     static int lt = -1;
@@ -1855,11 +1869,11 @@ cudaError_t ekf_launch_scan_lines(const EkfGeom& g, const EkfBuffers& b, const d
   if (L_ub <= ctas * 256) {
     /* small maps: 256-thread CTAs may use up to 255 registers -- no spills on the per-line critical path */
     cfg.blockDim = dim3(256);
-    return cudaLaunchKernelEx(&cfg, k_scan_lines2<256, false, true>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
+    return cudaLaunchKernelEx(&cfg, k_scan_lines2<256, false, true>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr, pred_u, pred_x, pred_m);
   }
   if (L_ub <= ctas * 512)
-    return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false, true>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
-  return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr);
+    return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false, true>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr, pred_u, pred_x, pred_m);
+  return cudaLaunchKernelEx(&cfg, k_scan_lines2<512, false, false>, g, b, d_z, d_R, line0, line1, own_slot0, prev_slot0, prev_cnt_ptr, pred_u, pred_x, pred_m);
 }
 cudaError_t ekf_launch_flush_done(const EkfBuffers& b, int next_line, cudaStream_t s) {
   k_flush_done<<<1, 32, 0, s>>>(b, next_line);
