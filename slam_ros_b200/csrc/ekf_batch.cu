@@ -112,16 +112,19 @@ __device__ __forceinline__ void b_bulk_store(void* dst, const void* src, unsigne
 template <bool TWO, int NW>
 __device__ __forceinline__ void batch_update_cold_t(double* __restrict__ P, const double2* __restrict__ K0, const double2* __restrict__ KS0,
                                                     const double2* __restrict__ K1, const double2* __restrict__ KS1,
-                                                    int nl, int w0, int lane) {
-  for (int rb = 0; rb + 2 < nl; rb += 32) {          /* the last column's cold rows end at nl - 3 */
+                                                    int nl, int qlo, int qhi, int w0, int lane) {
+  /* columns [qlo, qhi) only (the line loop folds the triangle one half at a time): below, `qhi` bounds the columns */
+  for (int rb = 0; rb + 2 < qhi; rb += 32) {         /* the last column's cold rows end at qhi - 3 */
     const int r = rb + lane;
     double2 a0 = make_double2(0.0, 0.0), a1 = a0;
     if (r < nl) { a0 = KS0[r]; if (TWO) a1 = KS1[r]; }
     const bool rok = r >= 3;
     /* Column q is cold above its landmark's diagonal block, rows < e(q) = (q - 1) | 1.  It reaches this band from
      * q = rb + 1 on and covers the whole band from q = rb + 33 on: only the columns in between need a per-row test. */
-    int q = (rb + 1 > 3 ? rb + 1 : 3) + w0;
-    const int qfull = rb + 33 < nl ? rb + 33 : nl;
+    int q = (rb + 1 > 3 ? rb + 1 : 3);
+    if (q < qlo) q = qlo;
+    q += w0;
+    const int qfull = rb + 33 < qhi ? rb + 33 : qhi;
     /* tri(q + d) - tri(q) = d q + tri(d): the four columns of a step sit at e, e + (NW q + tri(NW)), ...  Everything is
      * taken four columns at a time -- loads, then the multiply-add pairs, then stores -- so that a step costs one
      * shared-memory latency and one dependent chain, not four; the ragged steps carry a per-column predicate. */
@@ -148,11 +151,11 @@ __device__ __forceinline__ void batch_update_cold_t(double* __restrict__ P, cons
       k0p += 4 * NW; k1p += 4 * NW;                                                                                    \
       q += 4 * NW;                                                                                                     \
     }
-#define EKFB_COLD_OK(d) (rok && q + (d) < nl && r < ((q + (d) - 1) | 1))
+#define EKFB_COLD_OK(d) (rok && q + (d) < qhi && r < ((q + (d) - 1) | 1))
     while (q < qfull) EKFB_COLD_STEP(EKFB_COLD_OK(0), EKFB_COLD_OK(NW), EKFB_COLD_OK(2 * NW), EKFB_COLD_OK(3 * NW))
     if (rok) {
-      while (q + 3 * NW < nl) EKFB_COLD_STEP(true, true, true, true)
-      if (q < nl) EKFB_COLD_STEP(true, q + NW < nl, q + 2 * NW < nl, q + 3 * NW < nl)
+      while (q + 3 * NW < qhi) EKFB_COLD_STEP(true, true, true, true)
+      if (q < qhi) EKFB_COLD_STEP(true, q + NW < qhi, q + 2 * NW < qhi, q + 3 * NW < qhi)
     }
 #undef EKFB_COLD_OK
 #undef EKFB_COLD_STEP
@@ -161,13 +164,13 @@ __device__ __forceinline__ void batch_update_cold_t(double* __restrict__ P, cons
 /* nw is 3 beside an association (the fourth warp gates) and 4 after the scan's last line */
 __device__ __forceinline__ void batch_update_cold(double* __restrict__ P, const double2* __restrict__ K0, const double2* __restrict__ KS0,
                                                   const double2* __restrict__ K1, const double2* __restrict__ KS1, bool two,
-                                                  int nl, int w0, int nw, int lane) {
+                                                  int nl, int qlo, int qhi, int w0, int nw, int lane) {
   if (nw == 3) {
-    if (two) batch_update_cold_t<true, 3>(P, K0, KS0, K1, KS1, nl, w0, lane);
-    else batch_update_cold_t<false, 3>(P, K0, KS0, K1, KS1, nl, w0, lane);
+    if (two) batch_update_cold_t<true, 3>(P, K0, KS0, K1, KS1, nl, qlo, qhi, w0, lane);
+    else batch_update_cold_t<false, 3>(P, K0, KS0, K1, KS1, nl, qlo, qhi, w0, lane);
   } else {
-    if (two) batch_update_cold_t<true, 4>(P, K0, KS0, K1, KS1, nl, w0, lane);
-    else batch_update_cold_t<false, 4>(P, K0, KS0, K1, KS1, nl, w0, lane);
+    if (two) batch_update_cold_t<true, 4>(P, K0, KS0, K1, KS1, nl, qlo, qhi, w0, lane);
+    else batch_update_cold_t<false, 4>(P, K0, KS0, K1, KS1, nl, qlo, qhi, w0, lane);
   }
 }
 
@@ -312,11 +315,24 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   BT_MARK(1);
   int ne = 0, nmatch = 0;                                    /* uniform across the block */
   const double gate2x4 = 4.0 * g.gate * g.gate;
-  int np = 0;                                                /* matches nmatch-np .. nmatch-1: cold part of their update pending */
+  /* The cold triangle is folded one HALF at a time: H0 = columns < qs, H1 = columns >= qs, qs ~ nl / sqrt 2 (equal work), odd
+   * so that a landmark's two columns stay together.  np0 / np1: the most recent matches whose cold update is pending in H0 /
+   * H1.  Beside EVERY gate the three other warps fold the half with more pending terms (both its terms: each element is
+   * still read and written once per two rank-2 terms), so the cold work is the same every line instead of a full pass
+   * beside every second gate -- which took longer than the gate and made the gate warp wait.  After a fold the other half
+   * holds at most one pending term, so a gain row still corrects a column entry against at most one term, and a term is
+   * folded everywhere before its slot is reused two matches later.  -DEKFB_FULL_PASS: the whole triangle beside every second
+   * gate (A/B). */
+#ifdef EKFB_FULL_PASS
+  const int qs = nl;
+#else
+  const int qs = min(nl, max(3, (int)(0.7071f * (float)nl) | 1));
+#endif
+  int np0 = 0, np1 = 0, last_h = 1;
   bool have_new = false;                                     /* match nmatch-1: hot part pending too */
   for (int i = 0; i <= m; ++i) {
     const bool gating = i < m;
-    if (!gating && np == 0) break;
+    if (!gating && np0 == 0 && np1 == 0) break;
     /* ---- phase A ---- */
     if (have_new) {
       const double2* Kn = Ks + (size_t)((nmatch - 1) & 1) * kn;
@@ -351,11 +367,22 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     }
     BT_MARK(2);
     /* ---- phase B ---- */
-#ifdef EKFB_FOLD_EACH
-    const bool fold = np >= 1;                                 /* A/B: one term per pass, a pass beside every gate (measured: 3 542 vs 3 714 batch steps/s) */
+    int fh = -1;                                               /* the half folded beside this line's gate */
+    if (gating) {
+#ifdef EKFB_FULL_PASS
+      if (np0 == 2) fh = 0;
 #else
-    const bool fold = np == 2 || (np == 1 && !gating);
+      if (np0 > np1 || (np0 == np1 && np0 > 0 && last_h == 1)) fh = 0;
+      else if (np1 > 0) fh = 1;
 #endif
+    }
+    /* fold of half h: its np_h most recent matches, the older first */
+    auto cold_half = [&](int h, int w0, int nw) {
+      const int n = h ? np1 : np0;
+      const int s0 = (nmatch - n) & 1;
+      batch_update_cold(Ps, Ks + (size_t)s0 * kn, KSs + (size_t)s0 * kn, Ks + (size_t)(s0 ^ 1) * kn, KSs + (size_t)(s0 ^ 1) * kn,
+                        n == 2, nl, h ? qs : 3, h ? nl : qs, w0, nw, lane);
+    };
     if (warp == gw && gating) {
       const double z0 = zs[2 * i], z1 = zs[2 * i + 1];
       const double Rl[4] = {Rs[4 * i], Rs[4 * i + 1], Rs[4 * i + 2], Rs[4 * i + 3]};
@@ -431,16 +458,17 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
         if (best == EKF_NO_MATCH) { ext[ne] = i; if (jout) jout[i] = -1; }           /* :309 / :325 / :493 */
         else { matched[best] = 1; if (jout) jout[i] = best; }                       /* :501 */
       }
-    } else if (fold && (warp != gw || !gating)) {
-      const int w0 = gating ? ((warp - gw - 1) & 3) : warp, nw = gating ? nt / 32 - 1 : nt / 32;
-      const int s0 = (nmatch - np) & 1;                               /* the older pending match first */
-      batch_update_cold(Ps, Ks + (size_t)s0 * kn, KSs + (size_t)s0 * kn, Ks + (size_t)(s0 ^ 1) * kn, KSs + (size_t)(s0 ^ 1) * kn,
-                        np == 2, nl, w0, nw, lane);
+    } else if (gating && fh >= 0) {
+      cold_half(fh, (warp - gw - 1) & 3, nt / 32 - 1);
+    } else if (!gating) {                                             /* after the last line: whatever is still pending, all warps */
+      if (np0 > 0) cold_half(0, warp, nt / 32);
+      if (np1 > 0) cold_half(1, warp, nt / 32);
     }
     BT_MARK(3);
     __syncthreads();
     BT_MARK(4);
-    if (fold) np = 0;
+    if (fh == 0) { np0 = 0; last_h = 0; }
+    else if (fh == 1) { np1 = 0; last_h = 1; }
     if (!gating) break;
     const int jb = s_best;
     if (jb == EKF_NO_MATCH) { ne += 1; continue; }
@@ -448,12 +476,13 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     {
       const int a = 3 + 2 * jb, bb = a + 1;
       const int ta = tri(a), tb = tri(bb);
-      const double2* Kp = Ks + (size_t)((nmatch - 1) & 1) * kn;       /* the pending match, if any (np == 1) */
+      const double2* Kp = Ks + (size_t)((nmatch - 1) & 1) * kn;       /* the one match that may still be pending in a half */
       const double2* KSp = KSs + (size_t)((nmatch - 1) & 1) * kn;
       double2* Kw = Ks + (size_t)(nmatch & 1) * kn;
       double2* KSw = KSs + (size_t)(nmatch & 1) * kn;
       double2 kpa = make_double2(0.0, 0.0), kpb = kpa, kspa = kpa, kspb = kpa;
-      if (np == 1) { kpa = Kp[a]; kpb = Kp[bb]; kspa = KSp[a]; kspb = KSp[bb]; }
+      if (np0 + np1 > 0) { kpa = Kp[a]; kpb = Kp[bb]; kspa = KSp[a]; kspb = KSp[bb]; }
+      const bool pend_ca = (a >= qs ? np1 : np0) == 1, pend_cb = (bb >= qs ? np1 : np0) == 1;   /* columns a, b (rows above) */
       BT_MARK(8);
       for (int r = tid; r < nl; r += nt) {
         const int tr_ = tri(r);
@@ -462,9 +491,17 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
         const double p2 = (r <= 2) ? Ps[tri(2) + r] : Ps[tr_ + 2];
         double pa = (r <= a) ? Ps[ta + r] : Ps[tr_ + a];
         double pb = (r <= bb) ? Ps[tb + r] : Ps[tr_ + bb];
-        if (np == 1 && r > 2 && r != a && r != bb) {                  /* cold entries: the pending term, on the fly */
-          if (r < a) { const double2 ksr = KSp[r]; pa = sub_rank2(pa, ksr, kpa); pb = sub_rank2(pb, ksr, kpb); }
-          else { const double2 kr = Kp[r]; pa = sub_rank2(pa, kspa, kr); pb = sub_rank2(pb, kspb, kr); }
+        if (r > 2 && r != a && r != bb) {                             /* cold entries: the pending term of their half, on the fly */
+          if (r < a) {
+            if (pend_ca || pend_cb) {
+              const double2 ksr = KSp[r];
+              if (pend_ca) pa = sub_rank2(pa, ksr, kpa);
+              if (pend_cb) pb = sub_rank2(pb, ksr, kpb);
+            }
+          } else if ((r >= qs ? np1 : np0) == 1) {                    /* (a, r), (b, r) live in column r */
+            const double2 kr = Kp[r];
+            pa = sub_rank2(pa, kspa, kr); pb = sub_rank2(pb, kspb, kr);
+          }
         }
         BT_MARK(9);
         double2 Kr, KSr;
@@ -474,7 +511,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
         BT_MARK(11);
       }
     }
-    nmatch += 1; np += 1; have_new = true;
+    nmatch += 1; np0 += 1; if (qs < nl) np1 += 1; have_new = true;
     BT_MARK(5);
     __syncthreads();
     BT_MARK(6);
