@@ -369,7 +369,7 @@ int line_event(ekf_ctx* ctx) {
  * scan's line loop already executes.  Buffers: sweep(s) reads X and writes X^1; the next line loop
  * reads X (complete once sweep(s-1) is done) plus this scan's pending terms. */
 int enqueue_scan_overlapped(ekf_ctx* ctx, const double* d_u, const double* d_x_t0, int m, const double* d_z, const double* d_R) {
-  /* Scans of more than kChunkAbove lines go through the pipeline as CHUNKS of kChunkLines: a chunk's sweep (16 pending terms,
+  /* Scans of more than chunk_above (32) lines go through the pipeline as CHUNKS of chunk_lines (16): a chunk's sweep (16 pending terms,
    * one tensor-core pass) runs while the next chunk's line loop executes, exactly as a scan's sweep runs under the next
    * scan's line loop.  A line then corrects its column reads against at most 2 x 16 pending terms instead of up to 128, and
    * the sweeps of a 64-line scan hide under its own line loop.  Prediction runs before the first chunk, the end-of-scan
