@@ -485,6 +485,47 @@ def test_chunked_scan_through_capacity_map_reset_and_empty_map(libekf, oracle_cl
     compare_state(f, so, "after reset, empty map and table growth")
 
 
+@pytest.mark.parametrize("N,cap_extra,m", [(3100, 128, 8), (10200, 560, 8), (10200, 560, 32)])
+def test_device_resident_scans_equal_the_host_path(libekf, N, cap_extra, m):
+    """ekf_scan_device (inputs already in HBM, no read-back: the path bench.py's `value` times) against ekf_scan on the same
+    sequence, bit for bit: a burst the host never waits for (its bound of the map size only drifts upwards, past the
+    threads of the register-resident line loop at 10 200 landmarks), then paced scans with a pause in between (the
+    asynchronous snapshot of the device state lands and tightens the bound), with lines that match nothing so that the
+    map really grows, then a burst again."""
+    import time
+    import torch
+    from slam_ros_b200 import EkfFilter
+    steps = 36
+    scn = sc.map_scenario(N, steps, m=m, seed=17, stride=m + 3)
+    for s in (3, 9, 20, 21, 30):
+        scn["z"][s][1, 1] += 6.0 + 0.01 * s                         # one new landmark in each of these scans
+    f = EkfFilter(capacity_lines=N + cap_extra)                     # device-resident inputs
+    g = EkfFilter(capacity_lines=N + cap_extra)                     # host buffers
+    for x in (f, g):
+        x.scan(np.zeros(3), scn["seed_z"], scn["seed_R"])
+    dev = torch.device("cuda:0")
+    d_u = torch.tensor(scn["u"], dtype=torch.float64, device=dev)
+    d_z = torch.tensor(scn["z"], dtype=torch.float64, device=dev)
+    d_R = torch.tensor(scn["R"], dtype=torch.float64, device=dev)
+    d_j = torch.full((steps, m), -7, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for s in range(steps):
+        f.scan_device(d_u[s].data_ptr(), m, d_z[s].data_ptr(), d_R[s].data_ptr(), d_j[s].data_ptr())
+        if 12 <= s < 24:
+            time.sleep(0.02)                                        # paced: the snapshots land
+    f.sync()
+    j_dev = d_j.cpu().numpy()
+    for s in range(steps):
+        rc, j, pose = g.scan(scn["u"][s], scn["z"][s], scn["R"][s])
+        assert rc == 0 and np.array_equal(j, j_dev[s]), "step %d" % s
+    assert f.lines == g.lines == N + 5
+    assert np.array_equal(f.pose, g.pose) and f.cov_stats() == g.cov_stats()
+    assert np.array_equal(f.download_y(), g.download_y())
+    nl = 3 + 2 * g.lines
+    for (r0, c0) in [(0, 0), (0, nl - 64), (nl - 64, nl - 64), (1000, 5000)]:
+        assert np.array_equal(f.download_block(r0, c0, 64, 64), g.download_block(r0, c0, 64, 64)), (r0, c0)
+
+
 def test_overlapped_pipeline_with_changing_line_counts(libekf):
     """Scans of 8 / 32 / 64 / 16 / 40 lines in turn on a map whose capacity (10 752 lines) makes the line loop of the
     longer scans take 21 SMs instead of 20 (one thread per landmark of the capacity): the sweep in flight was sized for
