@@ -326,7 +326,10 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
 #ifdef EKFB_FULL_PASS
   const int qs = nl;
 #else
-  const int qs = min(nl, max(3, (int)(0.7071f * (float)nl) | 1));
+#ifndef EKFB_SPLIT
+#define EKFB_SPLIT 0.7071f
+#endif
+  const int qs = min(nl, max(3, (int)(EKFB_SPLIT * (float)nl) | 1));
 #endif
   int np0 = 0, np1 = 0, last_h = 1;
   bool have_new = false;                                     /* match nmatch-1: hot part pending too */
