@@ -86,7 +86,7 @@ def test_cpp_line_extractor_feeds_robot(libekf):
         ref, m = lo.extract(S["scans"][s])
         assert n == m
         assert np.abs(rows[:, :2] - ref[:, :2]).max() < 1e-10
-        assert (np.abs(rows[:, [2, 5]] - ref[:, [2, 5]]) / ref[:, [2, 5]]).max() < 1e-4
+        assert (np.abs(rows[:, [2, 5]] - ref[:, [2, 5]]) / ref[:, [2, 5]]).max() < 2e-6
         assert np.abs(rows[:, 6:] - ref[:, 6:]).max() < 1e-8
         assert np.isfinite(pose).all() and pose[3] >= 9
     assert k == out.size

@@ -3,7 +3,9 @@ itself bitwise equal to the reference's own lineFitting.cpp) and the golden vect
 
 Tolerances (floating point; the kernel evaluates the fit's pair sums in closed form and reduces in parallel):
   number of lines and their order: exact;  (alfa, r): 1e-10 absolute;  lineInterval end points: 1e-8;
-  C_AR: 1e-4 relative -- the reference's own forward differences (eps = 1e-6) carry ~1e-7 relative rounding noise."""
+  C_AR: 2e-6 relative -- the reference's own forward differences (eps = 1e-6) carry ~1e-7 relative rounding noise; the
+  worst of 11 578 entries over the golden payloads and 240 room scans is 2.2e-7 (scripts/lx_tolerance_probe.py); 2e-5 for
+  the deliberately messy payloads (3 cm of range noise, outliers: worst 5.4e-6)."""
 import os
 
 import numpy as np
@@ -15,7 +17,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lines_literal.npz")
 
 
-def _compare(rows, n, ref, m, what):
+def _compare(rows, n, ref, m, what, car_tol=2e-6):
     assert n == m, "%s: %d lines vs %d" % (what, n, m)
     if n == 0:
         return
@@ -26,7 +28,7 @@ def _compare(rows, n, ref, m, what):
     assert (rows[:, 3] == 0).all() and (rows[:, 4] == 0).all()
     for c in (2, 5):
         rel = np.abs(rows[:, c] - ref[:, c]) / np.maximum(np.abs(ref[:, c]), 1e-300)
-        assert rel.max() < 1e-4, (what, c, rel.max())
+        assert rel.max() < car_tol, (what, c, rel.max())
     # end points: a degenerate segment (duplicated beams: first == last point) gives NaN in the reference too
     assert np.array_equal(np.isnan(rows[:, 6:]), np.isnan(ref[:, 6:])), what
     da = np.abs(rows[:, [6, 8]] - ref[:, [6, 8]])
@@ -111,7 +113,7 @@ def test_messy_payloads(libekf):
         else:
             p = p[::rng.integers(2, 6)]
         rows, n = lx.extract(p); ref, m = lo.extract(p)
-        _compare(rows, n, ref, m, "payload %d (kind %d)" % (t, kind))
+        _compare(rows, n, ref, m, "payload %d (kind %d)" % (t, kind), car_tol=2e-5)   # 3 cm of range noise: worst 5.4e-6
 
 
 @pytest.mark.parametrize("beams,step_deg", [(1440, 0.25), (2880, 0.125), (4096, 360.0 / 4096)])
