@@ -5,7 +5,7 @@ Tolerances (floating point; the kernel evaluates the fit's pair sums in closed f
   number of lines and their order: exact;  (alfa, r): 1e-10 absolute;  lineInterval end points: 1e-8;
   C_AR: 2e-6 relative -- the reference's own forward differences (eps = 1e-6) carry ~1e-7 relative rounding noise; the
   worst of 11 578 entries over the golden payloads and 240 room scans is 2.2e-7 (scripts/lx_tolerance_probe.py); 2e-5 for
-  the deliberately messy payloads (3 cm of range noise, outliers: worst 5.4e-6)."""
+  the deliberately messy payloads (3 cm of range noise, outliers: worst 5.4e-6) and the dense scanners (worst 4.8e-6)."""
 import os
 
 import numpy as np
@@ -127,7 +127,7 @@ def test_dense_scanners(libekf, beams, step_deg):
     for pose in ((0.3, -0.2, 0.1), (-1.0, 0.8, 2.0)):
         p = sc.room_scan(pose, beams=beams, range_sigma=2e-3, rng=rng, step_deg=step_deg)
         rows, n = lx.extract(p); ref, m = lo.extract(p)
-        _compare(rows, n, ref, m, "%d beams at %s" % (beams, pose))
+        _compare(rows, n, ref, m, "%d beams at %s" % (beams, pose), car_tol=2e-5)   # hundreds of points per leaf: worst 4.8e-6
         assert n >= 15
 
 
