@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_parity.py -m gpu -q -x -k "batch or monte" ) > gpurun_out/r2_mc_tests_v17.log 2>&1; head -3 gpurun_out/r2_mc_tests_v17.log
+timeout 300 python bench.py --workload mc --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/r2_mc_v17.json 2> gpurun_out/r2_mc_v17.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2_mc_v17.json').read().strip().split('\n')[-1]); print('mc value',d['value'],'e2e',d['e2e']['value'])"
+timeout 300 python bench.py --workload mc --mc-per-gpu 512 --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/r2_mc_v17_512.json 2> gpurun_out/r2_mc_v17_512.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2_mc_v17_512.json').read().strip().split('\n')[-1]); print('mc 512 filters value',d['value'],'e2e',d['e2e']['value'])"

@@ -43,6 +43,8 @@ struct EkfBatchState {
 struct EkfBatchGeom {
   double2* scratch;         /* [B][4][n]: the pending gains of filters that run off chip */
   unsigned* sm_turn;        /* [256]: per SM, CTAs started there so far -- deals the association warp round-robin over the schedulers */
+  EkfBatchState* st_out;    /* [B] or NULL: this launch's copy of the filters' records (the pipelined host path reads it back while the
+                               next step's kernel already runs on the records themselves) */
   int B, cap, n, headroom;
   double gate, enc_noise, gate_d2max;
   long long pstride;        /* doubles per filter in the packed covariance array (even: 16-byte aligned filters) */
@@ -609,6 +611,11 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     st->L = L; st->pose[0] = ps0; st->pose[1] = ps1; st->pose[2] = ps2;
     st->sticky = s_sticky;                        /* status reports this scan only */
     st->resets += resets;
+    if (g.st_out) {
+      EkfBatchState o;
+      o.pose[0] = ps0; o.pose[1] = ps1; o.pose[2] = ps2; o.L = L; o.sticky = s_sticky; o.resets = st->resets; o.pad = 0;
+      g.st_out[f] = o;
+    }
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   /* the shared-memory source has been read: the CTA may go */
   }
   BT_MARK(7);
@@ -648,7 +655,9 @@ struct ekf_batch {
   double* d_in[2]; double* h_in[2];       /* [u (3B) | z (2 m B) | R (4 m B)] */
   int* d_jout[2]; int* h_jout[2];
   EkfBatchState* h_sts[2];
-  cudaEvent_t ev_in[2], ev_done[2];
+  EkfBatchState* d_sts[2];          /* per-slot copy of the records as the slot's kernel left them */
+  cudaStream_t dstream;             /* read-backs of the pipelined host path (run under the next step's kernel) */
+  cudaEvent_t ev_in[2], ev_done[2], ev_kernel[2];
   int slot_m[2];
   int head, inflight;               /* oldest submitted slot, submitted-but-not-collected steps (0..2) */
   EkfBatchState* h_st;
@@ -698,6 +707,7 @@ int batch_ensure_m(ekf_batch* b, int m) {
   if (b->inflight) { snprintf(b->err, sizeof b->err, "a scan with more lines than any before (%d) while steps are in flight: collect them first", m); return EKF_ESTATE; }
   CUB(cudaStreamSynchronize(b->stream));
   CUB(cudaStreamSynchronize(b->cstream));
+  CUB(cudaStreamSynchronize(b->dstream));
   b->max_m = 0;                       /* until every buffer below exists, the next call must come back here */
   const size_t B = b->g.B;
   for (int k = 0; k < 2; ++k) {
@@ -714,7 +724,7 @@ int batch_ensure_m(ekf_batch* b, int m) {
   return EKF_OK;
 }
 
-int batch_launch(ekf_batch* b, const double* d_u, int m, const double* d_z, const double* d_R, int* d_jout) {
+int batch_launch(ekf_batch* b, const double* d_u, int m, const double* d_z, const double* d_R, int* d_jout, EkfBatchState* d_st_out = 0) {
   int ns = batch_ns(b);
   while (ns > 3 && (size_t)batch_layout(ns, b->g.n, b->g.cap, m).bytes > kBatchSmemMax) ns -= 4;   /* very large maps: partly off chip */
   const size_t smem = (size_t)batch_layout(ns, b->g.n, b->g.cap, m).bytes;
@@ -724,7 +734,9 @@ int batch_launch(ekf_batch* b, const double* d_u, int m, const double* d_z, cons
     CUB(cudaFuncSetAttribute(k_batch_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     b->smem_set = smem;
   }
-  k_batch_scan<<<b->g.B, EKFB_THREADS, smem, b->stream>>>(b->g, ns, b->d_y, b->d_P, b->d_st, d_u, d_z, d_R, m, d_jout);
+  EkfBatchGeom gl = b->g;
+  gl.st_out = d_st_out;
+  k_batch_scan<<<gl.B, EKFB_THREADS, smem, b->stream>>>(gl, ns, b->d_y, b->d_P, b->d_st, d_u, d_z, d_R, m, d_jout);
   CUB(cudaGetLastError());
   b->L_exact = 0;
   return EKF_OK;
@@ -770,11 +782,14 @@ int ekf_batch_create(ekf_batch** out, const ekf_config* cfg, int n_filters) {
   { const char* e = getenv("EKF_BATCH_NS"); b->ns_forced = e ? atoi(e) : 0; if (b->ns_forced < 0) b->ns_forced = 0; if (b->ns_forced > 0 && b->ns_forced < 3) b->ns_forced = 3; }
   CUB(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   CUB(cudaStreamCreateWithFlags(&b->cstream, cudaStreamNonBlocking));
+  CUB(cudaStreamCreateWithFlags(&b->dstream, cudaStreamNonBlocking));
   const size_t B = g.B;
   for (int k = 0; k < 2; ++k) {
     CUB(cudaEventCreateWithFlags(&b->ev_in[k], cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&b->ev_done[k], cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&b->ev_kernel[k], cudaEventDisableTiming));
     CUB(cudaMallocHost(&b->h_sts[k], B * sizeof(EkfBatchState)));
+    CUB(cudaMalloc(&b->d_sts[k], B * sizeof(EkfBatchState)));
   }
   CUB(cudaMalloc(&b->d_y, B * (size_t)g.ystride * sizeof(double)));
   CUB(cudaMalloc(&b->d_P, B * (size_t)g.pstride * sizeof(double)));
@@ -803,15 +818,19 @@ int ekf_batch_destroy(ekf_batch* b) {
   cudaSetDevice(b->cfg.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   if (b->cstream) cudaStreamSynchronize(b->cstream);
+  if (b->dstream) cudaStreamSynchronize(b->dstream);
   cudaFree(b->d_y); cudaFree(b->d_P); cudaFree(b->d_st); cudaFree(b->d_scratch); cudaFree(b->d_sm_turn);
   for (int k = 0; k < 2; ++k) {
     cudaFree(b->d_in[k]); cudaFree(b->d_jout[k]); cudaFreeHost(b->h_in[k]); cudaFreeHost(b->h_jout[k]); cudaFreeHost(b->h_sts[k]);
     if (b->ev_in[k]) cudaEventDestroy(b->ev_in[k]);
     if (b->ev_done[k]) cudaEventDestroy(b->ev_done[k]);
+    if (b->ev_kernel[k]) cudaEventDestroy(b->ev_kernel[k]);
+    cudaFree(b->d_sts[k]);
   }
   cudaFreeHost(b->h_st); cudaFreeHost(b->h_P);
   if (b->stream) cudaStreamDestroy(b->stream);
   if (b->cstream) cudaStreamDestroy(b->cstream);
+  if (b->dstream) cudaStreamDestroy(b->dstream);
   delete b;
   return EKF_OK;
 }
@@ -846,11 +865,15 @@ int ekf_batch_submit(ekf_batch* b, const double* u, int m, const double* z, cons
   CUB(cudaMemcpyAsync(b->d_in[k], h, total * sizeof(double), cudaMemcpyHostToDevice, b->cstream));
   CUB(cudaEventRecord(b->ev_in[k], b->cstream));
   CUB(cudaStreamWaitEvent(b->stream, b->ev_in[k], 0));
-  rc = batch_launch(b, b->d_in[k], m, b->d_in[k] + 3 * B, b->d_in[k] + 3 * B + 2 * (size_t)m * B, b->d_jout[k]);
+  rc = batch_launch(b, b->d_in[k], m, b->d_in[k] + 3 * B, b->d_in[k] + 3 * B + 2 * (size_t)m * B, b->d_jout[k], b->d_sts[k]);
   if (rc) return rc;
-  if (m > 0) CUB(cudaMemcpyAsync(b->h_jout[k], b->d_jout[k], (size_t)m * B * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  CUB(cudaMemcpyAsync(b->h_sts[k], b->d_st, B * sizeof(EkfBatchState), cudaMemcpyDeviceToHost, b->stream));
-  CUB(cudaEventRecord(b->ev_done[k], b->stream));
+  /* the matches and the slot's copy of the records travel back on a stream of their own: the next step's kernel follows
+   * this one directly instead of waiting for the read-back */
+  CUB(cudaEventRecord(b->ev_kernel[k], b->stream));
+  CUB(cudaStreamWaitEvent(b->dstream, b->ev_kernel[k], 0));
+  if (m > 0) CUB(cudaMemcpyAsync(b->h_jout[k], b->d_jout[k], (size_t)m * B * sizeof(int), cudaMemcpyDeviceToHost, b->dstream));
+  CUB(cudaMemcpyAsync(b->h_sts[k], b->d_sts[k], B * sizeof(EkfBatchState), cudaMemcpyDeviceToHost, b->dstream));
+  CUB(cudaEventRecord(b->ev_done[k], b->dstream));
   b->slot_m[k] = m;
   b->inflight += 1;
   return EKF_OK;
