@@ -223,6 +223,12 @@ int ekf_lx_extract(ekf_lx* lx, int n_pairs, const float* data, int* n_lines, dou
 int ekf_lx_extract_device(ekf_lx* lx, int n_pairs, const float* d_data, const double** d_z, const double** d_R,
                           const int** d_count);
 int ekf_lx_sync(ekf_lx* lx);
+/* The consumers after the filter.  lineprovider/main.cpp:60-84 (Transform): the two end points of every
+ * line of the LAST extraction, from the robot frame to the world frame with the filter's pose (x, y, theta) -- what the
+ * `lines_1` topic carries, 4 floats (x0, y0, x1, y1) per line; astar/main.cpp:44-73 (lines_cb) takes those floats times
+ * 100 as the planner's obstacle segments in centimetres: scale = 100 (a float product, as there), scale = 1 for `lines_1`
+ * itself.  *n_lines = lines of the last extraction; at most max_out_lines are written. */
+int ekf_lx_world_segments(ekf_lx* lx, const double pose[3], double scale, float* out, int max_out_lines, int* n_lines);
 
 const char* ekf_version(void);
 

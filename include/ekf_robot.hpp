@@ -188,6 +188,19 @@ class LineExtractor {
     return n;
   }
 
+  /* lineprovider/main.cpp:60-84 (Transform) for the lines of the last extract(): appends 4 floats per line (x0, y0, x1, y1,
+   * world frame) to `data` -- the `lines_1` message; scale = 100 gives the planner's centimetres (astar/main.cpp:44-73).
+   * Returns the number of lines. */
+  int worldSegments(double x, double y, double theta, std::vector<float>& data, double scale = 1.0) {
+    const double pose[3] = {x, y, theta};
+    std::vector<float> seg(4 * (size_t)max_lines_);
+    int n = 0;
+    const int rc = ekf_lx_world_segments(lx_, pose, scale, seg.data(), max_lines_, &n);
+    if (rc != EKF_OK) throw std::runtime_error(std::string("libekfcuda: ") + ekf_lx_last_error(lx_));
+    data.insert(data.end(), seg.begin(), seg.begin() + 4 * (size_t)n);
+    return n;
+  }
+
  private:
   ekf_lx* lx_;
   int max_lines_;

@@ -334,3 +334,27 @@ class LiteralLineExtraction:
 
     def extract(self, payload, max_lines=128):
         return _extract(self._lib.ref_extract_lines, payload, max_lines)
+
+
+class LineProviderTransform:
+    """The reference's own end-point transform: lineprovider/main.cpp's Transform() (lines 60-84) compiled unmodified into
+    oracle/_ref/libslamlineprov.so (oracle/lineprov_harness.cpp).  Test infrastructure."""
+    PATH = os.path.join(_HERE, "_ref", "libslamlineprov.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        self._lib = C.CDLL(self.PATH, mode=C.RTLD_LOCAL)
+        self._lib.lp_transform.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_float)]
+
+    def transform(self, intervals, pose):
+        """intervals: (n, 4) = (alfa0, r0, alfa1, r1) per line; pose = (x, y, theta).  Returns (n, 4) float32."""
+        iv = np.ascontiguousarray(np.asarray(intervals, dtype=np.float64).reshape(-1, 4))
+        ps = np.ascontiguousarray(np.asarray(pose, dtype=np.float64).reshape(3))
+        out = np.zeros((iv.shape[0], 4), dtype=np.float32)
+        k = self._lib.lp_transform(iv.shape[0], iv.ctypes.data_as(C.POINTER(C.c_double)), ps.ctypes.data_as(C.POINTER(C.c_double)),
+                                   out.ctypes.data_as(C.POINTER(C.c_float)))
+        assert k == 4 * iv.shape[0]
+        return out

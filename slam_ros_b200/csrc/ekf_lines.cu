@@ -466,6 +466,31 @@ __global__ void __launch_bounds__(LX_PREP_THREADS) k_lx_finish(LxBuffers b, int 
   if (t == 0) *b.count = total;
 }
 
+/* lineprovider/main.cpp:60-84 (Transform): the two end points of every line of the last extraction from the robot frame
+ * to the world frame, ex = (cos theta, sin theta), ey = (cos, sin)(theta + PI/2) with the reference's truncated PI
+ * (lineFitting.h:12) and its wrap at M_PI, p = ex p.x + ey p.y + pose, every product and sum rounded on its own as the
+ * reference's Vec2 operators do; then astar/main.cpp:44-73 (lines_cb): the planner takes the FLOATS of the `lines_1`
+ * message times 100 (centimetres) -- a float product.  One thread per line; out: 4 floats per line. */
+__global__ void k_lx_world(LxBuffers b, int max_lines, double px, double py, double theta, float scale, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(*b.count, max_lines);
+  if (i >= n) return;
+  const double exx = cos(theta), exy = sin(theta);
+  double t = theta + 3.14159265 / 2;
+  t = t > LX_MPI ? t - 2.0 * LX_MPI : t;
+  const double eyx = cos(t), eyy = sin(t);
+  const double* o = b.out + 10 * i;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double a = o[6 + 2 * k], r = o[7 + 2 * k];
+    const double fx = __dmul_rn(cos(a), r), fy = __dmul_rn(sin(a), r);              /* polar2descart, lineFitting.cpp:170-176 */
+    const double wx = __dadd_rn(__dadd_rn(__dmul_rn(exx, fx), __dmul_rn(eyx, fy)), px);
+    const double wy = __dadd_rn(__dadd_rn(__dmul_rn(exy, fx), __dmul_rn(eyy, fy)), py);
+    out[4 * i + 2 * k] = __fmul_rn((float)wx, scale);
+    out[4 * i + 2 * k + 1] = __fmul_rn((float)wy, scale);
+  }
+}
+
 }  // namespace
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -478,6 +503,7 @@ struct ekf_lx {
   LxBuffers b;
   float* d_data; float* h_data;
   double* h_out; int* h_count;
+  float* d_seg; float* h_seg;         /* world-frame end points of the last extraction's lines (ekf_lx_world_segments) */
   long long launches;
   char err[256];
 };
@@ -520,6 +546,8 @@ int ekf_lx_create(ekf_lx** out, int device, int max_lines) {
   LXCU(cudaMalloc(&lx->b.count, sizeof(int)));
   LXCU(cudaMallocHost(&lx->h_out, 10 * (size_t)max_lines * sizeof(double)));
   LXCU(cudaMallocHost(&lx->h_count, sizeof(int)));
+  LXCU(cudaMalloc(&lx->d_seg, 4 * (size_t)max_lines * sizeof(float)));
+  LXCU(cudaMallocHost(&lx->h_seg, 4 * (size_t)max_lines * sizeof(float)));
   lx->b.data = lx->d_data;
   LXCU(cudaFuncSetAttribute(k_lx_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmem));
   LXCU(cudaFuncSetAttribute(k_lx_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegSmem));
@@ -533,7 +561,7 @@ int ekf_lx_destroy(ekf_lx* lx) {
   if (lx->stream) cudaStreamSynchronize(lx->stream);
   cudaFree(lx->d_data); cudaFreeHost(lx->h_data); cudaFree(lx->b.a); cudaFree(lx->b.seg); cudaFree(lx->b.leaf);
   cudaFree(lx->b.out); cudaFree(lx->b.z); cudaFree(lx->b.R); cudaFree(lx->b.count);
-  cudaFreeHost(lx->h_out); cudaFreeHost(lx->h_count);
+  cudaFreeHost(lx->h_out); cudaFreeHost(lx->h_count); cudaFree(lx->d_seg); cudaFreeHost(lx->h_seg);
   if (lx->stream) cudaStreamDestroy(lx->stream);
   delete lx;
   return EKF_OK;
@@ -578,6 +606,22 @@ int ekf_lx_extract_device(ekf_lx* lx, int n_pairs, const float* d_data, const do
   if (d_z) *d_z = lx->b.z;
   if (d_R) *d_R = lx->b.R;
   if (d_count) *d_count = lx->b.count;
+  return EKF_OK;
+}
+
+int ekf_lx_world_segments(ekf_lx* lx, const double pose[3], double scale, float* out, int max_out_lines, int* n_lines) {
+  if (!lx || !pose || !out || max_out_lines < 0 || !n_lines) return EKF_EINVAL;
+  LXCU(cudaSetDevice(lx->device));
+  k_lx_world<<<(lx->max_lines + 127) / 128, 128, 0, lx->stream>>>(lx->b, lx->max_lines, pose[0], pose[1], pose[2], (float)scale, lx->d_seg);
+  LXCU(cudaGetLastError());
+  lx->launches += 1;
+  LXCU(cudaMemcpyAsync(lx->h_count, lx->b.count, sizeof(int), cudaMemcpyDeviceToHost, lx->stream));
+  LXCU(cudaMemcpyAsync(lx->h_seg, lx->d_seg, 4 * (size_t)lx->max_lines * sizeof(float), cudaMemcpyDeviceToHost, lx->stream));
+  LXCU(cudaStreamSynchronize(lx->stream));
+  int n = *lx->h_count < lx->max_lines ? *lx->h_count : lx->max_lines;
+  *n_lines = n;
+  if (n > max_out_lines) n = max_out_lines;
+  if (n > 0) memcpy(out, lx->h_seg, 4 * (size_t)n * sizeof(float));
   return EKF_OK;
 }
 

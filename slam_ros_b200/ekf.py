@@ -48,7 +48,7 @@ SYMBOLS = [
     "ekf_download_block", "ekf_cov_stats", "ekf_profile_enable", "ekf_profile_read", "ekf_profile_read_lines", "ekf_timer_start", "ekf_timer_stop", "ekf_sweep_probe",
     "ekf_nccl_unique_id", "ekf_create_sharded", "ekf_shard_ipc_handle", "ekf_shard_connect", "ekf_shard_use_fused", "ekf_batch_create", "ekf_batch_destroy", "ekf_batch_scan",
     "ekf_batch_submit", "ekf_batch_collect", "ekf_batch_scan_device", "ekf_batch_sync", "ekf_batch_download", "ekf_batch_last_error", "ekf_version",
-    "ekf_lx_create", "ekf_lx_destroy", "ekf_lx_last_error", "ekf_lx_extract", "ekf_lx_extract_device", "ekf_lx_sync",
+    "ekf_lx_create", "ekf_lx_destroy", "ekf_lx_last_error", "ekf_lx_extract", "ekf_lx_extract_device", "ekf_lx_sync", "ekf_lx_world_segments",
 ]
 
 
@@ -112,6 +112,7 @@ def load_library():
     lib.ekf_lx_extract.argtypes = [vp, C.c_int, C.POINTER(C.c_float), _ip, _dp]
     lib.ekf_lx_extract_device.argtypes = [vp, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.ekf_lx_sync.argtypes = [vp]
+    lib.ekf_lx_world_segments.argtypes = [vp, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     _lib = lib
     return lib
 
@@ -464,6 +465,15 @@ class LineExtractor:
         self._check(self._lib.ekf_lx_extract_device(self._h, int(n_pairs), C.c_void_p(d_payload), C.byref(z), C.byref(R),
                                                     C.byref(cnt)), "ekf_lx_extract_device")
         return z.value, R.value, cnt.value
+
+    def world_segments(self, pose, scale=1.0):
+        """lineprovider's Transform (main.cpp:60-84) on the lines of the last extraction: (n, 4) float32 world-frame end
+        points (x0, y0, x1, y1), i.e. the `lines_1` message; scale=100: the planner's centimetres (astar/main.cpp:44-73)."""
+        ps = np.ascontiguousarray(np.asarray(pose, dtype=np.float64).reshape(3))
+        out = np.zeros((self.max_lines, 4), dtype=np.float32); n = C.c_int(0)
+        self._check(self._lib.ekf_lx_world_segments(self._h, _p(ps), float(scale), out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                    self.max_lines, C.byref(n)), "ekf_lx_world_segments")
+        return out[:min(n.value, self.max_lines)].copy()
 
     def sync(self):
         self._check(self._lib.ekf_lx_sync(self._h), "ekf_lx_sync")

@@ -43,6 +43,11 @@ int main(int argc, char** argv) {
     rover.localize(lines, (float*)0, enc);
     const double pose[4] = {rover.xPos, rover.yPos, rover.thetaPos, (double)rover.savedLineCount};
     std::fwrite(pose, sizeof(double), 4, fo);
+    /* the consumer after the filter (lineprovider/main.cpp:60-84): every extracted line's end points in the world frame */
+    std::vector<float> seg;
+    const int ns = extractor.worldSegments(rover.xPos, rover.yPos, rover.thetaPos, seg);
+    if (ns != n || seg.size() != 4 * (size_t)n) return 6;
+    for (size_t i = 0; i < seg.size(); ++i) { const double v = seg[i]; std::fwrite(&v, sizeof(double), 1, fo); }
   }
   std::fclose(fo);
   return 0;

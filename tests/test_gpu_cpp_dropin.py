@@ -89,4 +89,11 @@ def test_cpp_line_extractor_feeds_robot(libekf):
         assert (np.abs(rows[:, [2, 5]] - ref[:, [2, 5]]) / ref[:, [2, 5]]).max() < 2e-6
         assert np.abs(rows[:, 6:] - ref[:, 6:]).max() < 1e-8
         assert np.isfinite(pose).all() and pose[3] >= 9
+        seg = out[k:k + 4 * n].reshape(n, 4); k += 4 * n          # LineExtractor::worldSegments at the pose just published
+        ok = ~np.isnan(rows[:, 6:10]).any(axis=1)
+        th = pose[2]
+        for e in (0, 1):                                          # lineprovider/main.cpp:60-84 in numpy (float output: 1e-5)
+            px = rows[ok, 7 + 2 * e] * np.cos(rows[ok, 6 + 2 * e]); py = rows[ok, 7 + 2 * e] * np.sin(rows[ok, 6 + 2 * e])
+            wx = np.cos(th) * px - np.sin(th) * py + pose[0]; wy = np.sin(th) * px + np.cos(th) * py + pose[1]
+            assert np.abs(seg[ok, 2 * e] - wx).max() < 1e-5 and np.abs(seg[ok, 2 * e + 1] - wy).max() < 1e-5
     assert k == out.size

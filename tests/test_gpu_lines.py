@@ -137,3 +137,33 @@ def test_payload_larger_than_the_limit_is_rejected(libekf):
     with pytest.raises(EkfError) as e:
         LineExtractor().extract(np.ones((4097, 2), dtype=np.float32))
     assert e.value.code == EKF_EINVAL
+
+
+def test_world_segments_against_the_reference_lineprovider(libekf):
+    """the consumers after the filter.  ekf_lx_world_segments against the reference's own Transform()
+    (lineprovider/main.cpp:60-84, compiled unmodified: oracle/_ref/libslamlineprov.so) on the lines the device extracted,
+    for poses in every quadrant and across the wrap of theta + PI/2 at pi; scale = 100 is the planner's centimetres
+    (astar/main.cpp:44-73: the floats of the message times 100, a float product, so it must be exactly 100 x the scale-1
+    result rounded to float)."""
+    from slam_ros_b200 import LineExtractor
+    from oracle.oracle import LineProviderTransform
+    if not LineProviderTransform.available():
+        pytest.skip("oracle/_ref/libslamlineprov.so not built (needs /root/reference: make -C oracle ref)")
+    ref = LineProviderTransform()
+    lx = LineExtractor()
+    S = sc.room_scans(steps=12, seed=41, range_sigma=2e-3)
+    poses = [(0.0, 0.0, 0.0), (1.5, -2.25, 0.4), (-3.0, 0.7, 1.6), (0.2, 0.1, 1.5707963), (2.0, 2.0, 3.1), (-1.0, -1.0, -2.9),
+             (4.0, -0.5, -1.0), (0.3, 0.3, 2.0), (0.0, 5.0, 1.58), (7.0, 1.0, -0.01), (-2.0, 3.0, 3.14159), (1.0, 1.0, -3.14)]
+    total = 0
+    for s, pose in enumerate(poses):
+        rows, n = lx.extract(S["scans"][s])
+        seg = lx.world_segments(pose)
+        assert seg.shape == (n, 4) and n > 5
+        ok = ~np.isnan(rows[:, 6:10]).any(axis=1)                # degenerate segments carry NaN end points in the reference too
+        want = ref.transform(rows[ok, 6:10], pose)
+        assert np.abs(seg[ok] - want).max() <= 2e-6 * max(1.0, float(np.abs(want).max())), (s, np.abs(seg[ok] - want).max())
+        assert np.isnan(seg[~ok]).all()
+        cm = lx.world_segments(pose, scale=100.0)
+        assert np.array_equal(cm[ok], seg[ok] * np.float32(100.0))
+        total += int(ok.sum())
+    assert total > 100
