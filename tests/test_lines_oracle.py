@@ -77,3 +77,25 @@ def test_closed_form_of_the_pair_sums_used_on_the_device():
         ar = 0.5 * np.arctan2(-2.0 * (dx * dy).sum(), -((dx * dx).sum() - (dy * dy).sum()))
         rr = (np.cos(ar) * X.sum() + np.sin(ar) * Y.sum()) / p
         assert abs((ar * 180 / PI) * (PI / 180) - ref[0]) < 1e-11 and abs(rr - ref[1]) < 1e-11
+
+
+def test_lineprovider_transform_harness():
+    """The reference's own Transform() (lineprovider/main.cpp:60-84, oracle/_ref/libslamlineprov.so) behaves as the rotation
+    plus translation it is meant to be -- including its quirk: ey is built from theta + PI/2 with PI = 3.14159265
+    (lineFitting.h:12), so the frame is orthogonal only to ~2e-9 -- which pins the harness that the device path is
+    compared with (tests/test_gpu_lines.py)."""
+    import numpy as np
+    import pytest
+    from oracle.oracle import LineProviderTransform
+    if not LineProviderTransform.available():
+        pytest.skip("oracle/_ref/libslamlineprov.so not built (needs /root/reference: make -C oracle ref)")
+    ref = LineProviderTransform()
+    rng = np.random.default_rng(3)
+    iv = np.column_stack([rng.uniform(-3.1, 3.1, 200), rng.uniform(0.1, 9.0, 200), rng.uniform(-3.1, 3.1, 200), rng.uniform(0.1, 9.0, 200)])
+    for pose in ((0.0, 0.0, 0.0), (1.0, -2.0, 0.7), (-4.0, 3.0, 2.9), (0.5, 0.5, -3.0), (2.0, 1.0, 1.5707963)):
+        out = ref.transform(iv, pose)
+        th = pose[2]
+        for e in (0, 1):
+            px = iv[:, 1 + 2 * e] * np.cos(iv[:, 2 * e]); py = iv[:, 1 + 2 * e] * np.sin(iv[:, 2 * e])
+            wx = np.cos(th) * px - np.sin(th) * py + pose[0]; wy = np.sin(th) * px + np.cos(th) * py + pose[1]
+            assert np.abs(out[:, 2 * e] - wx).max() < 2e-6 and np.abs(out[:, 2 * e + 1] - wy).max() < 2e-6
