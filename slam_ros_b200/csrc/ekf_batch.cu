@@ -343,17 +343,23 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
       const double2* Kn = Ks + (size_t)((nmatch - 1) & 1) * kn;
       const double2* KSn = KSs + (size_t)((nmatch - 1) & 1) * kn;
       const double v0 = sG.v[0], v1 = sG.v[1];
+      const double2 ks0 = KSn[0], ks1 = KSn[1], ks2 = KSn[2];
       for (int q = tid; q < nl; q += nt) {
         double* c = Ps + tri(q);
         const double2 kq = Kn[q];
-        const int top = q < 3 ? q + 1 : 3;
-        for (int r = 0; r < top; ++r) c[r] = sub_rank2(c[r], KSn[r], kq);           /* :564-568, rows 0..2 */
         if (q >= 3) {
-          if (q & 1) c[q] = sub_rank2(c[q], KSn[q], kq);                             /* (a,a) */
-          else { c[q - 1] = sub_rank2(c[q - 1], KSn[q - 1], kq); c[q] = sub_rank2(c[q], KSn[q], kq); }   /* (a,b), (b,b) */
+          /* :564-568 on the column's hot entries -- rows 0..2 and the landmark's diagonal block -- all loaded first */
+          const bool odd = q & 1;                                                    /* q = a: (a,a); q = b: (a,b), (b,b) */
+          const double2 ksq = KSn[q], ksp = KSn[q - 1];
+          const double c0 = c[0], c1 = c[1], c2 = c[2], cq = c[q], cp = c[q - 1];
+          c[0] = sub_rank2(c0, ks0, kq); c[1] = sub_rank2(c1, ks1, kq); c[2] = sub_rank2(c2, ks2, kq);
+          c[q] = sub_rank2(cq, ksq, kq);
+          if (!odd) c[q - 1] = sub_rank2(cp, ksp, kq);
           double t = 0.0;                                                            /* :585-589  y += K * delta */
           axpy_skip(t, kq.x, v0); axpy_skip(t, kq.y, v1);
           ys[q] = add_rn(ys[q], t);
+        } else {
+          for (int r = 0; r <= q; ++r) c[r] = sub_rank2(c[r], KSn[r], kq);           /* the robot block's upper triangle */
         }
       }
       if (tid == nt - 1) {            /* the robot pose: on the last thread, which has no column of its own up to 127 rows */
