@@ -40,7 +40,7 @@ def stale():
 #   exact   -DEKF_EXACT_RANK2: the reference's four-rounding p - (ks.x k.x + ks.y k.y) instead of two FMAs
 #   timing  -DEKF_LINE_TIMING: %globaltimer stamps of the line loop's phases (scripts/line_timing*.py)
 #   mctiming -DEKFB_TIMING: clock64 phase totals of one Monte-Carlo filter's scan, printed by the kernel
-VARIANTS = {"exact": ["-DEKF_EXACT_RANK2"], "timing": ["-DEKF_LINE_TIMING"], "mctiming": ["-DEKFB_TIMING"], "mcfull": ["-DEKFB_FULL_PASS"]}
+VARIANTS = {"exact": ["-DEKF_EXACT_RANK2"], "timing": ["-DEKF_LINE_TIMING"], "mctiming": ["-DEKFB_TIMING"], "mcfull": ["-DEKFB_FULL_PASS"], "sepsincos": ["-DEKF_SEPARATE_SINCOS"]}
 
 
 def variant_path(name):

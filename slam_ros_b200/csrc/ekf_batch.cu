@@ -257,7 +257,8 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   /* ---- prediction, Robot.cpp:130-258 ---- */
   const double u0 = u[0], u2 = u[2];
   const double ang = add_rn(pose2, __ddiv_rn(u2, 2.0));
-  const double ca = cos(ang), sa = sin(ang);
+  double ca, sa;
+  cos_sin(ang, ca, sa);
   const double F02 = mul_rn(-u0, sa), F12 = mul_rn(u0, ca);
   for (int q = 3 + tid; q < nl; q += nt) {                            /* :242 rows 0,1 */
     double* c = Ps + tri(q);
@@ -546,7 +547,8 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
     double alfa = zs[2 * i], rr = zs[2 * i + 1];
     rr = add_rn(rr, add_rn(mul_rn(ps0, cos(alfa)), mul_rn(ps1, sin(alfa))));          /* :792 (Q8) */
     alfa = add_rn(alfa, ps2);                                                       /* :793 */
-    const double cw = cos(alfa), sw = sin(alfa);
+    double cw, sw;
+    cos_sin(alfa, cw, sw);
     /* a new column lives on chip while it fits the carve-up, else straight in the filter's HBM copy (write-mostly:
      * only its rows 0..2 are read again, by the columns appended after it in this scan) */
     double* c0 = ((on_chip && l < ns) ? Psm : Pf) + tri(l);

@@ -82,7 +82,8 @@ __device__ __forceinline__ void predict_body(const EkfGeom& g, const EkfBuffers&
   const double x0 = x[0], x1 = x[1], x2 = x[2];
   const double u0 = u[0], u2 = u[2];
   const double ang = add_rn(x2, __ddiv_rn(u2, 2.0));
-  const double ca = cos(ang), sa = sin(ang);
+  double ca, sa;
+  cos_sin(ang, ca, sa);
   const double F02 = mul_rn(-u0, sa), F12 = mul_rn(u0, ca);               /* :157, :160 */
   const int nl = 3 + 2 * st->L;
   double* t0p = b.top; double* t1p = b.top + g.ld; const double* t2p = b.top + 2 * (size_t)g.ld;
@@ -1577,7 +1578,8 @@ __global__ void __launch_bounds__(512) k_end_scan_a(EkfGeom g, EkfBuffers b, con
     const int l = 3 + 2 * (L + e);
     r = add_rn(r, add_rn(mul_rn(s_pose[0], cos(alfa)), mul_rn(s_pose[1], sin(alfa))));   /* :792 (Q8) */
     alfa = add_rn(alfa, s_pose[2]);                                                 /* :793 */
-    const double cw = cos(alfa), sw = sin(alfa);
+    double cw, sw;
+    cos_sin(alfa, cw, sw);
     const double Gx[2][3] = {{0.0, 0.0, 1.0}, {cw, sw, 0.0}};
     const double Gl[2][2] = {{1.0, 0.0}, {sub_rn(mul_rn(s_y01[1], cw), mul_rn(s_y01[0], sw)), 1.0}};   /* :797-798 */
     normalize_radian(alfa);                                                       /* :801 */
