@@ -210,6 +210,7 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   __shared__ int s_best, s_sticky, s_gw;
   __shared__ int s_cand[32];                                 /* survivors of the pre-test, in index order */
   __shared__ double s_xpre[3];
+  __shared__ double s_M[6];                                   /* Fu Q Fu' (upper triangle, packed by columns) */
   __shared__ Gate sG;
 
   const int tid = threadIdx.x, nt = EKFB_THREADS, lane = tid & 31, warp = tid >> 5;
@@ -249,17 +250,41 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
   /* the scan's lines travel to shared memory under the bulk copies: a gate then starts from a 29-cycle load instead of an
    * L2 / HBM round trip at the head of every line's dependent chain */
   for (int k = tid; k < 6 * m; k += nt) zs[k] = (k < 2 * m) ? z[k] : R[k - 2 * m];
-  __syncthreads();
-  b_mbar_wait(&s_bar, 0);
-  BT_MARK(0);
-
-  const int gw = s_gw;
-  /* ---- prediction, Robot.cpp:130-258 ---- */
+  /* ---- prediction, Robot.cpp:130-258: everything that does not need the covariance -- the
+   * trigonometry, Fu Q Fu' (:180-218, :250-258), x_pre -- is computed while the bulk copies are in flight ---- */
   const double u0 = u[0], u2 = u[2];
   const double ang = add_rn(pose2, __ddiv_rn(u2, 2.0));
   double ca, sa;
   cos_sin(ang, ca, sa);
   const double F02 = mul_rn(-u0, sa), F12 = mul_rn(u0, ca);
+  if (tid == 0) {
+    const double Fu[3][3] = {{ca, 0.0, __ddiv_rn(mul_rn(-u0, sa), 2.0)},
+                             {sa, 1.0, __ddiv_rn(mul_rn(u0, ca), 2.0)},
+                             {0.0, 0.0, 1.0}};
+    const double qf = add_rn(__ddiv_rn(-1.0, add_rn(1.0, fabs(u0))), 1.0);
+    const double Q[3] = {mul_rn(g.enc_noise, qf), mul_rn(mul_rn(2.0, g.enc_noise), qf), mul_rn(g.enc_noise, qf)};
+    double FQ[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < 3; ++k)
+      for (int i = 0; i < 3; ++i) {
+        const double t = mul_rn(1.0, Fu[i][k]);
+        if (t != 0.0)
+          for (int j = 0; j < 3; ++j) FQ[i][j] = add_rn(FQ[i][j], mul_rn(t, (j == k) ? Q[k] : 0.0));
+      }
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) {
+        double t = 0.0;
+        for (int k = 0; k < 3; ++k) t = add_rn(t, mul_rn(FQ[i][k], Fu[j][k]));
+        s_M[tri(j) + i] = add_rn(0.0, mul_rn(1.0, t));                /* added to the predicted 3x3 block below */
+      }
+    s_xpre[0] = add_rn(pose0, mul_rn(u0, ca));
+    s_xpre[1] = add_rn(pose1, mul_rn(u0, sa));
+    s_xpre[2] = add_rn(pose2, u2);
+  }
+  __syncthreads();
+  b_mbar_wait(&s_bar, 0);
+  BT_MARK(0);
+
+  const int gw = s_gw;
   for (int q = 3 + tid; q < nl; q += nt) {                            /* :242 rows 0,1 */
     double* c = Ps + tri(q);
     const double p2 = c[2];
@@ -281,27 +306,8 @@ __device__ __forceinline__ void batch_scan_body(const EkfBatchGeom& g, const int
       double c1 = 0.0; c1 = add_rn(c1, mul_rn(T[i][1], 1.0)); c1 = add_rn(c1, mul_rn(T[i][2], F12));
       Pn[i][0] = add_rn(0.0, c0); Pn[i][1] = add_rn(0.0, c1); Pn[i][2] = T[i][2];
     }
-    const double Fu[3][3] = {{ca, 0.0, __ddiv_rn(mul_rn(-u0, sa), 2.0)},
-                             {sa, 1.0, __ddiv_rn(mul_rn(u0, ca), 2.0)},
-                             {0.0, 0.0, 1.0}};
-    const double qf = add_rn(__ddiv_rn(-1.0, add_rn(1.0, fabs(u0))), 1.0);
-    const double Q[3] = {mul_rn(g.enc_noise, qf), mul_rn(mul_rn(2.0, g.enc_noise), qf), mul_rn(g.enc_noise, qf)};
-    double FQ[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = 0; k < 3; ++k)
-      for (int i = 0; i < 3; ++i) {
-        const double t = mul_rn(1.0, Fu[i][k]);
-        if (t != 0.0)
-          for (int j = 0; j < 3; ++j) FQ[i][j] = add_rn(FQ[i][j], mul_rn(t, (j == k) ? Q[k] : 0.0));
-      }
     for (int i = 0; i < 3; ++i)
-      for (int j = i; j < 3; ++j) {
-        double t = 0.0;
-        for (int k = 0; k < 3; ++k) t = add_rn(t, mul_rn(FQ[i][k], Fu[j][k]));
-        Ps[tri(j) + i] = add_rn(Pn[i][j], add_rn(0.0, mul_rn(1.0, t)));
-      }
-    s_xpre[0] = add_rn(pose0, mul_rn(u0, ca));
-    s_xpre[1] = add_rn(pose1, mul_rn(u0, sa));
-    s_xpre[2] = add_rn(pose2, u2);
+      for (int j = i; j < 3; ++j) Ps[tri(j) + i] = add_rn(Pn[i][j], s_M[tri(j) + i]);
   }
   __syncthreads();
 
